@@ -1,0 +1,461 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the MSDeformAttn hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W          (N>1: launched by torch.distributed.run)
+    python bench.py --impl reference ...                   (the reference's CPU path on the host cores)
+
+One "step" = one pass of the hot path over one batch: Injector (n_levels=3) forward+backward and
+Extractor (n_levels=1) forward+backward at the ViT-Adapter shape named in `config.workload`
+(BASELINE.json configs[1]: ViT-Adapter-B, 512x512, 16 images per GPU, fp32 by default).
+metric = sampled points per second (Gsamples/s), pts = N*Lq*M*L*P, whole job over all GPUs.
+
+Printed: ONE JSON line on stdout (rank 0). Keys follow the driver contract plus `roofline`,
+`cpu_baseline`, `e2e`, `clocks`, `gpu_launches`, and informational `kernels` / `ref_cuda`.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+# ---------------------------------------------------------------------------------------------------
+# workloads. (M, D) per variant; levels derived from the image side.
+# ---------------------------------------------------------------------------------------------------
+VARIANTS = {
+    # name: (heads, channels/head, image side, default images per GPU)
+    'B': (12, 32, 512, 16),    # ViT-Adapter-B  (upernet_deit_adapter_base_512_160k_ade20k.py:14,21,23)
+    'S': (6, 64, 512, 16),     # ViT-Adapter-S
+    'T': (6, 32, 512, 16),     # ViT-Adapter-T
+    'L': (16, 32, 896, 1),     # ViT-Adapter-L as configured by the reference (deform_ratio 0.5 -> 32 ch)
+    'L64': (16, 64, 896, 1),   # ViT-Adapter-L as BASELINE.json words it (16 x 64)
+    'HTC': (16, 32, 1024, 1),  # HTC++ inference shape (21 504 value tokens)
+}
+P = 4
+
+
+def call_shapes(variant, batch):
+    """The two operator calls of one adapter interaction: (name, N, M, D, Lq, level shapes)."""
+    M, D, side, _ = VARIANTS[variant]
+    l8, l16, l32 = side // 8, side // 16, side // 32
+    inj = ('injector', batch, M, D, l16 * l16, [(l8, l8), (l16, l16), (l32, l32)])
+    ext = ('extractor', batch, M, D, l8 * l8 + l16 * l16 + l32 * l32, [(l16, l16)])
+    return [inj, ext]
+
+
+def n_points(N, M, Lq, L):
+    return N * Lq * M * L * P
+
+
+def algorithmic_bytes(N, M, D, Lq, shapes, esize):
+    """every tensor touched once; loc/aw fp32 (12 B per point)."""
+    S = sum(h * w for h, w in shapes)
+    L = len(shapes)
+    b_val = esize * N * S * M * D
+    b_out = esize * N * Lq * M * D
+    b_la = 12 * n_points(N, M, Lq, L)
+    return {'fwd': b_val + b_la + b_out, 'bwd': b_out + 2 * b_val + 2 * b_la}
+
+
+def adapter_inputs(name, N, M, D, Lq, shapes, seed, dtype):
+    """Distribution A of SURVEY.md §8(d): reference-point grid (adapter_modules.py:13-25) + the module's
+    initial offset ring (ms_deform_attn.py:66-75) + N(0, 1 px) noise; softmax(N(0,1)) weights; value and
+    grad_out ~ N(0,1). Drawn on the CPU generator, like detection/ops/test.py."""
+    import math
+    g = torch.Generator().manual_seed(seed)
+    shapes_t = torch.as_tensor(shapes, dtype=torch.long)
+    L = len(shapes)
+    S = int(shapes_t.prod(1).sum())
+    lsi = torch.cat((shapes_t.new_zeros((1,)), shapes_t.prod(1).cumsum(0)[:-1]))
+    # reference points: the query grid(s) — injector queries are the H/16 grid, extractor queries the 3 levels
+    if name == 'injector':
+        grids = [shapes[1]]
+    else:
+        h, w = shapes[0]
+        grids = [(2 * h, 2 * w), (h, w), (h // 2, w // 2)]
+    refs = []
+    for (h, w) in grids:
+        ys = (torch.arange(h, dtype=torch.float32) + 0.5) / h
+        xs = (torch.arange(w, dtype=torch.float32) + 0.5) / w
+        yy, xx = torch.meshgrid(ys, xs, indexing='ij')
+        refs.append(torch.stack([xx.reshape(-1), yy.reshape(-1)], -1))
+    ref = torch.cat(refs, 0)
+    assert ref.shape[0] == Lq
+    theta = torch.arange(M, dtype=torch.float32) * (2.0 * math.pi / M)
+    ray = torch.stack([theta.cos(), theta.sin()], -1)
+    ray = ray / ray.abs().max(-1, keepdim=True)[0]
+    off = ray.view(1, 1, M, 1, 1, 2) * torch.arange(1, P + 1, dtype=torch.float32).view(1, 1, 1, 1, P, 1)
+    off = off + torch.randn(N, Lq, M, L, P, 2, generator=g)
+    wh = torch.stack([shapes_t[:, 1], shapes_t[:, 0]], -1).float()
+    loc = (ref.view(1, Lq, 1, 1, 1, 2) + off / wh.view(1, 1, 1, L, 1, 2)).contiguous()
+    aw = torch.softmax(torch.randn(N, Lq, M, L * P, generator=g), -1).view(N, Lq, M, L, P).contiguous()
+    value = torch.randn(N, S, M, D, generator=g).to(dtype)
+    grad_out = torch.randn(N, Lq, M * D, generator=g).to(dtype)
+    return dict(value=value, shapes=shapes_t, lsi=lsi, loc=loc, aw=aw, grad_out=grad_out)
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region (B200_PROFILING.md recipe)
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.samples = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.FIELDS, '--format=csv,noheader,nounits',
+                 '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        inside = [s for (t, s) in self.samples if t0 <= t <= t1 + 0.1] or [s for (_, s) in self.samples]
+        mhz, mx, reasons = [], None, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for s in inside:
+            parts = [x.strip() for x in s.split(',')]
+            if len(parts) < 6:
+                continue
+            try:
+                mhz.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return {'sm_mhz': statistics.median(mhz) if mhz else None, 'sm_max_mhz': mx,
+                'reasons': sorted(reasons), 'samples': len(mhz)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the reference's CPU path (oracle/core_pytorch.py restates ms_deform_attn_core_pytorch)
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_pass(variant, sample_batch, threads, steps, warmup):
+    """Time fwd+bwd of Injector+Extractor on the host cores for `sample_batch` images. Returns
+    (Gsamples/s, seconds per step, points per step)."""
+    from oracle import core_pytorch  # the ONLY place bench.py executes oracle/ code
+    torch.set_num_threads(threads)
+    calls = []
+    pts = 0
+    for i, (name, N, M, D, Lq, shapes) in enumerate(call_shapes(variant, sample_batch)):
+        calls.append(adapter_inputs(name, N, M, D, Lq, shapes, seed=i, dtype=torch.float32))
+        pts += n_points(N, M, Lq, len(shapes))
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        for c in calls:
+            core_pytorch.forward_backward(c['value'], c['shapes'], c['loc'], c['aw'], c['grad_out'])
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    mean = sum(times) / len(times)
+    return pts / mean / 1e9, mean, pts
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    variant = args.variant
+    _, _, _, default_batch = VARIANTS[variant]
+    batch = args.batch or default_batch
+    sample_batch = min(batch, 2)
+    threads = os.cpu_count() or 1
+    value, sec, pts = cpu_reference_pass(variant, sample_batch, threads, args.steps, max(1, args.warmup))
+    M, D, side, _ = VARIANTS[variant]
+    line = {
+        'impl': 'reference', 'metric': 'msdeformattn_fwd_bwd_gsamples_per_s', 'value': value, 'unit': 'Gsamples/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': max(1, args.warmup), 'ms_per_step': sec * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(variant, batch, 'f32'),
+        'cpu_baseline': {'value': value, 'unit': 'Gsamples/s', 'cores': threads, 'kind': 'port',
+                         'sample': '%d of %d images per step (BASELINE cfg 1 shape), Injector+Extractor fwd+bwd via '
+                                   'oracle/core_pytorch.py (restatement of ms_deform_attn_core_pytorch, F.grid_sample '
+                                   '+ autograd), torch %d threads' % (sample_batch, batch, threads)},
+        'e2e': {'value': value, 'unit': 'Gsamples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(variant, batch, dtype):
+    M, D, side, _ = VARIANTS[variant]
+    return {
+        'workload': 'ViT-Adapter-%s MSDeformAttn fwd+bwd: Injector(n_levels=3)+Extractor(n_levels=1), %dx%d, '
+                    '%d images per GPU, %d heads x %d ch, 4 points' % (variant, side, side, batch, M, D),
+        'variant': variant, 'image': side, 'batch_per_gpu': batch, 'heads': M, 'channels': D, 'points': P,
+        'io_dtype': dtype, 'inputs': 'distribution A (adapter reference grid + init ring + N(0,1px))',
+        'l2': 'working set per step is larger than L2 (no explicit flush)', 'parallelism': 'batch-sharded, no collective',
+    }
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    import vit_adapter_b200 as vab
+    from vit_adapter_b200 import _cabi
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device: the product path has no CPU fallback '
+                           '(use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    _cabi.load()
+
+    variant = args.variant
+    M, D, side, default_batch = VARIANTS[variant]
+    batch = args.batch or default_batch
+    dtype = {'f32': torch.float32, 'bf16': torch.bfloat16}[args.dtype]
+    esize = 4 if dtype == torch.float32 else 2
+
+    # ---- inputs: host (pinned) master copies + device-resident copies -----------------------------------
+    calls = []
+    pts_step = 0
+    for i, (name, N, Mh, Dh, Lq, shapes) in enumerate(call_shapes(variant, batch)):
+        host = adapter_inputs(name, N, Mh, Dh, Lq, shapes, seed=1000 * rank + i, dtype=dtype)
+        pinned = {k: v.pin_memory() for k, v in host.items()}
+        devt = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+        calls.append({'name': name, 'dims': (N, Mh, Dh, Lq, shapes), 'host': pinned, 'dev': devt,
+                      'pts': n_points(N, Mh, Lq, len(shapes)), 'bytes': algorithmic_bytes(N, Mh, Dh, Lq, shapes, esize)})
+        pts_step += calls[-1]['pts']
+    torch.cuda.synchronize()
+
+    def step_device(events=None):
+        """One step on device-resident inputs, straight through the C-ABI binding."""
+        for ci, c in enumerate(calls):
+            d = c['dev']
+            if events is not None:
+                events[ci][0].record()
+            _cabi.forward(d['value'], d['shapes'], d['lsi'], d['loc'], d['aw'], 64)
+            if events is not None:
+                events[ci][1].record()
+            _cabi.backward(d['value'], d['shapes'], d['lsi'], d['loc'], d['aw'], d['grad_out'], 64)
+            if events is not None:
+                events[ci][2].record()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up -------------------------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+
+    # ---- timed region: exactly K steps, CUDA events, per-kernel events inside ------------------------------
+    K = args.steps
+    ev = [[[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in calls] for _ in range(K)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = _cabi.launch_count()
+    barrier()
+    t0 = time.time()
+    e0.record()
+    for k in range(K):
+        step_device(ev[k])
+    e1.record()
+    barrier()
+    t1 = time.time()
+    launches = _cabi.launch_count() - launches0
+    elapsed_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop(t0, t1) if sampler else None
+
+    # per-kernel average durations (fwd: events 0->1, bwd: events 1->2; bwd includes its grad_value zero-fill)
+    kernels = []
+    for ci, c in enumerate(calls):
+        fwd = sum(ev[k][ci][0].elapsed_time(ev[k][ci][1]) for k in range(K)) / K
+        bwd = sum(ev[k][ci][1].elapsed_time(ev[k][ci][2]) for k in range(K)) / K
+        kernels.append({'name': c['name'] + '_fwd', 'ms': fwd, 'alg_bytes': c['bytes']['fwd'], 'pts': c['pts']})
+        kernels.append({'name': c['name'] + '_bwd', 'ms': bwd, 'alg_bytes': c['bytes']['bwd'], 'pts': c['pts']})
+
+    # ---- max over ranks -----------------------------------------------------------------------------------
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / K
+    value = world * pts_step / (ms_per_step * 1e-3) / 1e9
+
+    # ---- e2e: public API (MSDeformAttnFunction.apply + autograd) from pinned HOST buffers -------------------
+    def step_e2e():
+        res = []
+        for c in calls:
+            h = c['host']
+            v = h['value'].to(dev, non_blocking=True).requires_grad_()
+            loc = h['loc'].to(dev, non_blocking=True).requires_grad_()
+            aw = h['aw'].to(dev, non_blocking=True).requires_grad_()
+            go = h['grad_out'].to(dev, non_blocking=True)
+            sh = h['shapes'].to(dev, non_blocking=True)
+            ls = h['lsi'].to(dev, non_blocking=True)
+            out = vab.MSDeformAttnFunction.apply(v, sh, ls, loc, aw, 64)
+            out.backward(go)
+            res.append([out.detach().to('cpu', non_blocking=True), v.grad.to('cpu', non_blocking=True),
+                        loc.grad.to('cpu', non_blocking=True), aw.grad.to('cpu', non_blocking=True)])
+        return res
+
+    h2d = sum(sum(c['host'][k].numel() * c['host'][k].element_size() for k in ('value', 'loc', 'aw', 'grad_out', 'shapes', 'lsi'))
+              for c in calls)
+    d2h = sum(c['host']['grad_out'].numel() * esize + c['host']['value'].numel() * esize + c['host']['loc'].numel() * 4
+              + c['host']['aw'].numel() * 4 for c in calls)
+    e2e_steps = max(2, min(K, 5))
+    step_e2e()
+    barrier()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    for _ in range(e2e_steps):
+        step_e2e()
+    a1.record()
+    barrier()
+    e2e_ms = a0.elapsed_time(a1)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * pts_step / (e2e_ms / e2e_steps * 1e-3) / 1e9
+
+    # ---- reference CUDA kernel on the same GPU, same inputs (fp32 only; informational) ---------------------
+    ref_cuda = None
+    if rank == 0 and not args.no_ref_cuda:
+        try:
+            from oracle import refcuda
+            if refcuda.available():
+                f32 = [{k: (v.float() if v.is_floating_point() else v) for k, v in c['dev'].items()} for c in calls]
+
+                def step_ref():
+                    for d in f32:
+                        refcuda.forward(d['value'], d['shapes'], d['lsi'], d['loc'], d['aw'])
+                        refcuda.backward(d['value'], d['shapes'], d['lsi'], d['loc'], d['aw'], d['grad_out'])
+                for _ in range(2):
+                    step_ref()
+                torch.cuda.synchronize()
+                r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                nref = max(2, min(K, 10))
+                r0.record()
+                for _ in range(nref):
+                    step_ref()
+                r1.record()
+                torch.cuda.synchronize()
+                rms = r0.elapsed_time(r1) / nref
+                ref_cuda = {'what': "reference's own CUDA kernels (ms_deform_im2col_cuda.cuh) recompiled for sm_100a, fp32, "
+                                    'same inputs, 1 GPU', 'ms_per_step': rms, 'value': pts_step / (rms * 1e-3) / 1e9,
+                            'unit': 'Gsamples/s'}
+                del f32
+        except Exception as e:  # informational only
+            ref_cuda = {'error': repr(e)}
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------------------
+    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(peaks_path):
+        peak = float(json.load(open(peaks_path))['hbm_gbs'])
+        peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    else:
+        peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
+    dom = max(kernels, key=lambda k: k['ms'])
+    for k in kernels:
+        k['gbs'] = k['alg_bytes'] / (k['ms'] * 1e-3) / 1e9
+        k['frac'] = k['gbs'] / peak
+        k['gsamples_s'] = k['pts'] / (k['ms'] * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get('%s_%s_%s' % (variant, args.dtype, dom['name']))
+        except Exception:
+            traffic = None
+    roofline = {'bound': 'hbm', 'kernel': dom['name'], 'achieved': dom['gbs'], 'peak': peak, 'unit': 'GB/s',
+                'frac': dom['frac'], 'traffic': traffic, 'peak_source': peak_src,
+                'step_frac': sum(k['alg_bytes'] for k in kernels) / (sum(k['ms'] for k in kernels) * 1e-3) / 1e9 / peak}
+
+    # ---- CPU baseline (rank 0, N=1 only; bounded sample) ----------------------------------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sb = min(batch, 2)
+        cv, csec, cpts = cpu_reference_pass(variant, sb, threads, steps=3, warmup=1)
+        cpu_baseline = {'value': cv, 'unit': 'Gsamples/s', 'cores': threads, 'kind': 'port',
+                        'sample': '%d of %d images, Injector+Extractor fwd+bwd, oracle/core_pytorch.py (restatement of the '
+                                  "reference's ms_deform_attn_core_pytorch), %.0f ms per pass" % (sb, batch, csec * 1e3)}
+
+    if rank == 0:
+        line = {
+            'metric': 'msdeformattn_fwd_bwd_gsamples_per_s', 'value': value, 'unit': 'Gsamples/s', 'n_gpus': world,
+            'steps': K, 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
+            'config': workload_config(variant, batch, args.dtype),
+            'roofline': roofline, 'cpu_baseline': cpu_baseline,
+            'e2e': {'value': e2e_value, 'unit': 'Gsamples/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'ms_per_step': e2e_ms / e2e_steps, 'api': 'MSDeformAttnFunction.apply + autograd backward, pinned host buffers'},
+            'gpu_launches': launches, 'clocks': clocks, 'kernels': kernels, 'ref_cuda': ref_cuda,
+            'points_per_step_per_gpu': pts_step,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--variant', default='B', choices=sorted(VARIANTS))
+    ap.add_argument('--dtype', default='f32', choices=['f32', 'bf16'])
+    ap.add_argument('--batch', type=int, default=0, help='images per GPU (0 = the variant default)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-ref-cuda', action='store_true')
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == 'ours':
+        args.warmup = 3
+    if args.impl == 'reference':
+        return run_reference_arm(args)  # each step: a bounded 2-image sample, ~0.2-1 s of CPU work
+    return run_ours(args)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

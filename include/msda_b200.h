@@ -1,0 +1,145 @@
+/*
+ * msda_b200.h — C ABI of the B200-native multi-scale deformable attention core.
+ *
+ * This header is the drop-in boundary for the hot path of ViT-Adapter's MSDeformAttn.
+ * It replaces the pybind11 surface of the reference extension
+ *   detection/ops/src/vision.cpp:13-16            (ms_deform_attn_forward / ms_deform_attn_backward)
+ *   detection/ops/src/ms_deform_attn.h:20-61      (device dispatch)
+ *   detection/ops/src/cuda/ms_deform_attn_cuda.cu:20-80, :83-153   (host wrappers)
+ * with plain pointers + sizes: no torch / ATen types cross this boundary.
+ *
+ * Conventions
+ *   - All tensor pointers are DEVICE pointers to contiguous row-major storage.
+ *   - The library never allocates or frees tensor memory (the reference allocates with
+ *     at::zeros inside C++, ms_deform_attn_cuda.cu:54,121-123). The caller owns every buffer.
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous w.r.t. the host,
+ *     performs no host<->device synchronisation and no allocation, so it is CUDA-graph capturable.
+ *   - Return value: 0 on success, a negative MSDA_E_* code for argument errors, or a positive
+ *     cudaError_t for CUDA runtime/launch errors (the reference only printf()s launch errors,
+ *     ms_deform_im2col_cuda.cuh:948-952,1321-1325; here they are surfaced).
+ *     msda_last_error() returns a thread-local human-readable message for the last failure.
+ *   - Thread-safe and re-entrant; no global mutable state.
+ *
+ * Tensor layouts (identical to the reference, ms_deform_attn_func.py:20-33):
+ *   value              [N, S, M, D]        dtype T   (T = f32 | bf16 | f64)
+ *   spatial_shapes     [L, 2]  int64       (H_l, W_l)      -- on device, as in the reference
+ *   level_start_index  [L]     int64                         -- on device
+ *   sampling_loc       [N, Lq, M, L, P, 2] dtype F   (x, y) normalised to [0,1]
+ *   attn_weight        [N, Lq, M, L, P]    dtype F
+ *   out / grad_out     [N, Lq, M*D]        dtype T
+ *   grad_value         [N, S, M, D]        dtype T
+ *   grad_sampling_loc  like sampling_loc, grad_attn_weight like attn_weight (dtype F)
+ * where F = f32 for T in {f32, bf16} and F = f64 for T = f64.
+ */
+#ifndef MSDA_B200_H_
+#define MSDA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSDA_ABI_VERSION 1
+
+/* dtype of value / out / grad_out / grad_value */
+enum msda_dtype {
+  MSDA_F32 = 0,  /* loc/aw f32; the reference's production dtype (custom_fwd casts to fp32)   */
+  MSDA_BF16 = 1, /* loc/aw f32, fp32 accumulation; new capability (reference has no bf16 path) */
+  MSDA_F64 = 2   /* loc/aw f64; exists so the reference's fp64 gradcheck (ops/test.py:78-101) runs */
+};
+
+/* negative error codes */
+enum msda_error {
+  MSDA_OK = 0,
+  MSDA_E_NULL = -1,      /* a required pointer is NULL                                  */
+  MSDA_E_DIMS = -2,      /* a dimension is <= 0 or a product overflows int32            */
+  MSDA_E_DTYPE = -3,     /* unknown dtype                                               */
+  MSDA_E_ALIGN = -4,     /* pointer not aligned to the element size                     */
+  MSDA_E_LEVELS = -5,    /* more levels than MSDA_MAX_LEVELS                            */
+  MSDA_E_WORKSPACE = -6, /* workspace missing or too small (see msda_backward_workspace_bytes) */
+  MSDA_E_STEP = -7       /* batch not divisible by min(batch, im2col_step)              */
+};
+
+#define MSDA_MAX_LEVELS 16
+
+/* Problem dimensions — the 7 ints the reference host code extracts from the tensors
+ * (ms_deform_attn_cuda.cu:40-48). */
+typedef struct msda_dims {
+  int32_t batch;        /* N  */
+  int32_t spatial_size; /* S  = sum_l H_l*W_l */
+  int32_t num_heads;    /* M  */
+  int32_t channels;     /* D  (per head) */
+  int32_t num_levels;   /* L  */
+  int32_t num_query;    /* Lq */
+  int32_t num_point;    /* P  */
+} msda_dims;
+
+/* ABI version of the loaded library (== MSDA_ABI_VERSION it was built with). */
+int msda_abi_version(void);
+
+/* Thread-local message describing the last non-zero return on this thread ("" if none). */
+const char* msda_last_error(void);
+
+/* Same precondition the reference asserts (ms_deform_attn_cuda.cu:50-52): batch % min(batch, step) == 0.
+ * The step is otherwise ignored: one launch covers the whole batch. Returns 0 or MSDA_E_STEP. */
+int msda_check_im2col_step(int32_t batch, int32_t im2col_step);
+
+/* Forward: replaces ms_deform_attn_cuda_forward (ms_deform_attn_cuda.cu:20-80) and kernel
+ * ms_deformable_im2col_gpu_kernel (ms_deform_im2col_cuda.cuh:237-299).
+ * `out` is fully overwritten (no pre-zeroing needed). */
+int msda_forward(const msda_dims* dims, int dtype,
+                 const void* value,
+                 const int64_t* spatial_shapes,
+                 const int64_t* level_start_index,
+                 const void* sampling_loc,
+                 const void* attn_weight,
+                 void* out,
+                 void* stream);
+
+/* Bytes of scratch the backward needs for (dims, dtype); 0 when none is needed.
+ * (bf16 accumulates grad_value in an fp32 scratch of N*S*M*D floats.) */
+size_t msda_backward_workspace_bytes(const msda_dims* dims, int dtype);
+
+/* Backward: replaces ms_deform_attn_cuda_backward (ms_deform_attn_cuda.cu:83-153) and the col2im
+ * kernels (ms_deform_im2col_cuda.cuh:301-920).
+ * grad_value, grad_sampling_loc and grad_attn_weight are fully written by the call (grad_value is
+ * zero-filled on `stream` before the scatter; the caller does not pre-zero anything).
+ * `workspace` may be NULL when msda_backward_workspace_bytes() == 0. */
+int msda_backward(const msda_dims* dims, int dtype,
+                  const void* value,
+                  const int64_t* spatial_shapes,
+                  const int64_t* level_start_index,
+                  const void* sampling_loc,
+                  const void* attn_weight,
+                  const void* grad_out,
+                  void* grad_value,
+                  void* grad_sampling_loc,
+                  void* grad_attn_weight,
+                  void* workspace, size_t workspace_bytes,
+                  void* stream);
+
+/* Test hook: for every sampling point (N*Lq*M*L*P of them, same order as attn_weight) write
+ *   idx[4*i+0] = h_low, idx[4*i+1] = w_low,
+ *   idx[4*i+2] = corner-validity mask (bit k = corner k+1 is read; 0 = sample skipped),
+ *   idx[4*i+3] = element offset of corner (h_low, w_low) inside value[b] (token*M*D + m*D)
+ * computed by the SAME device routine the kernels use. f32 locations only.
+ * Pins the index / level-offset arithmetic of ms_deform_im2col_cuda.cuh:33-53,274-288. */
+int msda_debug_point_index(const msda_dims* dims,
+                           const int64_t* spatial_shapes,
+                           const int64_t* level_start_index,
+                           const float* sampling_loc,
+                           int32_t* idx,
+                           void* stream);
+
+/* Number of kernel launches (ours) issued through this library by the calling process so far. */
+uint64_t msda_launch_count(void);
+
+/* Tuning override for benchmarking: queries per CTA chunk (0 = built-in heuristic). */
+void msda_set_query_chunk(int32_t fwd_chunk, int32_t bwd_chunk);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSDA_B200_H_ */

@@ -1,0 +1,3 @@
+// Empty stand-in (see ../ATen.h).
+#pragma once
+#include <cuda_runtime.h>

@@ -1,0 +1,195 @@
+"""Generate the golden fixtures in tests/golden/ by running the REAL reference code.
+
+Run in the authoring container only (needs /root/reference):
+    python tests/golden/make_golden.py
+
+It imports, unmodified and from where they lie,
+  /root/reference/detection/ops/functions/ms_deform_attn_func.py   (ms_deform_attn_core_pytorch)
+  /root/reference/detection/ops/modules/ms_deform_attn.py          (MSDeformAttn)
+  /root/reference/detection/mmdet_custom/models/backbones/adapter_modules.py
+        (deform_inputs, Injector, Extractor, InteractionBlock)
+with two sys.modules stubs for packages absent here: the compiled
+`MultiScaleDeformableAttention` extension and `timm.models.layers.DropPath`; the reference's
+MSDeformAttnFunction is routed to its own pure-PyTorch core (the function the reference itself calls
+its debug/test oracle). Inputs AND outputs are stored, so the tests do not depend on torch's RNG.
+"""
+import importlib.util
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = '/root/reference'
+
+
+def load_reference():
+    warnings.simplefilter('ignore')
+    sys.modules['MultiScaleDeformableAttention'] = types.ModuleType('MultiScaleDeformableAttention')
+    timm = types.ModuleType('timm')
+    timm_models = types.ModuleType('timm.models')
+    timm_layers = types.ModuleType('timm.models.layers')
+
+    class DropPath(torch.nn.Module):  # identity at drop_prob = 0 / eval, which is all the fixtures use
+        def __init__(self, drop_prob=0.):
+            super().__init__()
+            self.drop_prob = drop_prob
+
+        def forward(self, x):
+            assert self.drop_prob == 0. or not self.training
+            return x
+
+    timm_layers.DropPath = DropPath
+    timm.models = timm_models
+    timm_models.layers = timm_layers
+    sys.modules.update({'timm': timm, 'timm.models': timm_models, 'timm.models.layers': timm_layers})
+    sys.path.insert(0, os.path.join(REF, 'detection'))
+    import ops.functions.ms_deform_attn_func as ref_func
+    import ops.modules.ms_deform_attn as ref_mod
+
+    class _CoreFunction:
+        @staticmethod
+        def apply(value, shapes, lsi, loc, aw, step):
+            return ref_func.ms_deform_attn_core_pytorch(value, shapes, loc, aw)
+
+    ref_mod.MSDeformAttnFunction = _CoreFunction
+    spec = importlib.util.spec_from_file_location(
+        'ref_adapter_modules',
+        os.path.join(REF, 'detection/mmdet_custom/models/backbones/adapter_modules.py'))
+    ref_adapter = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_adapter)
+    return ref_func, ref_mod, ref_adapter
+
+
+def level_start(shapes):
+    return torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+
+
+def op_case(ref_func, name, N, M, D, Lq, shapes, P, seed, dist):
+    """One operator-level fixture: inputs, fp64 + fp32 outputs, fp64 grads (autograd through the core)."""
+    torch.manual_seed(seed)
+    shapes = torch.as_tensor(shapes, dtype=torch.long)
+    L = shapes.shape[0]
+    S = int(shapes.prod(1).sum())
+    if dist == 'ref_test':  # detection/ops/test.py:28-33
+        value = torch.rand(N, S, M, D) * 0.01
+        loc = torch.rand(N, Lq, M, L, P, 2)
+        aw = torch.rand(N, Lq, M, L, P) + 1e-5
+        aw /= aw.sum(-1, keepdim=True).sum(-2, keepdim=True)
+    elif dist == 'edges':   # out-of-range samples, exact texel centres, 0 and 1 (every validity branch)
+        value = torch.randn(N, S, M, D)
+        loc = torch.rand(N, Lq, M, L, P, 2) * 1.2 - 0.1
+        flat = loc.view(-1, 2)
+        k = flat.shape[0]
+        W0 = float(shapes[0, 1])
+        flat[0::7] = (torch.randint(0, int(W0), (len(flat[0::7]), 2)).float() + 0.5) / W0
+        flat[1::11] = 0.0
+        flat[2::13] = 1.0
+        flat[3::17] = torch.tensor([0.5 / W0, 1.0 - 0.5 / W0])
+        assert k > 17
+        aw = torch.softmax(torch.randn(N, Lq, M, L * P), -1).view(N, Lq, M, L, P)
+    else:
+        raise ValueError(dist)
+    grad_out = torch.randn(N, Lq, M * D)
+    out32 = ref_func.ms_deform_attn_core_pytorch(value, shapes, loc, aw)
+    v = value.double().requires_grad_()
+    l = loc.double().requires_grad_()
+    a = aw.double().requires_grad_()
+    out64 = ref_func.ms_deform_attn_core_pytorch(v, shapes, l, a)
+    out64.backward(grad_out.double())
+    np.savez_compressed(
+        os.path.join(HERE, name + '.npz'),
+        value=value.numpy(), shapes=shapes.numpy(), lsi=level_start(shapes).numpy(), loc=loc.numpy(),
+        aw=aw.numpy(), grad_out=grad_out.numpy(), out_f32=out32.numpy(), out_f64=out64.detach().numpy(),
+        grad_value_f64=v.grad.numpy(), grad_loc_f64=l.grad.numpy(), grad_aw_f64=a.grad.numpy())
+    print(name, 'S=%d pts=%d' % (S, N * Lq * M * L * P))
+
+
+def module_case(ref_mod, name, d_model, n_levels, n_heads, n_points, ratio, N, Lq, shapes, seed, ref_dim=2):
+    torch.manual_seed(seed)
+    m = ref_mod.MSDeformAttn(d_model, n_levels, n_heads, n_points, ratio).double()
+    with torch.no_grad():  # move off the all-zero init so every parameter matters
+        for p in m.parameters():
+            p.add_(torch.randn_like(p) * 0.05)
+    shapes = torch.as_tensor(shapes, dtype=torch.long)
+    S = int(shapes.prod(1).sum())
+    query = torch.randn(N, Lq, d_model, dtype=torch.double)
+    feat = torch.randn(N, S, d_model, dtype=torch.double)
+    ref_pts = torch.rand(N, Lq, n_levels, ref_dim, dtype=torch.double)
+    if ref_dim == 4:
+        ref_pts[..., 2:] = ref_pts[..., 2:] * 0.3 + 0.05
+    mask = torch.zeros(N, S, dtype=torch.bool)
+    mask[:, -3:] = True
+    out = m(query, ref_pts, feat, shapes, level_start(shapes), mask)
+    out_nomask = m(query, ref_pts, feat, shapes, level_start(shapes), None)
+    arrays = {('sd.' + k): v.numpy() for k, v in m.state_dict().items()}
+    arrays.update(query=query.numpy(), feat=feat.numpy(), ref_pts=ref_pts.numpy(), shapes=shapes.numpy(),
+                  mask=mask.numpy(), out=out.detach().numpy(), out_nomask=out_nomask.detach().numpy(),
+                  cfg=np.array([d_model, n_levels, n_heads, n_points], dtype=np.int64), ratio=np.array(ratio))
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), **arrays)
+    print(name)
+
+
+def init_case(ref_mod, name):
+    """The reference's deterministic init of sampling_offsets.bias for the adapter head counts."""
+    arrays = {}
+    for (d, L, M, P) in [(384, 3, 6, 4), (768, 1, 12, 4), (1024, 3, 16, 4), (256, 4, 8, 4)]:
+        m = ref_mod.MSDeformAttn(d, L, M, P, 1.0)
+        arrays['bias_%d_%d_%d_%d' % (d, L, M, P)] = m.sampling_offsets.bias.detach().numpy()
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), **arrays)
+    print(name)
+
+
+def adapter_case(ref_adapter, name, dim, heads, ratio, H, W, N, seed):
+    """deform_inputs + one InteractionBlock (Injector -> [no ViT blocks] -> Extractor + 2 extra extractors)."""
+    torch.manual_seed(seed)
+    blk = ref_adapter.InteractionBlock(dim=dim, num_heads=heads, n_points=4, init_values=0.,
+                                       deform_ratio=ratio, extra_extractor=True, with_cffn=True,
+                                       cffn_ratio=0.25).double()
+    with torch.no_grad():
+        for p in blk.parameters():
+            p.add_(torch.randn_like(p) * 0.05)
+    img = torch.zeros(N, 3, H, W)
+    di1, di2 = ref_adapter.deform_inputs(img)
+    h, w = H // 16, W // 16
+    x = torch.randn(N, h * w, dim, dtype=torch.double)
+    c = torch.randn(N, (2 * h) * (2 * w) + h * w + (h // 2) * (w // 2), dim, dtype=torch.double)
+    di1d = [di1[0].double(), di1[1], di1[2]]
+    di2d = [di2[0].double(), di2[1], di2[2]]
+    xo, co = blk(x, c, [], di1d, di2d, h, w)
+    arrays = {('sd.' + k): v.numpy() for k, v in blk.state_dict().items()}
+    arrays.update(x=x.numpy(), c=c.numpy(), x_out=xo.detach().numpy(), c_out=co.detach().numpy(),
+                  ref1=di1[0].numpy(), shapes1=di1[1].numpy(), lsi1=di1[2].numpy(),
+                  ref2=di2[0].numpy(), shapes2=di2[1].numpy(), lsi2=di2[2].numpy(),
+                  cfg=np.array([dim, heads, H, W, N], dtype=np.int64), ratio=np.array(ratio))
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), **arrays)
+    print(name)
+
+
+def main():
+    ref_func, ref_mod, ref_adapter = load_reference()
+    # 1. the reference's own test fixture (detection/ops/test.py:16-37), seed 3 == SURVEY App. A.4 KAT
+    op_case(ref_func, 'op_kat_seed3', N=1, M=2, D=2, Lq=2, shapes=[(6, 4), (3, 2)], P=2, seed=3, dist='ref_test')
+    # 2. injector-like (L=3) and extractor-like (L=1) miniatures, with the edge distribution
+    op_case(ref_func, 'op_inj_edges', N=2, M=3, D=8, Lq=16, shapes=[(8, 8), (4, 4), (2, 2)], P=4, seed=11, dist='edges')
+    op_case(ref_func, 'op_ext_edges', N=2, M=3, D=8, Lq=84, shapes=[(4, 4)], P=4, seed=12, dist='edges')
+    # 3. non-square levels, odd channel count (generic kernel), ref-test distribution
+    op_case(ref_func, 'op_odd_d5', N=1, M=2, D=5, Lq=7, shapes=[(5, 3), (2, 7)], P=3, seed=13, dist='ref_test')
+    # 4. vector-kernel channel counts with the real head widths
+    op_case(ref_func, 'op_d32_edges', N=1, M=2, D=32, Lq=9, shapes=[(6, 6), (3, 3), (2, 2)], P=4, seed=14, dist='edges')
+    op_case(ref_func, 'op_d64_edges', N=1, M=2, D=64, Lq=9, shapes=[(5, 7)], P=4, seed=15, dist='edges')
+    # 5. module level
+    module_case(ref_mod, 'module_l3', d_model=32, n_levels=3, n_heads=4, n_points=4, ratio=1.0, N=2, Lq=10,
+                shapes=[(6, 6), (3, 3), (2, 2)], seed=21)
+    module_case(ref_mod, 'module_ratio_half_box', d_model=32, n_levels=2, n_heads=2, n_points=2, ratio=0.5, N=1,
+                Lq=6, shapes=[(4, 5), (2, 3)], seed=22, ref_dim=4)
+    init_case(ref_mod, 'module_init_bias')
+    # 6. adapter level
+    adapter_case(ref_adapter, 'adapter_block', dim=32, heads=4, ratio=0.5, H=64, W=96, N=2, seed=31)
+
+
+if __name__ == '__main__':
+    main()

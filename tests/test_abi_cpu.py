@@ -1,0 +1,86 @@
+"""CPU-side checks of the C-ABI boundary: the library loads, exports every symbol include/msda_b200.h
+declares, validates arguments without touching a GPU, and the product path has no CPU fallback."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+import vit_adapter_b200 as vab
+from vit_adapter_b200 import _cabi
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, 'include', 'msda_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(msda_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _cabi.load()
+    names = _declared_functions()
+    assert set(names) == set(_cabi.EXPORTS), (names, _cabi.EXPORTS)
+    for n in names:
+        assert getattr(lib, n) is not None
+    assert lib.msda_abi_version() == 1
+
+
+def test_library_has_no_torch_dependency():
+    import subprocess
+    out = subprocess.run(['ldd', _cabi.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
+    assert 'libtorch' not in out and 'libc10' not in out and 'libpython' not in out and 'libcudart' not in out
+
+
+def test_argument_validation_without_gpu():
+    lib = _cabi.load()
+    d = _cabi.MsdaDims(2, 84, 3, 8, 3, 16, 4)
+    assert lib.msda_forward(None, 0, None, None, None, None, None, None, None) == -1
+    assert lib.msda_forward(ctypes.byref(d), 0, None, None, None, None, None, None, None) == -1  # NULL tensors
+    assert b'NULL' in lib.msda_last_error()
+    assert lib.msda_forward(ctypes.byref(d), 9, None, None, None, None, None, None, None) == -3  # dtype
+    bad = _cabi.MsdaDims(2, 84, 3, 0, 3, 16, 4)
+    assert lib.msda_forward(ctypes.byref(bad), 0, None, None, None, None, None, None, None) == -2
+    many = _cabi.MsdaDims(2, 84, 3, 8, 17, 16, 4)
+    assert lib.msda_forward(ctypes.byref(many), 0, None, None, None, None, None, None, None) == -5
+    # workspace: only bf16 needs one (fp32 accumulator of grad_value)
+    assert lib.msda_backward_workspace_bytes(ctypes.byref(d), _cabi.MSDA_F32) == 0
+    assert lib.msda_backward_workspace_bytes(ctypes.byref(d), _cabi.MSDA_BF16) == 2 * 84 * 3 * 8 * 4
+    # im2col_step precondition of the reference (ms_deform_attn_cuda.cu:50-52)
+    assert lib.msda_check_im2col_step(16, 64) == 0
+    assert lib.msda_check_im2col_step(128, 64) == 0
+    assert lib.msda_check_im2col_step(96, 64) == -7
+    assert b'must divide' in lib.msda_last_error()
+
+
+def test_cpu_tensors_are_rejected_like_the_reference():
+    """ms_deform_attn.h:38 — AT_ERROR("Not implemented on the CPU"); there is no CPU fallback here either."""
+    value = torch.rand(1, 30, 2, 4)
+    shapes = torch.as_tensor([(6, 4), (3, 2)], dtype=torch.long)
+    lsi = torch.as_tensor([0, 24], dtype=torch.long)
+    loc = torch.rand(1, 2, 2, 2, 2, 2)
+    aw = torch.rand(1, 2, 2, 2, 2)
+    with pytest.raises(RuntimeError, match='CPU'):
+        vab.MSDeformAttnFunction.apply(value, shapes, lsi, loc, aw, 2)
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_cabi, '_lib', None)
+    monkeypatch.setattr(_cabi, 'LIB_PATH', '/nonexistent/libmsda_b200.so')
+    with pytest.raises(RuntimeError, match='no CPU'):
+        _cabi.load()
+
+
+def test_product_path_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under vit-adapter_b200/ or include/ may reference it."""
+    pkg = os.path.join(ROOT, 'vit-adapter_b200')
+    offenders = []
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.cpp', '.h')):
+                text = open(os.path.join(base, f), errors='ignore').read()
+                if re.search(r'^\s*(from|import)\s+oracle|oracle[./]|grid_sample', text, flags=re.M):
+                    offenders.append(os.path.join(base, f))
+    assert not offenders, offenders

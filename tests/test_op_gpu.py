@@ -1,0 +1,345 @@
+"""GPU parity tests of the CUDA path (called through the C-ABI via MSDeformAttnFunction / _cabi)
+against the oracles. Tolerances are the north star's: indices bit-exact; fp32 forward 1e-5 rel / 1e-6
+abs; fp32 gradients 1e-4 rel (atomic order); bf16 1e-2."""
+import pytest
+import torch
+
+from conftest import OP_CASES, load_golden, make_inputs
+from oracle import c_oracle, refcuda
+
+import vit_adapter_b200 as vab
+from vit_adapter_b200 import _cabi
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _cuda(d, dtype=None):
+    out = {}
+    for k, v in d.items():
+        if v.dtype in (torch.int64, torch.bool) or dtype is None or not v.is_floating_point():
+            out[k] = v.to(DEV)
+        else:
+            out[k] = v.to(DEV, dtype)
+    return out
+
+
+def _run(inp, dtype):
+    """forward + backward through the public autograd Function on the GPU."""
+    g = _cuda(inp)
+    value = g['value'].to(dtype).requires_grad_()
+    cdt = torch.float64 if dtype == torch.float64 else torch.float32
+    loc = g['loc'].to(cdt).requires_grad_()
+    aw = g['aw'].to(cdt).requires_grad_()
+    out = vab.MSDeformAttnFunction.apply(value, g['shapes'], g['lsi'], loc, aw, 64)
+    out.backward(g['grad_out'].to(dtype))
+    torch.cuda.synchronize()
+    return out.detach().cpu(), value.grad.cpu(), loc.grad.cpu(), aw.grad.cpu()
+
+
+def _scale(t):
+    return float(t.abs().max()) + 1e-30
+
+
+# ---------------------------------------------------------------------------------------------------
+# golden fixtures (outputs of the real reference)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('case', OP_CASES)
+def test_golden_f32(case):
+    g = load_golden(case)
+    out, gv, gl, ga = _run(g, torch.float32)
+    torch.testing.assert_close(out.double(), g['out_f64'], rtol=1e-5, atol=1e-6)
+    # gradients vs the fp32 C oracle (same fmaf coordinate arithmetic): 1e-4 relative
+    ogv, ogl, oga = c_oracle.backward(g['value'], g['shapes'], g['lsi'], g['loc'], g['aw'], g['grad_out'])
+    torch.testing.assert_close(gv, ogv, rtol=1e-4, atol=1e-4 * _scale(ogv))
+    torch.testing.assert_close(gl, ogl, rtol=1e-4, atol=1e-4 * _scale(ogl))
+    torch.testing.assert_close(ga, oga, rtol=1e-4, atol=1e-4 * _scale(oga))
+    # and vs the reference's fp64 autograd gradients (looser: fp32 vs fp64 arithmetic)
+    torch.testing.assert_close(gv.double(), g['grad_value_f64'], rtol=1e-4, atol=1e-4 * _scale(ogv))
+    torch.testing.assert_close(ga.double(), g['grad_aw_f64'], rtol=1e-4, atol=1e-4 * _scale(oga))
+
+
+@pytest.mark.parametrize('case', OP_CASES)
+def test_golden_f64(case):
+    """fp64 through the generic kernel: the reference's own fp64 tolerance (ops/test.py:43, allclose defaults)."""
+    g = load_golden(case)
+    out, gv, gl, ga = _run(g, torch.float64)
+    torch.testing.assert_close(out, g['out_f64'], rtol=1e-5, atol=1e-8)
+    torch.testing.assert_close(gv, g['grad_value_f64'], rtol=1e-9, atol=1e-11)
+    torch.testing.assert_close(gl, g['grad_loc_f64'], rtol=1e-8, atol=1e-9)
+    torch.testing.assert_close(ga, g['grad_aw_f64'], rtol=1e-9, atol=1e-11)
+
+
+@pytest.mark.parametrize('case', ['op_inj_edges', 'op_ext_edges', 'op_d32_edges', 'op_d64_edges', 'op_odd_d5'])
+def test_golden_bf16(case):
+    g = load_golden(case)
+    # oracle on the bf16-rounded value / grad_out, in fp32: isolates kernel error from input rounding
+    vq = g['value'].bfloat16().float()
+    goq = g['grad_out'].bfloat16().float()
+    want = c_oracle.forward(vq, g['shapes'], g['lsi'], g['loc'], g['aw'])
+    wgv, wgl, wga = c_oracle.backward(vq, g['shapes'], g['lsi'], g['loc'], g['aw'], goq)
+    g2 = dict(g)
+    out, gv, gl, ga = _run(g2, torch.bfloat16)
+    assert out.dtype == torch.bfloat16 and gv.dtype == torch.bfloat16
+    torch.testing.assert_close(out.float(), want, rtol=1e-2, atol=1e-2 * _scale(want))
+    torch.testing.assert_close(gv.float(), wgv, rtol=1e-2, atol=1e-2 * _scale(wgv))
+    torch.testing.assert_close(gl, wgl, rtol=1e-2, atol=1e-2 * _scale(wgl))
+    torch.testing.assert_close(ga, wga, rtol=1e-2, atol=1e-2 * _scale(wga))
+
+
+# ---------------------------------------------------------------------------------------------------
+# seeded synthetic shapes vs the C oracle (sizes the oracle finishes in seconds)
+# ---------------------------------------------------------------------------------------------------
+SHAPES = [
+    # name, N, M, D, Lq, shapes, P, dist
+    ('S-injector', 2, 6, 64, 256, [(32, 32), (16, 16), (8, 8)], 4, 'adapter'),
+    ('B-injector', 2, 12, 32, 256, [(32, 32), (16, 16), (8, 8)], 4, 'adapter'),
+    ('B-extractor', 2, 12, 32, 1344, [(16, 16)], 4, 'adapter'),
+    ('L-injector', 1, 16, 32, 196, [(28, 28), (14, 14), (7, 7)], 4, 'edges'),
+    ('L-d64', 1, 16, 64, 196, [(28, 28), (14, 14), (7, 7)], 4, 'uniform'),
+    ('ragged-levels', 3, 5, 32, 37, [(7, 9), (3, 4), (1, 1), (2, 5)], 3, 'edges'),
+    ('one-query', 1, 1, 32, 1, [(2, 2)], 1, 'edges'),
+    ('d8', 2, 4, 8, 50, [(9, 9), (5, 5)], 4, 'edges'),
+    ('d128', 1, 2, 128, 33, [(9, 9), (5, 5)], 4, 'uniform'),
+    ('d16-p8', 2, 8, 16, 45, [(12, 10)], 8, 'edges'),
+]
+
+
+@pytest.mark.parametrize('cfg', SHAPES, ids=[s[0] for s in SHAPES])
+def test_vs_c_oracle_f32(cfg):
+    _, N, M, D, Lq, shapes, P, dist = cfg
+    inp = make_inputs(N, M, D, Lq, shapes, P, seed=5, dist=dist)
+    out, gv, gl, ga = _run(inp, torch.float32)
+    want = c_oracle.forward(inp['value'], inp['shapes'], inp['lsi'], inp['loc'], inp['aw'])
+    wgv, wgl, wga = c_oracle.backward(inp['value'], inp['shapes'], inp['lsi'], inp['loc'], inp['aw'], inp['grad_out'])
+    torch.testing.assert_close(out, want, rtol=1e-5, atol=1e-6 * max(1.0, _scale(want)))
+    torch.testing.assert_close(gv, wgv, rtol=1e-4, atol=1e-4 * _scale(wgv))
+    torch.testing.assert_close(gl, wgl, rtol=1e-4, atol=1e-4 * _scale(wgl))
+    torch.testing.assert_close(ga, wga, rtol=1e-4, atol=1e-4 * _scale(wga))
+
+
+@pytest.mark.parametrize('cfg', SHAPES[:6], ids=[s[0] for s in SHAPES[:6]])
+def test_vs_c_oracle_bf16(cfg):
+    _, N, M, D, Lq, shapes, P, dist = cfg
+    inp = make_inputs(N, M, D, Lq, shapes, P, seed=6, dist=dist)
+    vq, goq = inp['value'].bfloat16().float(), inp['grad_out'].bfloat16().float()
+    out, gv, gl, ga = _run(inp, torch.bfloat16)
+    want = c_oracle.forward(vq, inp['shapes'], inp['lsi'], inp['loc'], inp['aw'])
+    wgv, wgl, wga = c_oracle.backward(vq, inp['shapes'], inp['lsi'], inp['loc'], inp['aw'], goq)
+    torch.testing.assert_close(out.float(), want, rtol=1e-2, atol=1e-2 * _scale(want))
+    torch.testing.assert_close(gv.float(), wgv, rtol=1e-2, atol=1e-2 * _scale(wgv))
+    torch.testing.assert_close(gl, wgl, rtol=1e-2, atol=1e-2 * _scale(wgl))
+    torch.testing.assert_close(ga, wga, rtol=1e-2, atol=1e-2 * _scale(wga))
+
+
+@pytest.mark.parametrize('D', [30, 32, 64, 71, 1025, 2048, 3096])
+def test_reference_channel_sweep(D):
+    """The channel counts the reference's own test sweeps to hit every backward branch (ops/test.py:108)."""
+    inp = make_inputs(1, 2, D, 2, [(6, 4), (3, 2)], 2, seed=3, dist='uniform')
+    out, gv, gl, ga = _run(inp, torch.float32)
+    want = c_oracle.forward(inp['value'], inp['shapes'], inp['lsi'], inp['loc'], inp['aw'])
+    wgv, wgl, wga = c_oracle.backward(inp['value'], inp['shapes'], inp['lsi'], inp['loc'], inp['aw'], inp['grad_out'])
+    torch.testing.assert_close(out, want, rtol=1e-5, atol=1e-6 * max(1.0, _scale(want)))
+    torch.testing.assert_close(gv, wgv, rtol=1e-4, atol=1e-4 * _scale(wgv))
+    torch.testing.assert_close(gl, wgl, rtol=1e-4, atol=1e-4 * _scale(wgl))
+    torch.testing.assert_close(ga, wga, rtol=1e-4, atol=1e-4 * _scale(wga))
+
+
+@pytest.mark.parametrize('D', [4, 30, 32])
+def test_gradcheck_f64(D):
+    """The reference's gradient test: torch.autograd.gradcheck in fp64 (ops/test.py:78-101)."""
+    inp = make_inputs(1, 2, D, 2, [(6, 4), (3, 2)], 2, seed=3, dist='uniform', dtype=torch.float64)
+    g = _cuda(inp)
+    value = (g['value'] * 0.01).requires_grad_()
+    loc = g['loc'].clone().requires_grad_()
+    aw = g['aw'].clone().requires_grad_()
+    assert torch.autograd.gradcheck(vab.MSDeformAttnFunction.apply, (value, g['shapes'], g['lsi'], loc, aw, 2))
+
+
+# ---------------------------------------------------------------------------------------------------
+# index / level-offset arithmetic: bit-exact
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('dist', ['uniform', 'edges', 'adapter'])
+def test_point_index_bit_exact(dist):
+    inp = make_inputs(2, 12, 32, 1024, [(64, 64), (32, 32), (16, 16)], 4, seed=9, dist=dist)
+    want = c_oracle.point_index(inp['shapes'], inp['lsi'], inp['loc'], 12, 32)
+    got = _cabi.debug_point_index(inp['shapes'].to(DEV), inp['lsi'].to(DEV), inp['loc'].to(DEV), 12, 32).cpu()
+    assert torch.equal(got, want)
+
+
+def test_point_index_fma_sensitive_locations():
+    """Locations where fmaf(loc,H,-0.5) and (loc*H)-0.5 floor differently: the kernels must take the fused
+    result (what nvcc emits for the reference)."""
+    H = 112
+    cand = torch.rand(4_000_000, generator=torch.Generator().manual_seed(1)) * 1.0
+    fused = torch.floor(torch.addcmul(torch.tensor(-0.5, dtype=torch.float64), cand.double(), torch.tensor(float(H), dtype=torch.float64)).float())
+    unfused = torch.floor((cand * H) - 0.5)
+    sel = cand[fused != unfused][:64]
+    if sel.numel() == 0:
+        pytest.skip('no fma-sensitive location found')
+    n = sel.numel()
+    loc = torch.stack([sel, sel], -1).view(1, n, 1, 1, 1, 2).contiguous()
+    shapes = torch.as_tensor([(H, H)], dtype=torch.long)
+    lsi = torch.zeros(1, dtype=torch.long)
+    want = c_oracle.point_index(shapes, lsi, loc, 1, 4)
+    got = _cabi.debug_point_index(shapes.to(DEV), lsi.to(DEV), loc.to(DEV), 1, 4).cpu()
+    assert torch.equal(got, want)
+    assert torch.equal(want[:, 0].float(), fused[fused != unfused][:64])
+
+
+# ---------------------------------------------------------------------------------------------------
+# the reference's own CUDA kernels (oracle/_ref, compiled from /root/reference) on identical inputs
+# ---------------------------------------------------------------------------------------------------
+needs_ref = pytest.mark.skipif(not refcuda.available(), reason='oracle/_ref not built')
+
+
+@needs_ref
+@pytest.mark.parametrize('cfg', SHAPES[:6], ids=[s[0] for s in SHAPES[:6]])
+def test_vs_reference_cuda_f32(cfg):
+    _, N, M, D, Lq, shapes, P, dist = cfg
+    inp = make_inputs(N, M, D, Lq, shapes, P, seed=7, dist=dist)
+    g = _cuda(inp)
+    out, gv, gl, ga = _run(inp, torch.float32)
+    rout = refcuda.forward(g['value'], g['shapes'], g['lsi'], g['loc'], g['aw'])
+    rgv, rgl, rga = refcuda.backward(g['value'], g['shapes'], g['lsi'], g['loc'], g['aw'], g['grad_out'])
+    torch.cuda.synchronize()
+    torch.testing.assert_close(out, rout.cpu(), rtol=1e-5, atol=1e-6 * max(1.0, _scale(rout)))
+    torch.testing.assert_close(gv, rgv.cpu(), rtol=1e-4, atol=1e-4 * _scale(rgv))
+    torch.testing.assert_close(gl, rgl.cpu(), rtol=1e-4, atol=1e-4 * _scale(rgl))
+    torch.testing.assert_close(ga, rga.cpu(), rtol=1e-4, atol=1e-4 * _scale(rga))
+
+
+@needs_ref
+def test_c_oracle_matches_reference_cuda():
+    """Pins the C restatement against the reference kernel itself (forward in fp32 and fp64)."""
+    inp = make_inputs(2, 3, 8, 40, [(8, 8), (4, 4), (2, 2)], 4, seed=8, dist='edges')
+    g = _cuda(inp)
+    rout = refcuda.forward(g['value'], g['shapes'], g['lsi'], g['loc'], g['aw']).cpu()
+    want = c_oracle.forward(inp['value'], inp['shapes'], inp['lsi'], inp['loc'], inp['aw'])
+    torch.testing.assert_close(rout, want, rtol=1e-6, atol=1e-6)
+    g64 = _cuda(inp, torch.float64)
+    rout64 = refcuda.forward(g64['value'], g64['shapes'], g64['lsi'], g64['loc'], g64['aw']).cpu()
+    want64 = c_oracle.forward(inp['value'].double(), inp['shapes'], inp['lsi'], inp['loc'].double(), inp['aw'].double())
+    torch.testing.assert_close(rout64, want64, rtol=1e-12, atol=1e-13)
+    rgv, rgl, rga = refcuda.backward(g64['value'], g64['shapes'], g64['lsi'], g64['loc'], g64['aw'], g64['grad_out'])
+    wgv, wgl, wga = c_oracle.backward(inp['value'].double(), inp['shapes'], inp['lsi'], inp['loc'].double(),
+                                      inp['aw'].double(), inp['grad_out'].double())
+    torch.testing.assert_close(rgv.cpu(), wgv, rtol=1e-10, atol=1e-12)
+    torch.testing.assert_close(rgl.cpu(), wgl, rtol=1e-10, atol=1e-12)
+    torch.testing.assert_close(rga.cpu(), wga, rtol=1e-10, atol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE.json full sizes: size-independent properties (the oracle is too slow / not needed here)
+# ---------------------------------------------------------------------------------------------------
+FULL = [
+    ('B-injector-bs16', 16, 12, 32, 1024, [(64, 64), (32, 32), (16, 16)], 4),
+    ('B-extractor-bs16', 16, 12, 32, 5376, [(32, 32)], 4),
+    ('S-injector-bs16', 16, 6, 64, 1024, [(64, 64), (32, 32), (16, 16)], 4),
+    ('L-injector-896', 1, 16, 32, 3136, [(112, 112), (56, 56), (28, 28)], 4),
+    ('HTC-extractor-1024', 1, 16, 32, 21504, [(64, 64)], 4),
+]
+
+
+@pytest.mark.parametrize('cfg', FULL, ids=[s[0] for s in FULL])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['f32', 'bf16'])
+def test_full_size_properties(cfg, dtype):
+    _, N, M, D, Lq, shapes, P = cfg
+    inp = make_inputs(N, M, D, Lq, shapes, P, seed=1, dist='adapter')
+    g = _cuda(inp)
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    value = g['value'].to(dtype)
+    f = lambda v, a: vab.MSDeformAttnFunction.apply(v, g['shapes'], g['lsi'], g['loc'], a, 64).float()
+    out = f(value, g['aw'])
+    # (1) constant value + weights summing to 1 + all samples strictly inside => output == constant
+    ones = torch.ones_like(value)
+    loc_in = (g['loc'].clamp(0.02, 0.98)).contiguous()
+    o1 = vab.MSDeformAttnFunction.apply(ones, g['shapes'], g['lsi'], loc_in, g['aw'], 64).float()
+    inner = torch.ones_like(o1)
+    # samples within half a pixel of the border see zero padding; restrict to levels >= 26 px where 0.02 is > 0.5px
+    if min(min(s) for s in shapes) >= 26:
+        torch.testing.assert_close(o1, inner, rtol=tol, atol=tol)
+    # (2) linearity in value and in the attention weights
+    o2 = f((value.float() * 2).to(dtype), g['aw'])
+    torch.testing.assert_close(o2, 2 * out, rtol=2 * tol, atol=2 * tol * _scale(out))
+    o3 = f(value, (g['aw'] * 0.5).contiguous())
+    torch.testing.assert_close(o3, 0.5 * out, rtol=2 * tol, atol=2 * tol * _scale(out))
+    # (3) batch independence: running a single image alone reproduces its slice exactly (bit-for-bit)
+    b = N - 1
+    ob = vab.MSDeformAttnFunction.apply(value[b:b + 1].contiguous(), g['shapes'], g['lsi'], g['loc'][b:b + 1].contiguous(),
+                                        g['aw'][b:b + 1].contiguous(), 64).float()
+    assert torch.equal(ob[0], out[b])
+    # (4) adjoint identity: <grad_out, J v> == <J^T grad_out, v>  (forward is linear in value)
+    v = value.clone().requires_grad_()
+    o = vab.MSDeformAttnFunction.apply(v, g['shapes'], g['lsi'], g['loc'], g['aw'], 64)
+    go = g['grad_out'].to(dtype)
+    o.backward(go)
+    lhs = (o.detach().double() * go.double()).sum()
+    rhs = (v.grad.double() * value.double()).sum()
+    assert abs(float(lhs - rhs)) <= (1e-4 if dtype == torch.float32 else 2e-2) * max(1.0, abs(float(lhs)))
+    # (5) a checksum against the reference CUDA kernel at full size
+    if refcuda.available() and dtype == torch.float32:
+        rout = refcuda.forward(g['value'], g['shapes'], g['lsi'], g['loc'], g['aw'])
+        torch.testing.assert_close(out, rout, rtol=1e-5, atol=1e-6 * max(1.0, _scale(rout)))
+        loc = g['loc'].clone().requires_grad_()
+        aw = g['aw'].clone().requires_grad_()
+        v = g['value'].clone().requires_grad_()
+        vab.MSDeformAttnFunction.apply(v, g['shapes'], g['lsi'], loc, aw, 64).backward(g['grad_out'])
+        rgv, rgl, rga = refcuda.backward(g['value'], g['shapes'], g['lsi'], g['loc'], g['aw'], g['grad_out'])
+        torch.testing.assert_close(v.grad, rgv, rtol=1e-4, atol=1e-4 * _scale(rgv))
+        torch.testing.assert_close(loc.grad, rgl, rtol=1e-4, atol=1e-4 * _scale(rgl))
+        torch.testing.assert_close(aw.grad, rga, rtol=1e-4, atol=1e-4 * _scale(rga))
+
+
+# ---------------------------------------------------------------------------------------------------
+# boundary behaviour
+# ---------------------------------------------------------------------------------------------------
+def test_non_contiguous_rejected():
+    inp = _cuda(make_inputs(1, 2, 32, 8, [(4, 4)], 4, seed=2))
+    v = inp['value'].transpose(1, 2).contiguous().transpose(1, 2)  # same shape, non-contiguous
+    with pytest.raises(RuntimeError, match='contiguous'):
+        vab.MSDeformAttnFunction.apply(v, inp['shapes'], inp['lsi'], inp['loc'], inp['aw'], 64)
+
+
+def test_im2col_step_precondition():
+    inp = _cuda(make_inputs(3, 2, 32, 8, [(4, 4)], 4, seed=2))
+    with pytest.raises(RuntimeError, match='must divide'):
+        vab.MSDeformAttnFunction.apply(inp['value'], inp['shapes'], inp['lsi'], inp['loc'], inp['aw'], 2)
+    out = vab.MSDeformAttnFunction.apply(inp['value'], inp['shapes'], inp['lsi'], inp['loc'], inp['aw'], 3)
+    assert out.shape == (3, 8, 64)
+
+
+def test_all_samples_out_of_range_give_zero():
+    inp = _cuda(make_inputs(1, 2, 32, 8, [(4, 4)], 4, seed=2))
+    loc = torch.full_like(inp['loc'], 5.0)
+    out = vab.MSDeformAttnFunction.apply(inp['value'], inp['shapes'], inp['lsi'], loc, inp['aw'], 64)
+    assert out.abs().max() == 0
+
+
+def test_autocast_matches_reference_policy():
+    """Under autocast the reference up-casts to fp32 (custom_fwd(cast_inputs=float32), func.py:21)."""
+    inp = _cuda(make_inputs(1, 2, 32, 8, [(4, 4)], 4, seed=2))
+    want = vab.MSDeformAttnFunction.apply(inp['value'], inp['shapes'], inp['lsi'], inp['loc'], inp['aw'], 64)
+    with torch.autocast('cuda', dtype=torch.bfloat16):
+        got = vab.MSDeformAttnFunction.apply(inp['value'].bfloat16().float(), inp['shapes'], inp['lsi'], inp['loc'], inp['aw'], 64)
+        assert got.dtype == torch.float32
+    vab.set_amp_value_dtype(torch.bfloat16)
+    try:
+        with torch.autocast('cuda', dtype=torch.bfloat16):
+            got16 = vab.MSDeformAttnFunction.apply(inp['value'], inp['shapes'], inp['lsi'], inp['loc'], inp['aw'], 64)
+            assert got16.dtype == torch.bfloat16
+    finally:
+        vab.set_amp_value_dtype(torch.float32)
+    torch.testing.assert_close(got16.float(), want, rtol=2e-2, atol=2e-2 * _scale(want))
+
+
+def test_launch_counter_and_stream():
+    inp = _cuda(make_inputs(1, 2, 32, 8, [(4, 4)], 4, seed=2))
+    n0 = _cabi.launch_count()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        out = vab.MSDeformAttnFunction.apply(inp['value'], inp['shapes'], inp['lsi'], inp['loc'], inp['aw'], 64)
+    s.synchronize()
+    assert _cabi.launch_count() == n0 + 1
+    want = vab.MSDeformAttnFunction.apply(inp['value'], inp['shapes'], inp['lsi'], inp['loc'], inp['aw'], 64)
+    assert torch.equal(out, want)

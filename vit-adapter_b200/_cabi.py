@@ -1,0 +1,204 @@
+"""ctypes binding of include/msda_b200.h (lib/libmsda_b200.so).
+
+This is the only place Python touches the native library. It passes raw device pointers, the 7
+dimensions and the current CUDA stream; it never computes anything itself and there is NO fallback:
+if the shared library is missing or a tensor is not on a CUDA device the call raises.
+
+Replaces the pybind11 module of the reference (detection/ops/src/vision.cpp:13-16).
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libmsda_b200.so')
+
+MSDA_F32, MSDA_BF16, MSDA_F64 = 0, 1, 2
+_DTYPES = {torch.float32: MSDA_F32, torch.bfloat16: MSDA_BF16, torch.float64: MSDA_F64}
+
+# every symbol include/msda_b200.h declares
+EXPORTS = (
+    'msda_abi_version', 'msda_last_error', 'msda_check_im2col_step', 'msda_forward',
+    'msda_backward_workspace_bytes', 'msda_backward', 'msda_debug_point_index', 'msda_launch_count',
+    'msda_set_query_chunk',
+)
+
+
+class MsdaDims(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in
+                ('batch', 'spatial_size', 'num_heads', 'channels', 'num_levels', 'num_query', 'num_point')]
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load():
+    """dlopen the C-ABI library (once). Raises if it has not been built — there is no CPU path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                'native library %s is missing: build it with `python vit-adapter_b200/build.py` '
+                '(or __graft_entry__.build()). There is no CPU / PyTorch fallback for this op.' % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        vp, i64p = ctypes.c_void_p, ctypes.c_void_p
+        dp = ctypes.POINTER(MsdaDims)
+        lib.msda_abi_version.restype = ctypes.c_int
+        lib.msda_abi_version.argtypes = []
+        lib.msda_last_error.restype = ctypes.c_char_p
+        lib.msda_last_error.argtypes = []
+        lib.msda_check_im2col_step.restype = ctypes.c_int
+        lib.msda_check_im2col_step.argtypes = [ctypes.c_int32, ctypes.c_int32]
+        lib.msda_forward.restype = ctypes.c_int
+        lib.msda_forward.argtypes = [dp, ctypes.c_int, vp, i64p, i64p, vp, vp, vp, vp]
+        lib.msda_backward_workspace_bytes.restype = ctypes.c_size_t
+        lib.msda_backward_workspace_bytes.argtypes = [dp, ctypes.c_int]
+        lib.msda_backward.restype = ctypes.c_int
+        lib.msda_backward.argtypes = [dp, ctypes.c_int, vp, i64p, i64p, vp, vp, vp, vp, vp, vp, vp,
+                                      ctypes.c_size_t, vp]
+        lib.msda_debug_point_index.restype = ctypes.c_int
+        lib.msda_debug_point_index.argtypes = [dp, i64p, i64p, vp, vp, vp]
+        lib.msda_launch_count.restype = ctypes.c_uint64
+        lib.msda_launch_count.argtypes = []
+        lib.msda_set_query_chunk.restype = None
+        lib.msda_set_query_chunk.argtypes = [ctypes.c_int32, ctypes.c_int32]
+        if lib.msda_abi_version() != 1:
+            raise RuntimeError('libmsda_b200.so ABI version %d, expected 1' % lib.msda_abi_version())
+        _lib = lib
+    return _lib
+
+
+def _raise(code, what):
+    msg = load().msda_last_error().decode('utf-8', 'replace')
+    raise RuntimeError('%s failed (code %d): %s' % (what, code, msg))
+
+
+def _check_cuda(**tensors):
+    # Same contract as the reference host code (ms_deform_attn_cuda.cu:28-38): contiguous CUDA
+    # tensors are REQUIRED, never silently fixed up; CPU tensors are an error (ms_deform_attn.h:38).
+    dev = None
+    for name, t in tensors.items():
+        if not t.is_cuda:
+            raise RuntimeError('%s must be a CUDA tensor (Not implemented on the CPU)' % name)
+        if not t.is_contiguous():
+            raise RuntimeError('%s tensor has to be contiguous' % name)
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError('%s is on %s, expected %s' % (name, t.device, dev))
+    return dev
+
+
+def _dims(value, spatial_shapes, sampling_loc):
+    if value.dim() != 4 or sampling_loc.dim() != 6 or spatial_shapes.dim() != 2:
+        raise RuntimeError('expected value [N,S,M,D], spatial_shapes [L,2], sampling_loc [N,Lq,M,L,P,2]')
+    N, S, M, D = value.shape
+    L = spatial_shapes.shape[0]
+    Lq, P = sampling_loc.shape[1], sampling_loc.shape[4]
+    return MsdaDims(N, S, M, D, L, Lq, P)
+
+
+def _dtype_code(value, sampling_loc, attn_weight):
+    code = _DTYPES.get(value.dtype)
+    if code is None:
+        raise RuntimeError('unsupported value dtype %s (float32, bfloat16, float64)' % value.dtype)
+    want = torch.float64 if code == MSDA_F64 else torch.float32
+    if sampling_loc.dtype != want or attn_weight.dtype != want:
+        raise RuntimeError('sampling_loc / attn_weight must be %s for value dtype %s' % (want, value.dtype))
+    return code
+
+
+def _check_meta(spatial_shapes, level_start_index):
+    if spatial_shapes.dtype != torch.int64 or level_start_index.dtype != torch.int64:
+        raise RuntimeError('spatial_shapes / level_start_index must be int64 (as in the reference)')
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step):
+    """ms_deform_attn_forward of the reference pybind module: returns out [N, Lq, M*D]."""
+    lib = load()
+    dev = _check_cuda(value=value, spatial_shapes=spatial_shapes, level_start_index=level_start_index,
+                      sampling_loc=sampling_loc, attn_weight=attn_weight)
+    _check_meta(spatial_shapes, level_start_index)
+    dims = _dims(value, spatial_shapes, sampling_loc)
+    code = _dtype_code(value, sampling_loc, attn_weight)
+    rc = lib.msda_check_im2col_step(dims.batch, int(im2col_step))
+    if rc != 0:
+        _raise(rc, 'ms_deform_attn_forward')
+    with torch.cuda.device(dev):
+        out = torch.empty((dims.batch, dims.num_query, dims.num_heads * dims.channels),
+                          dtype=value.dtype, device=dev)
+        rc = lib.msda_forward(ctypes.byref(dims), code, value.data_ptr(), spatial_shapes.data_ptr(),
+                              level_start_index.data_ptr(), sampling_loc.data_ptr(), attn_weight.data_ptr(),
+                              out.data_ptr(), _stream())
+    if rc != 0:
+        _raise(rc, 'ms_deform_attn_forward')
+    return out
+
+
+def backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output, im2col_step):
+    """ms_deform_attn_backward of the reference pybind module: (grad_value, grad_loc, grad_attn)."""
+    lib = load()
+    dev = _check_cuda(value=value, spatial_shapes=spatial_shapes, level_start_index=level_start_index,
+                      sampling_loc=sampling_loc, attn_weight=attn_weight, grad_output=grad_output)
+    _check_meta(spatial_shapes, level_start_index)
+    dims = _dims(value, spatial_shapes, sampling_loc)
+    code = _dtype_code(value, sampling_loc, attn_weight)
+    if grad_output.dtype != value.dtype:
+        raise RuntimeError('grad_output dtype %s != value dtype %s' % (grad_output.dtype, value.dtype))
+    rc = lib.msda_check_im2col_step(dims.batch, int(im2col_step))
+    if rc != 0:
+        _raise(rc, 'ms_deform_attn_backward')
+    with torch.cuda.device(dev):
+        grad_value = torch.empty_like(value)
+        grad_loc = torch.empty_like(sampling_loc)
+        grad_aw = torch.empty_like(attn_weight)
+        ws_bytes = lib.msda_backward_workspace_bytes(ctypes.byref(dims), code)
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
+        rc = lib.msda_backward(ctypes.byref(dims), code, value.data_ptr(), spatial_shapes.data_ptr(),
+                               level_start_index.data_ptr(), sampling_loc.data_ptr(), attn_weight.data_ptr(),
+                               grad_output.data_ptr(), grad_value.data_ptr(), grad_loc.data_ptr(),
+                               grad_aw.data_ptr(), ws.data_ptr() if ws is not None else None, ws_bytes,
+                               _stream())
+    if rc != 0:
+        _raise(rc, 'ms_deform_attn_backward')
+    return grad_value, grad_loc, grad_aw
+
+
+def debug_point_index(spatial_shapes, level_start_index, sampling_loc, num_heads, channels):
+    """[N*Lq*M*L*P, 4] int32: (h_low, w_low, corner mask, corner-1 element offset) per point."""
+    lib = load()
+    dev = _check_cuda(spatial_shapes=spatial_shapes, level_start_index=level_start_index,
+                      sampling_loc=sampling_loc)
+    _check_meta(spatial_shapes, level_start_index)
+    N, Lq, M, L, P, _ = sampling_loc.shape
+    if sampling_loc.dtype != torch.float32 or M != num_heads:
+        raise RuntimeError('debug_point_index: float32 sampling_loc [N,Lq,M,L,P,2] expected')
+    S = int((spatial_shapes[:, 0] * spatial_shapes[:, 1]).sum().item())
+    dims = MsdaDims(N, S, M, channels, L, Lq, P)
+    with torch.cuda.device(dev):
+        idx = torch.empty((N * Lq * M * L * P, 4), dtype=torch.int32, device=dev)
+        rc = lib.msda_debug_point_index(ctypes.byref(dims), spatial_shapes.data_ptr(),
+                                        level_start_index.data_ptr(), sampling_loc.data_ptr(),
+                                        idx.data_ptr(), _stream())
+    if rc != 0:
+        _raise(rc, 'msda_debug_point_index')
+    return idx
+
+
+def launch_count():
+    return int(load().msda_launch_count())
+
+
+def set_query_chunk(fwd_chunk=0, bwd_chunk=0):
+    load().msda_set_query_chunk(int(fwd_chunk), int(bwd_chunk))

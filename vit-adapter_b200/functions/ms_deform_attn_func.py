@@ -1,0 +1,63 @@
+"""MSDeformAttnFunction — autograd entry of the B200-native multi-scale deformable attention.
+
+Drop-in for the reference's `ops.functions.ms_deform_attn_func.MSDeformAttnFunction`
+(detection/ops/functions/ms_deform_attn_func.py:19-46): same 6-argument `apply`, gradients for
+arguments 0, 3 and 4 only, `once_differentiable` backward. The native side is the C-ABI library
+declared in include/msda_b200.h (called through `_cabi`); there is no PyTorch / CPU fallback here.
+
+AMP: the reference decorates forward with `custom_fwd(cast_inputs=torch.float32)` (:21), i.e. under
+autocast everything is up-cast to fp32. That stays the default. `set_amp_value_dtype(torch.bfloat16)`
+opts in to the bf16 I/O kernels under autocast (value / out in bf16, locations and weights fp32,
+fp32 accumulation) — a capability the reference does not have.
+"""
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from .. import _cabi
+
+_AMP_VALUE_DTYPE = torch.float32
+
+
+def set_amp_value_dtype(dtype):
+    """dtype `value` is cast to when the op runs under torch.autocast (float32 = reference behaviour)."""
+    global _AMP_VALUE_DTYPE
+    if dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError('amp value dtype must be torch.float32 or torch.bfloat16')
+    _AMP_VALUE_DTYPE = dtype
+
+
+def _coord_dtype(value_dtype):
+    return torch.float64 if value_dtype == torch.float64 else torch.float32
+
+
+class MSDeformAttnFunction(Function):
+
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index,
+                sampling_locations, attention_weights, im2col_step):
+        if torch.is_autocast_enabled('cuda') and value.is_cuda:
+            value = value.to(_AMP_VALUE_DTYPE)
+        if value.dtype == torch.float16:
+            value = value.float()
+        cdt = _coord_dtype(value.dtype)
+        # .to() is a no-op (same tensor) when the dtype already matches
+        sampling_locations = sampling_locations.to(cdt)
+        attention_weights = attention_weights.to(cdt)
+        ctx.im2col_step = im2col_step
+        output = _cabi.forward(value, value_spatial_shapes, value_level_start_index,
+                               sampling_locations, attention_weights, im2col_step)
+        ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index,
+                              sampling_locations, attention_weights)
+        return output
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, shapes, level_start, loc, attn = ctx.saved_tensors
+        if grad_output.dtype != value.dtype:
+            grad_output = grad_output.to(value.dtype)
+        grad_output = grad_output.contiguous()
+        grad_value, grad_loc, grad_attn = _cabi.backward(
+            value, shapes, level_start, loc, attn, grad_output, ctx.im2col_step)
+        return grad_value, None, None, grad_loc, grad_attn, None
