@@ -136,8 +136,10 @@ int msda_debug_point_index(const msda_dims* dims,
 /* Number of kernel launches (ours) issued through this library by the calling process so far. */
 uint64_t msda_launch_count(void);
 
-/* Tuning override for benchmarking: queries per CTA chunk (0 = built-in heuristic). */
-void msda_set_query_chunk(int32_t fwd_chunk, int32_t bwd_chunk);
+/* Tuning overrides for benchmarking (0 = built-in heuristic for every field):
+ * queries per CTA chunk, and the min-resident-CTAs-per-SM variant of the vector kernels
+ * (forward: 3, 4 or 6; backward: 2, 3 or 4). Process-wide; affects subsequent calls. */
+void msda_set_tuning(int32_t fwd_chunk, int32_t bwd_chunk, int32_t fwd_min_ctas, int32_t bwd_min_ctas);
 
 #ifdef __cplusplus
 }

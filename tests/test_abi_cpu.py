@@ -84,3 +84,24 @@ def test_product_path_never_touches_the_oracle():
                 if re.search(r'^\s*(from|import)\s+oracle|oracle[./]|grid_sample', text, flags=re.M):
                     offenders.append(os.path.join(base, f))
     assert not offenders, offenders
+
+
+def test_pybind_compat_module_has_reference_surface():
+    """The stand-in for the reference's pybind module exposes exactly vision.cpp:13-16's two functions."""
+    import importlib
+    import inspect
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, 'vit-adapter_b200', 'pybind_compat'))
+    try:
+        sys.modules.pop('MultiScaleDeformableAttention', None)
+        m = importlib.import_module('MultiScaleDeformableAttention')
+    finally:
+        sys.path.pop(0)
+    assert list(inspect.signature(m.ms_deform_attn_forward).parameters) == [
+        'value', 'spatial_shapes', 'level_start_index', 'sampling_loc', 'attn_weight', 'im2col_step']
+    assert list(inspect.signature(m.ms_deform_attn_backward).parameters) == [
+        'value', 'spatial_shapes', 'level_start_index', 'sampling_loc', 'attn_weight', 'grad_output', 'im2col_step']
+    with pytest.raises(RuntimeError, match='CPU'):
+        m.ms_deform_attn_forward(torch.rand(1, 4, 1, 4), torch.as_tensor([(2, 2)]), torch.zeros(1, dtype=torch.long),
+                                 torch.rand(1, 1, 1, 1, 1, 2), torch.rand(1, 1, 1, 1, 1), 64)
+    sys.modules.pop('MultiScaleDeformableAttention', None)

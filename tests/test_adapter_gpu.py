@@ -1,0 +1,91 @@
+"""Module- and adapter-level parity on the GPU against golden outputs of the REAL reference modules
+(fp64 through the generic kernels: tight tolerances), plus fp32/bf16 sanity on the vector kernels."""
+import pytest
+import torch
+
+from conftest import load_golden
+
+from vit_adapter_b200 import MSDeformAttn
+from vit_adapter_b200.adapter import InteractionBlock, deform_inputs
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _lsi(shapes):
+    return torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+
+
+@pytest.mark.parametrize('name', ['module_l3', 'module_ratio_half_box'])
+def test_module_matches_reference_f64(name):
+    g = load_golden(name)
+    d_model, L, M, P = [int(x) for x in g['cfg']]
+    m = MSDeformAttn(d_model, L, M, P, float(g['ratio'])).double()
+    m.load_state_dict({k[3:]: v for k, v in g.items() if k.startswith('sd.')}, strict=True)
+    m = m.to(DEV)
+    shapes = g['shapes'].to(DEV)
+    args = (g['query'].to(DEV), g['ref_pts'].to(DEV), g['feat'].to(DEV), shapes, _lsi(shapes))
+    out = m(*args, g['mask'].to(DEV))
+    torch.testing.assert_close(out.cpu(), g['out'], rtol=1e-9, atol=1e-11)
+    out = m(*args, None)
+    torch.testing.assert_close(out.cpu(), g['out_nomask'], rtol=1e-9, atol=1e-11)
+
+
+def test_module_f32_and_steady_state_no_sync():
+    g = load_golden('module_l3')
+    d_model, L, M, P = [int(x) for x in g['cfg']]
+    m = MSDeformAttn(d_model, L, M, P, float(g['ratio']))
+    m.load_state_dict({k[3:]: v.float() for k, v in g.items() if k.startswith('sd.')}, strict=True)
+    m = m.to(DEV)
+    shapes = g['shapes'].to(DEV)
+    args = (g['query'].float().to(DEV), g['ref_pts'].float().to(DEV), g['feat'].float().to(DEV), shapes, _lsi(shapes))
+    out = m(*args)
+    torch.testing.assert_close(out.cpu().double(), g['out_nomask'], rtol=1e-4, atol=1e-4)
+    # second call with the same shapes tensor: the Len_in check is cached -> capturable in a CUDA graph
+    graph = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        with torch.no_grad():
+            for _ in range(2):
+                m(*args)
+            torch.cuda.synchronize()
+            with torch.cuda.graph(graph, stream=s):
+                out2 = m(*args)
+    graph.replay()
+    torch.cuda.synchronize()
+    torch.testing.assert_close(out2, out, rtol=1e-6, atol=1e-6)
+
+
+def test_interaction_block_matches_reference_f64():
+    g = load_golden('adapter_block')
+    dim, heads, H, W, N = [int(v) for v in g['cfg']]
+    blk = InteractionBlock(dim=dim, num_heads=heads, n_points=4, init_values=0., deform_ratio=float(g['ratio']),
+                           extra_extractor=True, with_cffn=True, cffn_ratio=0.25).double()
+    blk.load_state_dict({k[3:]: v for k, v in g.items() if k.startswith('sd.')}, strict=True)
+    blk = blk.to(DEV)
+    # the golden was made with the reference's deform_inputs on the CPU; torch.linspace rounds differently on
+    # CUDA (1 ulp), so feed the golden's own reference points and check deform_inputs-on-GPU separately
+    d1 = [g['ref1'].double().to(DEV), g['shapes1'].to(DEV), g['lsi1'].to(DEV)]
+    d2 = [g['ref2'].double().to(DEV), g['shapes2'].to(DEV), g['lsi2'].to(DEV)]
+    e1, e2 = deform_inputs(torch.zeros(N, 3, H, W, device=DEV))
+    torch.testing.assert_close(e1[0].cpu(), g['ref1'], rtol=0, atol=2e-7)
+    torch.testing.assert_close(e2[0].cpu(), g['ref2'], rtol=0, atol=2e-7)
+    assert torch.equal(e1[1].cpu(), g['shapes1']) and torch.equal(e2[2].cpu(), g['lsi2'])
+    x, c = blk(g['x'].to(DEV), g['c'].to(DEV), [], d1, d2, H // 16, W // 16)
+    torch.testing.assert_close(x.cpu(), g['x_out'], rtol=1e-8, atol=1e-9)
+    torch.testing.assert_close(c.cpu(), g['c_out'], rtol=1e-8, atol=1e-9)
+
+
+def test_interaction_block_trains_f32_with_checkpointing():
+    torch.manual_seed(0)
+    blk = InteractionBlock(dim=64, num_heads=2, n_points=4, init_values=0.1, deform_ratio=1.0, extra_extractor=True,
+                           with_cp=True).to(DEV)
+    img = torch.zeros(2, 3, 64, 64, device=DEV)
+    d1, d2 = deform_inputs(img)
+    x = torch.randn(2, 16, 64, device=DEV, requires_grad=True)
+    c = torch.randn(2, 64 + 16 + 4, 64, device=DEV, requires_grad=True)
+    xo, co = blk(x, c, [], d1, d2, 4, 4)
+    (xo.square().mean() + co.square().mean()).backward()
+    for n, p in blk.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n
+    assert x.grad is not None and c.grad is not None

@@ -42,6 +42,10 @@ def main():
     ap.add_argument('--variants', default='B,S,L,L64,HTC')
     ap.add_argument('--iters', type=int, default=30)
     ap.add_argument('--qc', default='0', help='comma list of query-chunk overrides to try (0 = heuristic)')
+    ap.add_argument('--minb', default='0:0', help='comma list of fwd:bwd min-CTAs-per-SM kernel variants (0 = default)')
+    ap.add_argument('--regimes', default='flushed,warm')
+    ap.add_argument('--dtypes', default='f32,bf16')
+    ap.add_argument('--no-ref', action='store_true')
     ap.add_argument('--out', default=os.path.join(ROOT, 'gpurun_out', 'sweep.json'))
     ap.add_argument('--dist', default='adapter')
     args = ap.parse_args()
@@ -63,15 +67,20 @@ def main():
             d16 = dict(d32, value=d32['value'].bfloat16(), grad_out=d32['grad_out'].bfloat16())
             pts = n_points(N, Mh, Lq, len(shapes))
             for dtype, d, es in (('f32', d32, 4), ('bf16', d16, 2)):
+                if dtype not in args.dtypes.split(','):
+                    continue
                 ab = algorithmic_bytes(N, Mh, Dh, Lq, shapes, es)
-                for qc in [int(x) for x in args.qc.split(',')]:
-                    _cabi.set_query_chunk(qc, qc)
+                for qc, mb in [(int(x), y) for x in args.qc.split(',') for y in args.minb.split(',')]:
+                    fmb, bmb = [int(v) for v in mb.split(':')]
+                    _cabi.set_tuning(qc, qc, fmb, bmb)
                     fw = lambda: _cabi.forward(d['value'], d['shapes'], d['lsi'], d['loc'], d['aw'], 64)
                     bw = lambda: _cabi.backward(d['value'], d['shapes'], d['lsi'], d['loc'], d['aw'], d['grad_out'], 64)
                     for regime, fl in (('flushed', flush), ('warm', None)):
+                        if regime not in args.regimes.split(','):
+                            continue
                         tf = timeit(fw, args.iters, 5, fl)
                         tb = timeit(bw, args.iters, 5, fl)
-                        rows.append({'variant': variant, 'call': name, 'dtype': dtype, 'impl': 'ours', 'qc': qc,
+                        rows.append({'variant': variant, 'call': name, 'dtype': dtype, 'impl': 'ours', 'qc': '%d/%s' % (qc, mb),
                                      'regime': regime, 'fwd_us': tf['med'] * 1e3, 'bwd_us': tb['med'] * 1e3,
                                      'fwd_min_us': tf['min'] * 1e3, 'bwd_min_us': tb['min'] * 1e3, 'pts': pts,
                                      'gsamples_s': pts / ((tf['med'] + tb['med']) * 1e-3) / 1e9,
@@ -79,12 +88,14 @@ def main():
                                      'bwd_frac': ab['bwd'] / (tb['med'] * 1e-3) / 1e9 / peak,
                                      'frac': (ab['fwd'] + ab['bwd']) / ((tf['med'] + tb['med']) * 1e-3) / 1e9 / peak})
                         print(json.dumps(rows[-1]), flush=True)
-                _cabi.set_query_chunk(0, 0)
-            if refcuda.available():
+                _cabi.set_tuning(0, 0, 0, 0)
+            if refcuda.available() and not args.no_ref:
                 ab = algorithmic_bytes(N, Mh, Dh, Lq, shapes, 4)
                 fw = lambda: refcuda.forward(d32['value'], d32['shapes'], d32['lsi'], d32['loc'], d32['aw'])
                 bw = lambda: refcuda.backward(d32['value'], d32['shapes'], d32['lsi'], d32['loc'], d32['aw'], d32['grad_out'])
                 for regime, fl in (('flushed', flush), ('warm', None)):
+                    if regime not in args.regimes.split(','):
+                        continue
                     tf = timeit(fw, max(5, args.iters // 3), 2, fl)
                     tb = timeit(bw, max(5, args.iters // 3), 2, fl)
                     rows.append({'variant': variant, 'call': name, 'dtype': 'f32', 'impl': 'ref_cuda', 'qc': None,

@@ -22,7 +22,7 @@ _DTYPES = {torch.float32: MSDA_F32, torch.bfloat16: MSDA_BF16, torch.float64: MS
 EXPORTS = (
     'msda_abi_version', 'msda_last_error', 'msda_check_im2col_step', 'msda_forward',
     'msda_backward_workspace_bytes', 'msda_backward', 'msda_debug_point_index', 'msda_launch_count',
-    'msda_set_query_chunk',
+    'msda_set_tuning',
 )
 
 
@@ -67,8 +67,8 @@ def load():
         lib.msda_debug_point_index.argtypes = [dp, i64p, i64p, vp, vp, vp]
         lib.msda_launch_count.restype = ctypes.c_uint64
         lib.msda_launch_count.argtypes = []
-        lib.msda_set_query_chunk.restype = None
-        lib.msda_set_query_chunk.argtypes = [ctypes.c_int32, ctypes.c_int32]
+        lib.msda_set_tuning.restype = None
+        lib.msda_set_tuning.argtypes = [ctypes.c_int32] * 4
         if lib.msda_abi_version() != 1:
             raise RuntimeError('libmsda_b200.so ABI version %d, expected 1' % lib.msda_abi_version())
         _lib = lib
@@ -200,5 +200,6 @@ def launch_count():
     return int(load().msda_launch_count())
 
 
-def set_query_chunk(fwd_chunk=0, bwd_chunk=0):
-    load().msda_set_query_chunk(int(fwd_chunk), int(bwd_chunk))
+def set_tuning(fwd_chunk=0, bwd_chunk=0, fwd_min_ctas=0, bwd_min_ctas=0):
+    """Benchmark knobs (0 = heuristic): queries per CTA chunk; min resident CTAs per SM variant."""
+    load().msda_set_tuning(int(fwd_chunk), int(bwd_chunk), int(fwd_min_ctas), int(bwd_min_ctas))

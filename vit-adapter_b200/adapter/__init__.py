@@ -1,0 +1,2 @@
+from .adapter_modules import (ConvFFN, DropPath, DWConv, Extractor, Injector, InteractionBlock,  # noqa: F401
+                              InteractionBlockWithCls, SpatialPriorModule, deform_inputs, get_reference_points)

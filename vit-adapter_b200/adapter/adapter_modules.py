@@ -1,0 +1,258 @@
+"""Adapter-side callers of MSDeformAttn: deform_inputs, Injector, Extractor, InteractionBlock[WithCls].
+
+Drop-in for the reference's `adapter_modules.py` (three near-identical copies:
+detection/mmdet_custom/models/backbones/adapter_modules.py, segmentation/mmseg_custom/... (adds
+InteractionBlockWithCls, :194-234, and `with_cp` on SpatialPriorModule), wsdm2023/...). Same class
+names, constructor arguments, sub-module names (state_dict keys) and forward signatures, so the
+adapter backbones (vit_adapter.py:109-113) can import these instead.
+
+Differences from the reference, all host-side:
+  * `deform_inputs` memoises the (reference_points, spatial_shapes, level_start_index) triples per
+    (H, W, device): the reference rebuilds them from Python on every forward (adapter_modules.py:28-47),
+    which costs ~20 tiny kernel launches and makes the tensors' storage change every step (defeating
+    MSDeformAttn's cached shape check and CUDA-graph capture).
+  * DropPath is implemented here (timm is not a dependency).
+"""
+from functools import partial
+
+import torch
+import torch.nn as nn
+import torch.utils.checkpoint as cp
+
+from ..modules import MSDeformAttn
+
+
+class DropPath(nn.Module):
+    """Stochastic depth per sample (what timm.models.layers.DropPath does)."""
+
+    def __init__(self, drop_prob=0.):
+        super().__init__()
+        self.drop_prob = float(drop_prob)
+
+    def forward(self, x):
+        if self.drop_prob == 0. or not self.training:
+            return x
+        keep = 1.0 - self.drop_prob
+        mask = x.new_empty((x.shape[0],) + (1,) * (x.dim() - 1)).bernoulli_(keep)
+        return x * mask / keep
+
+    def extra_repr(self):
+        return 'drop_prob={:.3f}'.format(self.drop_prob)
+
+
+def get_reference_points(spatial_shapes, device):
+    """Cell centres (x, y) in [0,1] of each (H, W) grid, concatenated: [1, sum H*W, 1, 2]
+    (reference adapter_modules.py:13-25: linspace(0.5, H-0.5, H) / H)."""
+    pts = []
+    for (H, W) in spatial_shapes:
+        ys = torch.linspace(0.5, H - 0.5, H, dtype=torch.float32, device=device) / H
+        xs = torch.linspace(0.5, W - 0.5, W, dtype=torch.float32, device=device) / W
+        yy, xx = torch.meshgrid(ys, xs, indexing='ij')
+        pts.append(torch.stack((xx.reshape(-1), yy.reshape(-1)), -1)[None])
+    return torch.cat(pts, 1)[:, :, None]
+
+
+def _level_meta(shapes, device):
+    spatial_shapes = torch.as_tensor(shapes, dtype=torch.long, device=device)
+    level_start_index = torch.cat((spatial_shapes.new_zeros((1,)), spatial_shapes.prod(1).cumsum(0)[:-1]))
+    return spatial_shapes, level_start_index
+
+
+_DEFORM_CACHE = {}
+
+
+def deform_inputs(x):
+    """x: image batch [N, 3, H, W] (only its shape / device are used). Returns
+    deform_inputs1 = [ref points of the H/16 grid, shapes of the H/8, H/16, H/32 levels, level starts]  (Injector)
+    deform_inputs2 = [ref points of the three levels, shape of the H/16 grid, [0]]                     (Extractor)
+    exactly as reference adapter_modules.py:28-47, memoised per (H, W, device)."""
+    _, _, h, w = x.shape
+    key = (int(h), int(w), str(x.device))
+    hit = _DEFORM_CACHE.get(key)
+    if hit is not None:
+        return hit
+    pyramid = [(h // 8, w // 8), (h // 16, w // 16), (h // 32, w // 32)]
+    vit_grid = [(h // 16, w // 16)]
+    shapes1, lsi1 = _level_meta(pyramid, x.device)
+    ref1 = get_reference_points(vit_grid, x.device)
+    shapes2, lsi2 = _level_meta(vit_grid, x.device)
+    ref2 = get_reference_points(pyramid, x.device)
+    out = ([ref1, shapes1, lsi1], [ref2, shapes2, lsi2])
+    if len(_DEFORM_CACHE) > 32:
+        _DEFORM_CACHE.clear()
+    _DEFORM_CACHE[key] = out
+    return out
+
+
+class DWConv(nn.Module):
+    """Depth-wise 3x3 over the three token maps packed in one sequence of 21n tokens
+    (16n at H/8, 4n at H/16, n at H/32); reference adapter_modules.py:73-87."""
+
+    def __init__(self, dim=768):
+        super().__init__()
+        self.dwconv = nn.Conv2d(dim, dim, 3, 1, 1, bias=True, groups=dim)
+
+    def forward(self, x, H, W):
+        B, N, C = x.shape
+        n = N // 21
+        outs = []
+        for (lo, hi, h, w) in ((0, 16 * n, H * 2, W * 2), (16 * n, 20 * n, H, W), (20 * n, N, H // 2, W // 2)):
+            fmap = x[:, lo:hi, :].transpose(1, 2).reshape(B, C, h, w)
+            outs.append(self.dwconv(fmap).flatten(2).transpose(1, 2))
+        return torch.cat(outs, dim=1)
+
+
+class ConvFFN(nn.Module):
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.):
+        super().__init__()
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.dwconv = DWConv(hidden_features)
+        self.act = act_layer()
+        self.fc2 = nn.Linear(hidden_features, out_features)
+        self.drop = nn.Dropout(drop)
+
+    def forward(self, x, H, W):
+        x = self.drop(self.act(self.dwconv(self.fc1(x), H, W)))
+        return self.drop(self.fc2(x))
+
+
+class Extractor(nn.Module):
+    """c <- c + MSDeformAttn(LN(c), ref, LN(x)) ; c <- c + DropPath(ConvFFN(LN(c)))   (reference :90-124)."""
+
+    def __init__(self, dim, num_heads=6, n_points=4, n_levels=1, deform_ratio=1.0, with_cffn=True, cffn_ratio=0.25,
+                 drop=0., drop_path=0., norm_layer=partial(nn.LayerNorm, eps=1e-6), with_cp=False):
+        super().__init__()
+        self.query_norm = norm_layer(dim)
+        self.feat_norm = norm_layer(dim)
+        self.attn = MSDeformAttn(d_model=dim, n_levels=n_levels, n_heads=num_heads, n_points=n_points,
+                                 ratio=deform_ratio)
+        self.with_cffn = with_cffn
+        self.with_cp = with_cp
+        if with_cffn:
+            self.ffn = ConvFFN(in_features=dim, hidden_features=int(dim * cffn_ratio), drop=drop)
+            self.ffn_norm = norm_layer(dim)
+            self.drop_path = DropPath(drop_path) if drop_path > 0. else nn.Identity()
+
+    def forward(self, query, reference_points, feat, spatial_shapes, level_start_index, H, W):
+        def inner(query, feat):
+            query = query + self.attn(self.query_norm(query), reference_points, self.feat_norm(feat),
+                                      spatial_shapes, level_start_index, None)
+            if self.with_cffn:
+                query = query + self.drop_path(self.ffn(self.ffn_norm(query), H, W))
+            return query
+
+        if self.with_cp and query.requires_grad:
+            return cp.checkpoint(inner, query, feat, use_reentrant=True)
+        return inner(query, feat)
+
+
+class Injector(nn.Module):
+    """x <- x + gamma * MSDeformAttn(LN(x), ref, LN(c))   (reference :127-152; gamma starts at init_values)."""
+
+    def __init__(self, dim, num_heads=6, n_points=4, n_levels=1, deform_ratio=1.0,
+                 norm_layer=partial(nn.LayerNorm, eps=1e-6), init_values=0., with_cp=False):
+        super().__init__()
+        self.with_cp = with_cp
+        self.query_norm = norm_layer(dim)
+        self.feat_norm = norm_layer(dim)
+        self.attn = MSDeformAttn(d_model=dim, n_levels=n_levels, n_heads=num_heads, n_points=n_points,
+                                 ratio=deform_ratio)
+        self.gamma = nn.Parameter(init_values * torch.ones((dim)), requires_grad=True)
+
+    def forward(self, query, reference_points, feat, spatial_shapes, level_start_index):
+        def inner(query, feat):
+            attn = self.attn(self.query_norm(query), reference_points, self.feat_norm(feat), spatial_shapes,
+                             level_start_index, None)
+            return query + self.gamma * attn
+
+        if self.with_cp and query.requires_grad:
+            return cp.checkpoint(inner, query, feat, use_reentrant=True)
+        return inner(query, feat)
+
+
+class _InteractionBase(nn.Module):
+    def __init__(self, dim, num_heads=6, n_points=4, norm_layer=partial(nn.LayerNorm, eps=1e-6), drop=0., drop_path=0.,
+                 with_cffn=True, cffn_ratio=0.25, init_values=0., deform_ratio=1.0, extra_extractor=False,
+                 with_cp=False):
+        super().__init__()
+        self.injector = Injector(dim=dim, n_levels=3, num_heads=num_heads, init_values=init_values, n_points=n_points,
+                                 norm_layer=norm_layer, deform_ratio=deform_ratio, with_cp=with_cp)
+        ext = dict(dim=dim, num_heads=num_heads, n_points=n_points, norm_layer=norm_layer, deform_ratio=deform_ratio,
+                   with_cffn=with_cffn, cffn_ratio=cffn_ratio, drop=drop, drop_path=drop_path, with_cp=with_cp)
+        self.extractor = Extractor(n_levels=1, **ext)
+        self.extra_extractors = nn.Sequential(*[Extractor(**ext) for _ in range(2)]) if extra_extractor else None
+
+    def _inject(self, x, c, deform_inputs1):
+        return self.injector(query=x, reference_points=deform_inputs1[0], feat=c, spatial_shapes=deform_inputs1[1],
+                             level_start_index=deform_inputs1[2])
+
+    def _extract(self, x, c, deform_inputs2, H, W):
+        extractors = [self.extractor] + (list(self.extra_extractors) if self.extra_extractors is not None else [])
+        for e in extractors:
+            c = e(query=c, reference_points=deform_inputs2[0], feat=x, spatial_shapes=deform_inputs2[1],
+                  level_start_index=deform_inputs2[2], H=H, W=W)
+        return c
+
+
+class InteractionBlock(_InteractionBase):
+    """Injector -> the slice of ViT blocks -> Extractor (+2 extra extractors on the last block);
+    reference adapter_modules.py:155-191."""
+
+    def forward(self, x, c, blocks, deform_inputs1, deform_inputs2, H, W):
+        x = self._inject(x, c, deform_inputs1)
+        for blk in blocks:
+            x = blk(x, H, W)
+        return x, self._extract(x, c, deform_inputs2, H, W)
+
+
+class InteractionBlockWithCls(_InteractionBase):
+    """Same, with BEiT's class token re-attached around the ViT blocks (segmentation copy :194-234)."""
+
+    def forward(self, x, c, cls, blocks, deform_inputs1, deform_inputs2, H, W):
+        x = self._inject(x, c, deform_inputs1)
+        x = torch.cat((cls, x), dim=1)
+        for blk in blocks:
+            x = blk(x, H, W)
+        cls, x = x[:, :1, ], x[:, 1:, ]
+        return x, self._extract(x, c, deform_inputs2, H, W), cls
+
+
+class SpatialPriorModule(nn.Module):
+    """Convolutional stem producing the 1/4 map and the 1/8, 1/16, 1/32 token sequences the Injector
+    reads (reference :194-246). `norm_layer` defaults to nn.SyncBatchNorm as in the reference."""
+
+    def __init__(self, inplanes=64, embed_dim=384, with_cp=False, norm_layer=nn.SyncBatchNorm):
+        super().__init__()
+        self.with_cp = with_cp
+
+        def conv_bn_relu(cin, cout, stride):
+            return [nn.Conv2d(cin, cout, kernel_size=3, stride=stride, padding=1, bias=False), norm_layer(cout),
+                    nn.ReLU(inplace=True)]
+
+        self.stem = nn.Sequential(*(conv_bn_relu(3, inplanes, 2) + conv_bn_relu(inplanes, inplanes, 1)
+                                    + conv_bn_relu(inplanes, inplanes, 1)
+                                    + [nn.MaxPool2d(kernel_size=3, stride=2, padding=1)]))
+        self.conv2 = nn.Sequential(*conv_bn_relu(inplanes, 2 * inplanes, 2))
+        self.conv3 = nn.Sequential(*conv_bn_relu(2 * inplanes, 4 * inplanes, 2))
+        self.conv4 = nn.Sequential(*conv_bn_relu(4 * inplanes, 4 * inplanes, 2))
+        self.fc1 = nn.Conv2d(inplanes, embed_dim, kernel_size=1, stride=1, padding=0, bias=True)
+        self.fc2 = nn.Conv2d(2 * inplanes, embed_dim, kernel_size=1, stride=1, padding=0, bias=True)
+        self.fc3 = nn.Conv2d(4 * inplanes, embed_dim, kernel_size=1, stride=1, padding=0, bias=True)
+        self.fc4 = nn.Conv2d(4 * inplanes, embed_dim, kernel_size=1, stride=1, padding=0, bias=True)
+
+    def forward(self, x):
+        def inner(x):
+            c1 = self.stem(x)
+            c2 = self.conv2(c1)
+            c3 = self.conv3(c2)
+            c4 = self.conv4(c3)
+            c1, c2, c3, c4 = self.fc1(c1), self.fc2(c2), self.fc3(c3), self.fc4(c4)
+            bs, dim = c1.shape[:2]
+            tokens = [c.view(bs, dim, -1).transpose(1, 2) for c in (c2, c3, c4)]  # 8s, 16s, 32s
+            return (c1, *tokens)
+
+        if self.with_cp and x.requires_grad:
+            return cp.checkpoint(inner, x, use_reentrant=True)
+        return inner(x)

@@ -12,14 +12,14 @@
 #include "msda_common.cuh"
 
 namespace msda {
-bool fwd_vec_supported(int dtype, int D, int* G_out);
-cudaError_t launch_forward(const Params& p, int dtype, bool vec_ok, int G, cudaStream_t s);
-cudaError_t launch_backward(const Params& p, int dtype, bool vec_ok, int G, cudaStream_t s);
+bool vec_supported(int dtype, int D, int* G_out);
+cudaError_t launch_forward(const Params& p, int dtype, bool vec_ok, int G, int minb, cudaStream_t s);
+cudaError_t launch_backward(const Params& p, int dtype, bool vec_ok, int G, int minb, cudaStream_t s);
 cudaError_t launch_cvt_f32_bf16(const float* src, void* dst, size_t n, cudaStream_t s);
 
 static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
-static std::atomic<int> g_qc_fwd{0}, g_qc_bwd{0};
+static std::atomic<int> g_qc_fwd{0}, g_qc_bwd{0}, g_minb_fwd{0}, g_minb_bwd{0};
 
 static int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -47,12 +47,13 @@ static int check_dims(const msda_dims* d, int dtype) {
                 d->spatial_size, d->num_heads, d->channels, d->num_levels, d->num_query, d->num_point);
   if (d->num_levels > MSDA_MAX_LEVELS)
     return fail(MSDA_E_LEVELS, "num_levels=%d exceeds MSDA_MAX_LEVELS=%d", d->num_levels, MSDA_MAX_LEVELS);
-  // in-image element offsets are int32 in the kernels (as in the reference, which is int32 throughout)
+  // in-image byte offsets are uint32 in the kernels (the reference is int32 element offsets throughout);
+  // the token index shares a register with 4 flag bits.
   const int64_t per_image = (int64_t)d->spatial_size * d->num_heads * d->channels;
   const int64_t per_pair = (int64_t)d->num_levels * d->num_point;
-  if (per_image >= (1ll << 31) || per_pair >= (1ll << 20) ||
+  if (per_image >= (1ll << 29) || per_pair >= (1ll << 20) || d->spatial_size >= (1 << 27) ||
       (int64_t)d->num_heads * d->channels >= (1ll << 24))
-    return fail(MSDA_E_DIMS, "S*M*D=%lld does not fit the int32 in-image offset", (long long)per_image);
+    return fail(MSDA_E_DIMS, "S*M*D=%lld does not fit the 32-bit in-image byte offset", (long long)per_image);
   return 0;
 }
 
@@ -111,9 +112,11 @@ const char* msda_last_error(void) { return g_err; }
 
 uint64_t msda_launch_count(void) { return g_launches.load(); }
 
-void msda_set_query_chunk(int32_t fwd_chunk, int32_t bwd_chunk) {
+void msda_set_tuning(int32_t fwd_chunk, int32_t bwd_chunk, int32_t fwd_min_ctas, int32_t bwd_min_ctas) {
   g_qc_fwd.store(fwd_chunk);
   g_qc_bwd.store(bwd_chunk);
+  g_minb_fwd.store(fwd_min_ctas);
+  g_minb_bwd.store(bwd_min_ctas);
 }
 
 int msda_check_im2col_step(int32_t batch, int32_t im2col_step) {
@@ -140,13 +143,13 @@ int msda_forward(const msda_dims* dims, int dtype, const void* value, const int6
   p.loc = sampling_loc; p.aw = attn_weight; p.out = out;
 
   int G = 0;
-  bool vec = fwd_vec_supported(dtype, p.D, &G) && aligned(value, 16) && aligned(out, 16) &&
+  bool vec = vec_supported(dtype, p.D, &G) && aligned(value, 16) && aligned(out, 16) &&
              aligned(sampling_loc, 8);
   const int per_iter = vec ? kWarps * (32 / G) : kWarps;
   p.qc = pick_chunk(dims, per_iter, g_qc_fwd.load());
   p.nchunk = (p.Lq + p.qc - 1) / p.qc;
 
-  const cudaError_t e = launch_forward(p, dtype, vec, G, (cudaStream_t)stream);
+  const cudaError_t e = launch_forward(p, dtype, vec, G, g_minb_fwd.load(), (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "msda_forward launch");
   g_launches.fetch_add(1);
   return 0;
@@ -188,7 +191,7 @@ int msda_backward(const msda_dims* dims, int dtype, const void* value, const int
   p.grad_value = accum;
 
   int G = 0;
-  bool vec = fwd_vec_supported(dtype, p.D, &G) && aligned(value, 16) && aligned(grad_out, 16) &&
+  bool vec = vec_supported(dtype, p.D, &G) && aligned(value, 16) && aligned(grad_out, 16) &&
              aligned(accum, 16) && aligned(sampling_loc, 8) && aligned(grad_sampling_loc, 8);
   const int per_iter = vec ? kWarps * (32 / G) : kWarps;
   p.qc = pick_chunk(dims, per_iter, g_qc_bwd.load());
@@ -196,7 +199,7 @@ int msda_backward(const msda_dims* dims, int dtype, const void* value, const int
 
   cudaError_t e = cudaMemsetAsync(accum, 0, accum_bytes, s);
   if (e != cudaSuccess) return cuda_fail(e, "msda_backward memset(grad_value)");
-  e = launch_backward(p, dtype, vec, G, s);
+  e = launch_backward(p, dtype, vec, G, g_minb_bwd.load(), s);
   if (e != cudaSuccess) return cuda_fail(e, "msda_backward launch");
   g_launches.fetch_add(1);
   if (dtype == MSDA_BF16) {

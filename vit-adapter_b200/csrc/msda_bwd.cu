@@ -5,8 +5,13 @@
 // dynamic/global variants :513-920) plus the launcher switch (:956-1327). Not a port:
 //   * the reference launches one D-thread block per (b,q,m), stages 3*D partials in shared memory
 //     per point and reduces them serially (v1) or with a barrier tree (v2); here a group of G lanes
-//     owns a (b,q,m), each lane reduces its 4/8 channels in registers and the group finishes with
-//     warp shuffles — no shared memory, no __syncthreads in the point loop;
+//     owns a (b,q,m) and each lane keeps 4/8 channels. Because everything is linear in the corner
+//     values, a lane only accumulates u_k = sum_c grad_out[c] * v_k[c] for the four corners (4 FMAs
+//     per channel) and turns (u_1..u_4) into its share of d/d(attn), d/dx, d/dy once per point;
+//     the G shares of all G points of a round are then summed with ONE transposed shuffle
+//     reduction (3G values -> 3 per lane in ~3G shuffles, instead of 3*log2(G) per point) — no
+//     shared memory, no __syncthreads in the point loop;
+//   * corner rows are clamped into the level, so the value gathers need no predicates;
 //   * grad_value is scattered with one 16-byte vector reduction (REDG.E.ADD.F32x4) per lane per
 //     corner instead of one scalar atomicAdd per channel per corner (:121,130,139,148);
 //   * grad_sampling_loc / grad_attn_weight are written exactly once, so only grad_value is
@@ -23,20 +28,47 @@ __device__ __forceinline__ float group_sum(float v) {
   return v;
 }
 
+// Transposed reduction over a group of G lanes: every lane holds NV = 3*G partials laid out
+// [point][component]; afterwards lane j holds the three totals of point j in v[0..2].
+// Each step halves the live values: a lane keeps the half that belongs to its side of the split and
+// receives the partner's partials for that half.
+template <int G, int NV>
+__device__ __forceinline__ void group_transpose_sum(float (&v)[NV], int j) {
+  static_assert(NV == 3 * G, "layout is [G points][3 components]");
+  int n = NV;
+#pragma unroll
+  for (int s = G / 2; s > 0; s >>= 1) {
+    const bool upper = (j & s) != 0;
+    const int half = n / 2;
+#pragma unroll
+    for (int i = 0; i < NV / 2; ++i) {
+      if (i < half) {
+        const float send = upper ? v[i] : v[i + half];
+        const float keep = upper ? v[i + half] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s, G);
+      }
+    }
+    n = half;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Vector kernel (same work decomposition as the forward).
 // ---------------------------------------------------------------------------------------------
-template <typename T, int G, int LT, int PT>
-__global__ void __launch_bounds__(kThreads) msda_bwd_vec_kernel(const Params p) {
+template <typename T, int G, int LT, int PT, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) msda_bwd_vec_kernel(const Params p) {
   using V = Vec<T>;
   constexpr int kCpl = V::kCpl;
   constexpr int kGpw = 32 / G;
   constexpr bool kStatic = (LT > 0);
+  constexpr bool kTranspose = (G <= 8);  // 3*G partial registers per lane
 
   const int L = kStatic ? LT : p.L;
   const int P = kStatic ? PT : p.P;
   const int LP = L * P;
   const int MD = p.M * p.D;
+  const unsigned MDb = (unsigned)MD * (unsigned)sizeof(T);  // bytes between neighbouring tokens (value)
+  const unsigned MDf = (unsigned)MD * 4u;                    // same in the fp32 grad_value accumulator
 
   __shared__ int sH[kMaxLevels], sW[kMaxLevels], sStart[kMaxLevels];
   if (threadIdx.x < L) {
@@ -46,13 +78,17 @@ __global__ void __launch_bounds__(kThreads) msda_bwd_vec_kernel(const Params p) 
   }
   __syncthreads();
 
+  unsigned rsl[kStatic ? LT : 1];  // token rows: bytes between rows per level, in units of MDb
+#pragma unroll
+  for (int l = 0; l < (kStatic ? LT : 1); ++l) rsl[l] = (unsigned)sW[l];
+
   const BlockCoord bc = block_coord(p);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = lane / G, j = lane % G;
 
-  const size_t img = (size_t)bc.b * p.S * MD + bc.m * p.D + j * kCpl;
-  const T* __restrict__ vbase = reinterpret_cast<const T*>(p.value) + img;
-  float* __restrict__ gvbase = reinterpret_cast<float*>(p.grad_value) + img;  // fp32 (scratch for bf16)
+  const size_t slab = (size_t)bc.b * p.S * MD + (size_t)bc.m * p.D;
+  const char* __restrict__ vb = reinterpret_cast<const char*>(p.value) + slab * sizeof(T) + j * 16;
+  char* __restrict__ gvb = reinterpret_cast<char*>(p.grad_value) + slab * 4u + j * (kCpl * 4);  // fp32 accumulator
   const float* __restrict__ loc = reinterpret_cast<const float*>(p.loc);
   const float* __restrict__ aw = reinterpret_cast<const float*>(p.aw);
   const T* __restrict__ gout = reinterpret_cast<const T*>(p.grad_out);
@@ -70,11 +106,10 @@ __global__ void __launch_bounds__(kThreads) msda_bwd_vec_kernel(const Params p) 
 
 #pragma unroll
     for (int r0 = 0; r0 < (kStatic ? LT * PT : LP); r0 += G) {
-      // ---- producer ---------------------------------------------------------------------------
+      // ---- producer: lane j prepares point r0 + j -----------------------------------------------
       const int pi = r0 + j;
       const bool mine = (pi < LP) && active;
-      int off = 0, rowstride = 0;
-      unsigned mask = 0u;
+      unsigned tokf = 0u, wrow = 0u;  // clamped top-left token index << 4 | (rl, rh, cl, ch) validity bits
       float lh = 0.f, lw = 0.f, a = 0.f, fH = 0.f, fW = 0.f;
       if (mine) {
         const int l = pi / P;
@@ -82,57 +117,77 @@ __global__ void __launch_bounds__(kThreads) msda_bwd_vec_kernel(const Params p) 
         const float2 xy = __ldg(reinterpret_cast<const float2*>(loc_pair) + pi);
         a = __ldg(aw_pair + pi);
         const PointGeom<float> g = point_geom<float>(xy.x, xy.y, H, W);
-        lh = g.lh; lw = g.lw; mask = g.mask;
-        off = (sStart[l] + g.h_low * W + g.w_low) * MD;
-        rowstride = W * MD;
+        lh = g.lh; lw = g.lw;
+        const unsigned rl = (g.mask & 3u) != 0u, rh = (g.mask & 12u) != 0u;  // row h_low / h_high readable
+        const unsigned cl = (g.mask & 5u) != 0u, ch = (g.mask & 10u) != 0u;  // col w_low / w_high readable
+        const int hl = max(g.h_low, 0), wl = max(g.w_low, 0);
+        tokf = ((unsigned)(sStart[l] + hl * W + wl) << 4) | rl | (rh << 1) | (cl << 2) | (ch << 3);
+        wrow = (unsigned)W;
         fH = (float)H; fW = (float)W;
       }
+      float part[kTranspose ? 3 * G : 3];
       float my_ga = 0.f, my_gw = 0.f, my_gh = 0.f;
-      // ---- consumers --------------------------------------------------------------------------
+      // ---- consumers ------------------------------------------------------------------------------
 #pragma unroll
       for (int jj = 0; jj < G; ++jj) {
+        float s_a = 0.f, s_w = 0.f, s_h = 0.f;
         if (r0 + jj < LP) {  // uniform
-          const unsigned mk = __shfl_sync(0xffffffffu, mask, jj, G);
-          const int o = __shfl_sync(0xffffffffu, off, jj, G);
-          const int rs = __shfl_sync(0xffffffffu, rowstride, jj, G);
+          const unsigned tf = __shfl_sync(0xffffffffu, tokf, jj, G);
           const float flh = __shfl_sync(0xffffffffu, lh, jj, G);
           const float flw = __shfl_sync(0xffffffffu, lw, jj, G);
           const float fa = __shfl_sync(0xffffffffu, a, jj, G);
-          float s_a = 0.f, s_w = 0.f, s_h = 0.f;
-          if (mk != 0u) {
-            const float hh = 1.f - flh, hw = 1.f - flw;
-            const float w1 = hh * hw, w2 = hh * flw, w3 = flh * hw, w4 = flh * flw;
-            const T* p1 = vbase + o;
-            const V v1 = (mk & 1u) ? V::load(p1) : V::zero();
-            const V v2 = (mk & 2u) ? V::load(p1 + MD) : V::zero();
-            const V v3 = (mk & 4u) ? V::load(p1 + rs) : V::zero();
-            const V v4 = (mk & 8u) ? V::load(p1 + rs + MD) : V::zero();
-            float t[kCpl];
-#pragma unroll
-            for (int c = 0; c < kCpl; ++c) {
-              const float g = go.v[c];
-              const float val = w1 * v1.v[c] + w2 * v2.v[c] + w3 * v3.v[c] + w4 * v4.v[c];
-              const float dw = hh * (v2.v[c] - v1.v[c]) + flh * (v4.v[c] - v3.v[c]);
-              const float dh = hw * (v3.v[c] - v1.v[c]) + flw * (v4.v[c] - v2.v[c]);
-              s_a = fmaf(g, val, s_a);
-              s_w = fmaf(g, dw, s_w);
-              s_h = fmaf(g, dh, s_h);
-              t[c] = g * fa;  // top_grad_value
-            }
-            float* g1 = gvbase + o;
-#pragma unroll
-            for (int c0 = 0; c0 < kCpl; c0 += 4) {
-              if (mk & 1u) red_add_v4(g1 + c0, w1 * t[c0], w1 * t[c0 + 1], w1 * t[c0 + 2], w1 * t[c0 + 3]);
-              if (mk & 2u) red_add_v4(g1 + MD + c0, w2 * t[c0], w2 * t[c0 + 1], w2 * t[c0 + 2], w2 * t[c0 + 3]);
-              if (mk & 4u) red_add_v4(g1 + rs + c0, w3 * t[c0], w3 * t[c0 + 1], w3 * t[c0 + 2], w3 * t[c0 + 3]);
-              if (mk & 8u) red_add_v4(g1 + rs + MD + c0, w4 * t[c0], w4 * t[c0 + 1], w4 * t[c0 + 2], w4 * t[c0 + 3]);
-            }
+          unsigned wr;
+          if (kStatic) {
+            wr = rsl[(r0 + jj) / (kStatic ? PT : 1)];
+          } else {
+            wr = __shfl_sync(0xffffffffu, wrow, jj, G);
           }
+          const bool rl = tf & 1u, rh = tf & 2u, cl = tf & 4u, ch = tf & 8u;
+          const unsigned tok = tf >> 4;
+          const unsigned dcol = (cl && ch) ? 1u : 0u;  // in tokens
+          const unsigned drow = (rl && rh) ? wr : 0u;
+          const unsigned t1 = tok, t2 = tok + dcol, t3 = tok + drow, t4 = tok + drow + dcol;
+          const V v1 = V::load(reinterpret_cast<const T*>(vb + t1 * MDb));
+          const V v2 = V::load(reinterpret_cast<const T*>(vb + t2 * MDb));
+          const V v3 = V::load(reinterpret_cast<const T*>(vb + t3 * MDb));
+          const V v4 = V::load(reinterpret_cast<const T*>(vb + t4 * MDb));
+          float u1 = 0.f, u2 = 0.f, u3 = 0.f, u4 = 0.f;
+#pragma unroll
+          for (int c = 0; c < kCpl; ++c) {
+            u1 = fmaf(go.v[c], v1.v[c], u1);
+            u2 = fmaf(go.v[c], v2.v[c], u2);
+            u3 = fmaf(go.v[c], v3.v[c], u3);
+            u4 = fmaf(go.v[c], v4.v[c], u4);
+          }
+          const bool m1 = rl && cl, m2 = rl && ch, m3 = rh && cl, m4 = rh && ch;
+          u1 = m1 ? u1 : 0.f; u2 = m2 ? u2 : 0.f; u3 = m3 ? u3 : 0.f; u4 = m4 ? u4 : 0.f;
+          const float hh = 1.f - flh, hw = 1.f - flw;
+          const float w1 = hh * hw, w2 = hh * flw, w3 = flh * hw, w4 = flh * flw;
+          s_a = w1 * u1 + w2 * u2 + w3 * u3 + w4 * u4;
+          s_w = hh * (u2 - u1) + flh * (u4 - u3);
+          s_h = hw * (u3 - u1) + flw * (u4 - u2);
+          // scatter: grad_value[corner k] += (w_k * attn) * grad_out
+          const float a1 = w1 * fa, a2 = w2 * fa, a3 = w3 * fa, a4 = w4 * fa;
+#pragma unroll
+          for (int c0 = 0; c0 < kCpl; c0 += 4) {
+            if (m1) red_add_v4(reinterpret_cast<float*>(gvb + t1 * MDf) + c0, a1 * go.v[c0], a1 * go.v[c0 + 1], a1 * go.v[c0 + 2], a1 * go.v[c0 + 3]);
+            if (m2) red_add_v4(reinterpret_cast<float*>(gvb + t2 * MDf) + c0, a2 * go.v[c0], a2 * go.v[c0 + 1], a2 * go.v[c0 + 2], a2 * go.v[c0 + 3]);
+            if (m3) red_add_v4(reinterpret_cast<float*>(gvb + t3 * MDf) + c0, a3 * go.v[c0], a3 * go.v[c0 + 1], a3 * go.v[c0 + 2], a3 * go.v[c0 + 3]);
+            if (m4) red_add_v4(reinterpret_cast<float*>(gvb + t4 * MDf) + c0, a4 * go.v[c0], a4 * go.v[c0 + 1], a4 * go.v[c0 + 2], a4 * go.v[c0 + 3]);
+          }
+        }
+        if constexpr (kTranspose) {
+          part[3 * jj + 0] = s_a; part[3 * jj + 1] = s_w; part[3 * jj + 2] = s_h;
+        } else if (r0 + jj < LP) {
           s_a = group_sum<G>(s_a);
           s_w = group_sum<G>(s_w);
           s_h = group_sum<G>(s_h);
           if (j == jj) { my_ga = s_a; my_gw = s_w; my_gh = s_h; }
         }
+      }
+      if constexpr (kTranspose) {
+        group_transpose_sum<G, 3 * G>(part, j);
+        my_ga = part[0]; my_gw = part[1]; my_gh = part[2];
       }
       if (mine) {
         gaw[pair * LP + pi] = my_ga;
@@ -229,37 +284,46 @@ __global__ void __launch_bounds__(kThreads) msda_cvt_f32_bf16_kernel(const float
 // ---------------------------------------------------------------------------------------------
 // Launchers
 // ---------------------------------------------------------------------------------------------
-template <typename T, int G>
-static cudaError_t launch_vec_g(const Params& p, dim3 grid, cudaStream_t s) {
+template <typename T, int G, int MINB>
+static cudaError_t launch_vec_gm(const Params& p, dim3 grid, cudaStream_t s) {
   if (p.L == 3 && p.P == 4) {
-    msda_bwd_vec_kernel<T, G, 3, 4><<<grid, kThreads, 0, s>>>(p);
+    msda_bwd_vec_kernel<T, G, 3, 4, MINB><<<grid, kThreads, 0, s>>>(p);
   } else if (p.L == 1 && p.P == 4) {
-    msda_bwd_vec_kernel<T, G, 1, 4><<<grid, kThreads, 0, s>>>(p);
+    msda_bwd_vec_kernel<T, G, 1, 4, MINB><<<grid, kThreads, 0, s>>>(p);
   } else {
-    msda_bwd_vec_kernel<T, G, 0, 0><<<grid, kThreads, 0, s>>>(p);
+    msda_bwd_vec_kernel<T, G, 0, 0, MINB><<<grid, kThreads, 0, s>>>(p);
   }
   return cudaGetLastError();
 }
 
+template <typename T, int G>
+static cudaError_t launch_vec_g(const Params& p, int minb, dim3 grid, cudaStream_t s) {
+  switch (minb) {
+    case 2: return launch_vec_gm<T, G, 2>(p, grid, s);
+    case 4: return launch_vec_gm<T, G, 4>(p, grid, s);
+    default: return launch_vec_gm<T, G, 3>(p, grid, s);
+  }
+}
+
 template <typename T>
-static cudaError_t launch_vec(const Params& p, int G, dim3 grid, cudaStream_t s) {
+static cudaError_t launch_vec(const Params& p, int G, int minb, dim3 grid, cudaStream_t s) {
   switch (G) {
-    case 2: return launch_vec_g<T, 2>(p, grid, s);
-    case 4: return launch_vec_g<T, 4>(p, grid, s);
-    case 8: return launch_vec_g<T, 8>(p, grid, s);
-    case 16: return launch_vec_g<T, 16>(p, grid, s);
-    case 32: return launch_vec_g<T, 32>(p, grid, s);
+    case 2: return launch_vec_gm<T, 2, 3>(p, grid, s);
+    case 4: return launch_vec_g<T, 4>(p, minb, grid, s);
+    case 8: return launch_vec_g<T, 8>(p, minb, grid, s);
+    case 16: return launch_vec_g<T, 16>(p, minb, grid, s);
+    case 32: return launch_vec_gm<T, 32, 3>(p, grid, s);
     default: return cudaErrorInvalidValue;
   }
 }
 
 // `p.grad_value` must point at the ACCUMULATOR (T storage for f32/f64, fp32 scratch for bf16),
 // already zero-filled on `s`.
-cudaError_t launch_backward(const Params& p, int dtype, bool vec_ok, int G, cudaStream_t s) {
+cudaError_t launch_backward(const Params& p, int dtype, bool vec_ok, int G, int minb, cudaStream_t s) {
   const dim3 grid((unsigned)((size_t)p.N * p.nchunk * p.M));
   if (vec_ok) {
-    if (dtype == MSDA_F32) return launch_vec<float>(p, G, grid, s);
-    return launch_vec<__nv_bfloat16>(p, G, grid, s);
+    if (dtype == MSDA_F32) return launch_vec<float>(p, G, minb, grid, s);
+    return launch_vec<__nv_bfloat16>(p, G, minb, grid, s);
   }
   switch (dtype) {
     case MSDA_F32: msda_bwd_generic_kernel<float, float, float><<<grid, kThreads, 0, s>>>(p); break;

@@ -80,6 +80,42 @@ __device__ __forceinline__ PointGeom<F> point_geom(F loc_w, F loc_h, int H, int 
 }
 
 // ---------------------------------------------------------------------------------------------
+// A sampling point prepared for the vector kernels: the four corner rows are CLAMPED into the level
+// so they can be gathered without predicates; corners the reference does not read get weight 0
+// (forward) / mask bit 0 (backward), which reproduces its zero padding exactly for finite inputs.
+//   offf    byte offset of the clamped (h_low, w_low) row inside the (b, m) slab, 16-byte aligned,
+//           with flags in the low bits: bit0 = the right-hand corner is a different token,
+//           bit1 = the lower corners are a different row, bit2 = the sample passed the bounds test
+//   rowstep bytes between rows of this level (W * M * D * sizeof(T))
+// ---------------------------------------------------------------------------------------------
+struct PointTap {
+  unsigned offf, rowstep;
+  float w[4];
+};
+
+__device__ __forceinline__ unsigned tap_offset(const PointGeom<float>& g, int H, int W, int start,
+                                               unsigned MDb) {
+  const int hl = max(g.h_low, 0), hh = min(g.h_low + 1, H - 1);
+  const int wl = max(g.w_low, 0), wh = min(g.w_low + 1, W - 1);
+  return (unsigned)(start + hl * W + wl) * MDb | (unsigned)(wh != wl) | ((unsigned)(hh != hl) << 1) |
+         ((unsigned)(g.mask != 0u) << 2);
+}
+
+__device__ __forceinline__ PointTap point_tap(float x, float y, float a, int H, int W, int start,
+                                              unsigned MDb) {
+  const PointGeom<float> g = point_geom<float>(x, y, H, W);
+  const float hh = 1.f - g.lh, hw = 1.f - g.lw;
+  PointTap t;
+  t.w[0] = (g.mask & 1u) ? (hh * hw) * a : 0.f;
+  t.w[1] = (g.mask & 2u) ? (hh * g.lw) * a : 0.f;
+  t.w[2] = (g.mask & 4u) ? (g.lh * hw) * a : 0.f;
+  t.w[3] = (g.mask & 8u) ? (g.lh * g.lw) * a : 0.f;
+  t.offf = tap_offset(g, H, W, start, MDb);
+  t.rowstep = (unsigned)W * MDb;
+  return t;
+}
+
+// ---------------------------------------------------------------------------------------------
 // 16-byte channel vectors. One lane owns kCpl consecutive channels of a head:
 //   float          : 4 channels  (LDG.E.128)
 //   __nv_bfloat16  : 8 channels  (LDG.E.128), widened to fp32 in registers

@@ -6,9 +6,12 @@
 //   * a CTA owns (batch b, head m, a chunk of consecutive queries) so that the value rows its
 //     warps gather stay hot in L1 (consecutive queries are spatial neighbours in the adapter),
 //   * a group of G lanes owns one (b,q,m): each lane keeps 16 bytes of channels (4 fp32 / 8 bf16),
-//     so a warp serves 32/G queries at once and every gather is an LDG.E.128,
-//   * the coordinates / bilinear weights of a point are computed ONCE, by one lane of the group,
-//     pre-multiplied with the attention weight, and broadcast with warp shuffles,
+//     so a warp serves 32/G queries at once and every gather is an LDG.E.128 that covers whole
+//     128-byte lines (one L1 wavefront per corner row),
+//   * the geometry of a point is computed ONCE, by one lane of the group: corner rows are clamped
+//     into the level (so the four gathers need no predicate and no zero-fill), the bilinear weights
+//     are pre-multiplied with the attention weight and zeroed for corners the reference skips, and
+//     the lot is broadcast with 5 warp shuffles (packed offset+flags, 4 weights),
 //   * out is written exactly once (no at::zeros memset as in ms_deform_attn_cuda.cu:54).
 #include "msda_common.cuh"
 
@@ -16,10 +19,10 @@ namespace msda {
 
 // ---------------------------------------------------------------------------------------------
 // Vector kernel. T = float | __nv_bfloat16, G = lanes per (b,q,m) (D = G * Vec<T>::kCpl),
-// LT/PT = compile-time levels / points (0,0 = runtime).
+// LT/PT = compile-time levels / points (0,0 = runtime), MINB = min resident CTAs per SM.
 // ---------------------------------------------------------------------------------------------
-template <typename T, int G, int LT, int PT>
-__global__ void __launch_bounds__(kThreads) msda_fwd_vec_kernel(const Params p) {
+template <typename T, int G, int LT, int PT, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) msda_fwd_vec_kernel(const Params p) {
   using V = Vec<T>;
   constexpr int kCpl = V::kCpl;
   constexpr int kGpw = 32 / G;  // (b,q,m) groups per warp
@@ -29,6 +32,7 @@ __global__ void __launch_bounds__(kThreads) msda_fwd_vec_kernel(const Params p) 
   const int P = kStatic ? PT : p.P;
   const int LP = L * P;
   const int MD = p.M * p.D;
+  const unsigned MDb = (unsigned)MD * (unsigned)sizeof(T);  // bytes between neighbouring tokens
 
   __shared__ int sH[kMaxLevels], sW[kMaxLevels], sStart[kMaxLevels];
   if (threadIdx.x < L) {
@@ -38,12 +42,17 @@ __global__ void __launch_bounds__(kThreads) msda_fwd_vec_kernel(const Params p) 
   }
   __syncthreads();
 
+  unsigned rsl[kStatic ? LT : 1];  // bytes between rows, per level (registers; static indexing only)
+#pragma unroll
+  for (int l = 0; l < (kStatic ? LT : 1); ++l) rsl[l] = (unsigned)sW[l] * MDb;
+
   const BlockCoord bc = block_coord(p);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = lane / G, j = lane % G;
 
-  const T* __restrict__ vbase =
-      reinterpret_cast<const T*>(p.value) + (size_t)bc.b * p.S * MD + bc.m * p.D + j * kCpl;
+  // CTA-uniform slab base (batch b, head m) + this lane's 16 bytes inside a D-row
+  const char* __restrict__ vb = reinterpret_cast<const char*>(p.value) +
+                                ((size_t)bc.b * p.S * MD + (size_t)bc.m * p.D) * sizeof(T) + j * 16;
   const float* __restrict__ loc = reinterpret_cast<const float*>(p.loc);
   const float* __restrict__ aw = reinterpret_cast<const float*>(p.aw);
   T* __restrict__ out = reinterpret_cast<T*>(p.out);
@@ -61,43 +70,45 @@ __global__ void __launch_bounds__(kThreads) msda_fwd_vec_kernel(const Params p) 
     for (int r0 = 0; r0 < (kStatic ? LT * PT : LP); r0 += G) {
       // ---- producer: lane j prepares point r0 + j --------------------------------------------
       const int pi = r0 + j;
-      int off = 0, rowstride = 0;
-      float w1 = 0.f, w2 = 0.f, w3 = 0.f, w4 = 0.f;
+      PointTap tap;
+      tap.offf = 0u; tap.rowstep = 0u;
+      tap.w[0] = tap.w[1] = tap.w[2] = tap.w[3] = 0.f;
       if (pi < LP && active) {
         const int l = pi / P;
-        const int H = sH[l], W = sW[l];
         const float2 xy = __ldg(reinterpret_cast<const float2*>(loc_pair) + pi);
         const float a = __ldg(aw_pair + pi);
-        const PointGeom<float> g = point_geom<float>(xy.x, xy.y, H, W);
-        const float hh = 1.f - g.lh, hw = 1.f - g.lw;
-        w1 = (g.mask & 1u) ? (hh * hw) * a : 0.f;
-        w2 = (g.mask & 2u) ? (hh * g.lw) * a : 0.f;
-        w3 = (g.mask & 4u) ? (g.lh * hw) * a : 0.f;
-        w4 = (g.mask & 8u) ? (g.lh * g.lw) * a : 0.f;
-        off = (sStart[l] + g.h_low * W + g.w_low) * MD;
-        rowstride = W * MD;
+        tap = point_tap(xy.x, xy.y, a, sH[l], sW[l], sStart[l], MDb);
       }
       // ---- consumers: every lane of the group gathers its 16 bytes for each prepared point ----
 #pragma unroll
       for (int jj = 0; jj < G; ++jj) {
         if (r0 + jj < LP) {  // uniform
-          const int o = __shfl_sync(0xffffffffu, off, jj, G);
-          const int rs = __shfl_sync(0xffffffffu, rowstride, jj, G);
-          const float a1 = __shfl_sync(0xffffffffu, w1, jj, G);
-          const float a2 = __shfl_sync(0xffffffffu, w2, jj, G);
-          const float a3 = __shfl_sync(0xffffffffu, w3, jj, G);
-          const float a4 = __shfl_sync(0xffffffffu, w4, jj, G);
-          const T* p1 = vbase + o;
-          const V v1 = (a1 != 0.f) ? V::load(p1) : V::zero();
-          const V v2 = (a2 != 0.f) ? V::load(p1 + MD) : V::zero();
-          const V v3 = (a3 != 0.f) ? V::load(p1 + rs) : V::zero();
-          const V v4 = (a4 != 0.f) ? V::load(p1 + rs + MD) : V::zero();
+          const unsigned of = __shfl_sync(0xffffffffu, tap.offf, jj, G);
+          const float a1 = __shfl_sync(0xffffffffu, tap.w[0], jj, G);
+          const float a2 = __shfl_sync(0xffffffffu, tap.w[1], jj, G);
+          const float a3 = __shfl_sync(0xffffffffu, tap.w[2], jj, G);
+          const float a4 = __shfl_sync(0xffffffffu, tap.w[3], jj, G);
+          unsigned rs;
+          if (kStatic) {
+            rs = rsl[(r0 + jj) / (kStatic ? PT : 1)];  // level is a compile-time constant here
+          } else {
+            rs = __shfl_sync(0xffffffffu, tap.rowstep, jj, G);
+          }
+          const unsigned o1 = of & ~15u;
+          const unsigned dcol = (of & 1u) ? MDb : 0u;
+          const unsigned drow = (of & 2u) ? rs : 0u;
+          const V v1 = V::load(reinterpret_cast<const T*>(vb + o1));
+          const V v2 = V::load(reinterpret_cast<const T*>(vb + (o1 + dcol)));
+          const V v3 = V::load(reinterpret_cast<const T*>(vb + (o1 + drow)));
+          const V v4 = V::load(reinterpret_cast<const T*>(vb + (o1 + drow + dcol)));
+          if (of & 4u) {  // the reference skips out-of-range samples entirely (:288)
 #pragma unroll
-          for (int c = 0; c < kCpl; ++c) {
-            acc.v[c] = fmaf(a1, v1.v[c], acc.v[c]);
-            acc.v[c] = fmaf(a2, v2.v[c], acc.v[c]);
-            acc.v[c] = fmaf(a3, v3.v[c], acc.v[c]);
-            acc.v[c] = fmaf(a4, v4.v[c], acc.v[c]);
+            for (int c = 0; c < kCpl; ++c) {
+              acc.v[c] = fmaf(a1, v1.v[c], acc.v[c]);
+              acc.v[c] = fmaf(a2, v2.v[c], acc.v[c]);
+              acc.v[c] = fmaf(a3, v3.v[c], acc.v[c]);
+              acc.v[c] = fmaf(a4, v4.v[c], acc.v[c]);
+            }
           }
         }
       }
@@ -152,33 +163,42 @@ __global__ void __launch_bounds__(kThreads) msda_fwd_generic_kernel(const Params
 // ---------------------------------------------------------------------------------------------
 // Launchers
 // ---------------------------------------------------------------------------------------------
-template <typename T, int G>
-static cudaError_t launch_vec_g(const Params& p, dim3 grid, cudaStream_t s) {
+template <typename T, int G, int MINB>
+static cudaError_t launch_vec_gm(const Params& p, dim3 grid, cudaStream_t s) {
   if (p.L == 3 && p.P == 4) {
-    msda_fwd_vec_kernel<T, G, 3, 4><<<grid, kThreads, 0, s>>>(p);
+    msda_fwd_vec_kernel<T, G, 3, 4, MINB><<<grid, kThreads, 0, s>>>(p);
   } else if (p.L == 1 && p.P == 4) {
-    msda_fwd_vec_kernel<T, G, 1, 4><<<grid, kThreads, 0, s>>>(p);
+    msda_fwd_vec_kernel<T, G, 1, 4, MINB><<<grid, kThreads, 0, s>>>(p);
   } else {
-    msda_fwd_vec_kernel<T, G, 0, 0><<<grid, kThreads, 0, s>>>(p);
+    msda_fwd_vec_kernel<T, G, 0, 0, MINB><<<grid, kThreads, 0, s>>>(p);
   }
   return cudaGetLastError();
 }
 
+template <typename T, int G>
+static cudaError_t launch_vec_g(const Params& p, int minb, dim3 grid, cudaStream_t s) {
+  switch (minb) {
+    case 3: return launch_vec_gm<T, G, 3>(p, grid, s);
+    case 6: return launch_vec_gm<T, G, 6>(p, grid, s);
+    default: return launch_vec_gm<T, G, 4>(p, grid, s);
+  }
+}
+
 template <typename T>
-static cudaError_t launch_vec(const Params& p, int G, dim3 grid, cudaStream_t s) {
+static cudaError_t launch_vec(const Params& p, int G, int minb, dim3 grid, cudaStream_t s) {
   switch (G) {
-    case 2: return launch_vec_g<T, 2>(p, grid, s);
-    case 4: return launch_vec_g<T, 4>(p, grid, s);
-    case 8: return launch_vec_g<T, 8>(p, grid, s);
-    case 16: return launch_vec_g<T, 16>(p, grid, s);
-    case 32: return launch_vec_g<T, 32>(p, grid, s);
+    case 2: return launch_vec_gm<T, 2, 4>(p, grid, s);
+    case 4: return launch_vec_g<T, 4>(p, minb, grid, s);
+    case 8: return launch_vec_g<T, 8>(p, minb, grid, s);
+    case 16: return launch_vec_g<T, 16>(p, minb, grid, s);
+    case 32: return launch_vec_gm<T, 32, 4>(p, grid, s);
     default: return cudaErrorInvalidValue;
   }
 }
 
-// Returns true when the vector kernel supports (dtype, D): D*sizeof(T) is a multiple of 16 bytes and
+// Returns true when the vector kernels support (dtype, D): D*sizeof(T) is a multiple of 16 bytes and
 // D / (16/sizeof(T)) is a power of two in [2, 32].
-bool fwd_vec_supported(int dtype, int D, int* G_out) {
+bool vec_supported(int dtype, int D, int* G_out) {
   int cpl = dtype == MSDA_F32 ? 4 : dtype == MSDA_BF16 ? 8 : 0;
   if (cpl == 0 || D % cpl != 0) return false;
   const int G = D / cpl;
@@ -187,11 +207,11 @@ bool fwd_vec_supported(int dtype, int D, int* G_out) {
   return true;
 }
 
-cudaError_t launch_forward(const Params& p, int dtype, bool vec_ok, int G, cudaStream_t s) {
+cudaError_t launch_forward(const Params& p, int dtype, bool vec_ok, int G, int minb, cudaStream_t s) {
   const dim3 grid((unsigned)((size_t)p.N * p.nchunk * p.M));
   if (vec_ok) {
-    if (dtype == MSDA_F32) return launch_vec<float>(p, G, grid, s);
-    return launch_vec<__nv_bfloat16>(p, G, grid, s);
+    if (dtype == MSDA_F32) return launch_vec<float>(p, G, minb, grid, s);
+    return launch_vec<__nv_bfloat16>(p, G, minb, grid, s);
   }
   switch (dtype) {
     case MSDA_F32: msda_fwd_generic_kernel<float, float><<<grid, kThreads, 0, s>>>(p); break;
