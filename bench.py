@@ -105,56 +105,90 @@ def adapter_inputs(name, N, M, D, Lq, shapes, seed, dtype):
 # clocks sampling during the timed region (B200_PROFILING.md recipe)
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
-    FIELDS = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    """SM clock + throttle reasons sampled DURING the timed region. NVML polled from a thread every ~2 ms
+    (the timed region is tens of ms); falls back to `nvidia-smi -lms` when pynvml is unavailable."""
+    SMI_FIELDS = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+                  'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.samples = []
-        self.proc = None
+        self.samples = []   # (time, sm_mhz, reasons bitmask or None)
+        self.max_mhz = None
+        self.stop_flag = False
         self.thread = None
+        self.proc = None
+        self.nvml = None
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(
-                ['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.FIELDS, '--format=csv,noheader,nounits',
-                 '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                ['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.SMI_FIELDS, '--format=csv,noheader,nounits',
+                 '-lms', '20'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read_smi, daemon=True)
+            self.thread.start()
         except OSError:
             self.proc = None
-            return
-        self.thread = threading.Thread(target=self._read, daemon=True)
-        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.samples.append((time.time(), line.strip()))
+    def _poll_nvml(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                try:
+                    reasons = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    reasons = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.samples.append((time.time(), mhz, reasons))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        inside = [s for (t, s) in self.samples if t0 <= t <= t1 + 0.1] or [s for (_, s) in self.samples]
-        mhz, mx, reasons = [], None, set()
+    def _read_smi(self):
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for s in inside:
-            parts = [x.strip() for x in s.split(',')]
+        for line in self.proc.stdout:
+            parts = [x.strip() for x in line.split(',')]
             if len(parts) < 6:
                 continue
             try:
-                mhz.append(float(parts[0]))
-                mx = float(parts[1])
+                mhz = float(parts[0])
+                self.max_mhz = float(parts[1])
             except ValueError:
                 continue
-            for n, v in zip(names, parts[2:6]):
-                if v.lower().startswith('active'):
-                    reasons.add(n)
-        return {'sm_mhz': statistics.median(mhz) if mhz else None, 'sm_max_mhz': mx,
-                'reasons': sorted(reasons), 'samples': len(mhz)}
+            self.samples.append((time.time(), mhz, [n for n, v in zip(names, parts[2:6]) if v.lower().startswith('active')]))
+
+    def stop(self, t0, t1):
+        self.stop_flag = True
+        if self.proc is not None:
+            time.sleep(0.05)
+            self.proc.terminate()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': ['no clock samples'], 'samples': 0}
+        inside = [s for s in self.samples if t0 <= s[0] <= t1] or self.samples[-3:]
+        reasons = set()
+        for _, _, r in inside:
+            if isinstance(r, list):
+                reasons.update(r)
+            elif r is not None and self.nvml is not None:
+                n = self.nvml
+                for name, bit in (('hw_slowdown', 0x8), ('sw_thermal_slowdown', 0x20), ('hw_thermal_slowdown', 0x40),
+                                  ('sw_power_cap', 0x4)):
+                    if r & bit:
+                        reasons.add(name)
+        return {'sm_mhz': statistics.median([s[1] for s in inside]), 'sm_max_mhz': self.max_mhz,
+                'reasons': sorted(reasons), 'samples': len(inside), 'source': 'nvml' if self.nvml else 'nvidia-smi'}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -289,7 +323,7 @@ def run_ours(args):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-        time.sleep(0.25)
+        time.sleep(0.05)
     launches0 = _cabi.launch_count()
     barrier()
     t0 = time.time()

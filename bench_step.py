@@ -1,0 +1,260 @@
+#!/usr/bin/env python
+"""bench_step.py — model-level img/s around the MSDeformAttn hot path (BASELINE.json configs[2], [4]).
+
+    python bench_step.py --variant B --mode train --batch 2            # 1 GPU
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 bench_step.py --gpus 8 ...
+    python bench_step.py --variant L --mode infer --image 1024 --batch 1 --amp   # HTC++-shape backbone inference
+
+What runs. The adapter side is THIS repo's drop-in code (vit_adapter_b200.adapter: deform_inputs,
+SpatialPriorModule, InteractionBlock -> Injector/Extractor -> MSDeformAttn -> sm_100a kernels). The plain ViT
+trunk and the segmentation head are NOT part of the hot path and cannot come from the reference here
+(mmcv/mmseg/timm are absent), so they are re-stated minimally: a pre-norm ViT with
+F.scaled_dot_product_attention and a light multi-scale stand-in head (1x1 lateral convs + fuse + classifier,
+cross-entropy on synthetic labels). The adapter call structure is the reference's ViTAdapter.forward
+(segmentation/mmseg_custom/models/backbones/vit_adapter.py:93-137): 4 Injector + 6 Extractor calls per forward.
+Batch-sharded data parallel: one process per GPU, DDP gradient all-reduce over NCCL, SyncBatchNorm in the
+SPM / output norms as in the reference; per-GPU batch fixed (weak scaling).
+
+`--op ours|ref_cuda` swaps only the sampling core (ours vs the reference's own CUDA kernels from oracle/_ref),
+everything else identical, for an A/B at model level.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+import torch.nn as nn  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+CFG = {
+    # embed, depth, heads, deform_heads, deform_ratio, interaction_indexes, with_cp
+    'S': dict(embed=384, depth=12, heads=6, dheads=6, ratio=1.0, idx=[[0, 2], [3, 5], [6, 8], [9, 11]]),
+    'B': dict(embed=768, depth=12, heads=12, dheads=12, ratio=0.5, idx=[[0, 2], [3, 5], [6, 8], [9, 11]]),
+    'L': dict(embed=1024, depth=24, heads=16, dheads=16, ratio=0.5, idx=[[0, 5], [6, 11], [12, 17], [18, 23]]),
+}
+
+
+class ViTBlock(nn.Module):
+    """Plain pre-norm transformer block (stand-in for timm's Block; dense work -> cuBLAS / SDPA)."""
+
+    def __init__(self, dim, heads, mlp_ratio=4.0):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, eps=1e-6)
+        self.qkv = nn.Linear(dim, dim * 3)
+        self.proj = nn.Linear(dim, dim)
+        self.norm2 = nn.LayerNorm(dim, eps=1e-6)
+        self.fc1 = nn.Linear(dim, int(dim * mlp_ratio))
+        self.fc2 = nn.Linear(int(dim * mlp_ratio), dim)
+        self.heads = heads
+
+    def forward(self, x, H, W):
+        B, N, C = x.shape
+        qkv = self.qkv(self.norm1(x)).view(B, N, 3, self.heads, C // self.heads).permute(2, 0, 3, 1, 4)
+        a = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2])
+        x = x + self.proj(a.transpose(1, 2).reshape(B, N, C))
+        return x + self.fc2(F.gelu(self.fc1(self.norm2(x))))
+
+
+class MiniViTAdapter(nn.Module):
+    def __init__(self, variant, sync_bn, with_cp=False):
+        super().__init__()
+        from vit_adapter_b200.adapter import InteractionBlock, SpatialPriorModule
+        c = CFG[variant]
+        d = c['embed']
+        bn = nn.SyncBatchNorm if sync_bn else nn.BatchNorm2d
+        self.embed = d
+        self.idx = c['idx']
+        self.patch_embed = nn.Conv2d(3, d, 16, 16)
+        self.pos_embed = nn.Parameter(torch.zeros(1, 14 * 14, d))
+        self.blocks = nn.ModuleList([ViTBlock(d, c['heads']) for _ in range(c['depth'])])
+        self.level_embed = nn.Parameter(torch.randn(3, d) * 0.02)
+        self.spm = SpatialPriorModule(inplanes=64, embed_dim=d, norm_layer=bn)
+        self.interactions = nn.ModuleList([
+            InteractionBlock(dim=d, num_heads=c['dheads'], n_points=4, init_values=0., drop_path=0.,
+                             with_cffn=True, cffn_ratio=0.25, deform_ratio=c['ratio'],
+                             extra_extractor=(i == len(self.idx) - 1), with_cp=with_cp)
+            for i in range(len(self.idx))])
+        self.up = nn.ConvTranspose2d(d, d, 2, 2)
+        self.norms = nn.ModuleList([bn(d) for _ in range(4)])
+
+    def forward(self, x):
+        from vit_adapter_b200.adapter import deform_inputs
+        di1, di2 = deform_inputs(x)
+        c1, c2, c3, c4 = self.spm(x)
+        n2, n3 = c2.size(1), c3.size(1)
+        c = torch.cat([c2 + self.level_embed[0], c3 + self.level_embed[1], c4 + self.level_embed[2]], dim=1)
+        x = self.patch_embed(x)
+        bs, dim, H, W = x.shape
+        x = x.flatten(2).transpose(1, 2)
+        pos = F.interpolate(self.pos_embed.reshape(1, 14, 14, dim).permute(0, 3, 1, 2), size=(H, W), mode='bicubic',
+                            align_corners=False).reshape(1, dim, H * W).permute(0, 2, 1)
+        x = x + pos
+        outs = []
+        for i, layer in enumerate(self.interactions):
+            a, b = self.idx[i]
+            x, c = layer(x, c, self.blocks[a:b + 1], di1, di2, H, W)
+            outs.append(x.transpose(1, 2).reshape(bs, dim, H, W))
+        c2, c3, c4 = c[:, :n2], c[:, n2:n2 + n3], c[:, n2 + n3:]
+        c2 = c2.transpose(1, 2).reshape(bs, dim, H * 2, W * 2)
+        c3 = c3.transpose(1, 2).reshape(bs, dim, H, W)
+        c4 = c4.transpose(1, 2).reshape(bs, dim, H // 2, W // 2)
+        c1 = self.up(c2) + c1
+        x1, x2, x3, x4 = outs
+        c1 = c1 + F.interpolate(x1, scale_factor=4, mode='bilinear', align_corners=False)
+        c2 = c2 + F.interpolate(x2, scale_factor=2, mode='bilinear', align_corners=False)
+        c3 = c3 + x3
+        c4 = c4 + F.interpolate(x4, scale_factor=0.5, mode='bilinear', align_corners=False)
+        return [n(f) for n, f in zip(self.norms, (c1, c2, c3, c4))]
+
+
+class StandInHead(nn.Module):
+    """NOT UperNet: a light FPN-style fuse so that every pyramid level receives a gradient."""
+
+    def __init__(self, dim, classes=150, width=256):
+        super().__init__()
+        self.lat = nn.ModuleList([nn.Conv2d(dim, width, 1) for _ in range(4)])
+        self.fuse = nn.Conv2d(width, width, 3, padding=1)
+        self.cls = nn.Conv2d(width, classes, 1)
+
+    def forward(self, feats):
+        size = feats[0].shape[-2:]
+        y = 0
+        for f, l in zip(feats, self.lat):
+            y = y + F.interpolate(l(f), size=size, mode='bilinear', align_corners=False)
+        return self.cls(F.relu(self.fuse(y)))
+
+
+class Net(nn.Module):
+    def __init__(self, variant, sync_bn, with_cp):
+        super().__init__()
+        self.backbone = MiniViTAdapter(variant, sync_bn, with_cp)
+        self.head = StandInHead(self.backbone.embed)
+
+    def forward(self, img):
+        return self.head(self.backbone(img))
+
+
+def use_reference_cuda_core():
+    """Route MSDeformAttn's sampling core to the reference's own CUDA kernels (oracle/_ref) for the A/B."""
+    from oracle import refcuda
+    import vit_adapter_b200.modules.ms_deform_attn as mod
+
+    class RefFn(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, value, shapes, lsi, loc, aw, step):
+            value, loc, aw = value.float().contiguous(), loc.float().contiguous(), aw.float().contiguous()
+            ctx.save_for_backward(value, shapes, lsi, loc, aw)
+            ctx.step = step
+            return refcuda.forward(value, shapes, lsi, loc, aw, step)
+
+        @staticmethod
+        def backward(ctx, go):
+            value, shapes, lsi, loc, aw = ctx.saved_tensors
+            gv, gl, ga = refcuda.backward(value, shapes, lsi, loc, aw, go.float().contiguous(), ctx.step)
+            return gv, None, None, gl, ga, None
+
+    mod.MSDeformAttnFunction = RefFn
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--variant', default='B', choices=sorted(CFG))
+    ap.add_argument('--mode', default='train', choices=['train', 'infer'])
+    ap.add_argument('--image', type=int, default=512)
+    ap.add_argument('--batch', type=int, default=2, help='images per GPU (reference: 2 for B/S, 1 for L)')
+    ap.add_argument('--amp', action='store_true', help='torch.autocast(bfloat16) + bf16 sampling core')
+    ap.add_argument('--with-cp', action='store_true', help='activation checkpointing in Injector/Extractor (L configs)')
+    ap.add_argument('--op', default='ours', choices=['ours', 'ref_cuda'])
+    args = ap.parse_args()
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+
+    import vit_adapter_b200 as vab
+    from vit_adapter_b200 import _cabi
+    if args.op == 'ref_cuda':
+        use_reference_cuda_core()
+    if args.amp:
+        vab.set_amp_value_dtype(torch.bfloat16)
+
+    torch.manual_seed(1234 + rank)
+    net = Net(args.variant, sync_bn=(world > 1), with_cp=args.with_cp).to(dev)
+    n_params = sum(p.numel() for p in net.parameters())
+    n_adapter = sum(p.numel() for n, p in net.named_parameters() if 'interactions' in n or 'spm' in n)
+    model = net
+    if world > 1 and args.mode == 'train':
+        model = nn.parallel.DistributedDataParallel(net, device_ids=[local_rank], gradient_as_bucket_view=True)
+    opt = torch.optim.AdamW(net.parameters(), lr=6e-5, weight_decay=0.01, fused=True) if args.mode == 'train' else None
+    img = torch.randn(args.batch, 3, args.image, args.image, device=dev)
+    lab = torch.randint(0, 150, (args.batch, args.image // 4, args.image // 4), device=dev)
+
+    def step():
+        with torch.autocast('cuda', dtype=torch.bfloat16, enabled=args.amp):
+            if args.mode == 'train':
+                loss = F.cross_entropy(model(img).float(), lab)
+            else:
+                with torch.no_grad():
+                    return model(img)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    if args.mode == 'infer':
+        net.eval()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    l0 = _cabi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _cabi.launch_count() - l0
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank == 0:
+        print(json.dumps({
+            'metric': 'vit_adapter_%s_%s_img_per_s' % (args.variant, args.mode), 'value': world * args.batch * args.steps / (ms * 1e-3),
+            'unit': 'img/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'dtype': 'bf16-autocast' if args.amp else 'f32', 'data': 'synthetic',
+            'op': args.op, 'msda_kernel_launches': launches,
+            'config': {'workload': 'ViT-Adapter-%s backbone (this repo\'s adapter modules + MSDeformAttn) + stand-in head, %dx%d, '
+                                   '%d img/GPU, %s' % (args.variant, args.image, args.image, args.batch, args.mode),
+                       'params_total': n_params, 'params_adapter': n_adapter, 'with_cp': args.with_cp,
+                       'parallelism': 'dp%d (DDP all-reduce over NCCL, SyncBN)' % world if world > 1 else 'single GPU',
+                       'note': 'ViT trunk and head are minimal stand-ins (mmcv/mmseg/timm absent); adapter path is the drop-in code'},
+            'final': float(out.float().mean()) if torch.is_tensor(out) else None,
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -98,6 +98,21 @@ int msda_forward(const msda_dims* dims, int dtype,
                  void* out,
                  void* stream);
 
+/* Forward with the level shapes ALSO available on the host (`spatial_shapes_host`: [L,2] int64 in host
+ * memory, same values as the device tensor; may be NULL, which makes this identical to msda_forward).
+ * Host-known shapes let the library choose kernels that need the level geometry before launch (today: the
+ * opt-in shared-memory forward that stages whole level maps with cp.async). The reference reads the shapes only on the device (ms_deform_im2col_cuda.cuh:274-277); a caller
+ * that built the shapes tensor from Python ints (adapter_modules.py:30-33) has them on the host for free. */
+int msda_forward_ex(const msda_dims* dims, int dtype,
+                    const void* value,
+                    const int64_t* spatial_shapes,
+                    const int64_t* level_start_index,
+                    const void* sampling_loc,
+                    const void* attn_weight,
+                    void* out,
+                    const int64_t* spatial_shapes_host,
+                    void* stream);
+
 /* Bytes of scratch the backward needs for (dims, dtype); 0 when none is needed.
  * (bf16 accumulates grad_value in an fp32 scratch of N*S*M*D floats.) */
 size_t msda_backward_workspace_bytes(const msda_dims* dims, int dtype);
@@ -136,10 +151,15 @@ int msda_debug_point_index(const msda_dims* dims,
 /* Number of kernel launches (ours) issued through this library by the calling process so far. */
 uint64_t msda_launch_count(void);
 
-/* Tuning overrides for benchmarking (0 = built-in heuristic for every field):
- * queries per CTA chunk, and the min-resident-CTAs-per-SM variant of the vector kernels
- * (forward: 3, 4 or 6; backward: 2, 3 or 4). Process-wide; affects subsequent calls. */
-void msda_set_tuning(int32_t fwd_chunk, int32_t bwd_chunk, int32_t fwd_min_ctas, int32_t bwd_min_ctas);
+/* Tuning overrides for benchmarking; value 0 restores the built-in heuristic. Process-wide. Keys:
+ *   "fwd_chunk", "bwd_chunk"        queries per CTA chunk of the L1-path kernels
+ *   "fwd_min_ctas", "bwd_min_ctas"  min-resident-CTAs-per-SM variant (forward 3|4|6, backward 2|3|4)
+ *   "fwd_smem"                      2 = use the shared-memory forward whenever a plan exists (default: never;
+ *                                   measured no faster than the L1 path, see msda_abi.cu plan_forward_smem)
+ *   "fwd_smem_threads"              512 | 1024 threads per CTA of the shared-memory forward
+ *   "fwd_smem_chunks"               query chunks per (batch, head) of the shared-memory forward
+ * Returns 0, or MSDA_E_NULL for an unknown key. */
+int msda_set_tuning(const char* key, int32_t value);
 
 #ifdef __cplusplus
 }

@@ -343,3 +343,45 @@ def test_launch_counter_and_stream():
     assert _cabi.launch_count() == n0 + 1
     want = vab.MSDeformAttnFunction.apply(inp['value'], inp['shapes'], inp['lsi'], inp['loc'], inp['aw'], 64)
     assert torch.equal(out, want)
+
+
+# ---------------------------------------------------------------------------------------------------
+# shared-memory forward (TMA-staged level maps): must be bit-identical to the L1-path forward
+# ---------------------------------------------------------------------------------------------------
+SMEM_SHAPES = [
+    ('B-extractor', 2, 12, 32, 1344, [(16, 16)], 4, 'adapter'),
+    ('B-injector', 2, 12, 32, 256, [(32, 32), (16, 16), (8, 8)], 4, 'adapter'),
+    ('S-injector', 2, 6, 64, 256, [(32, 32), (16, 16), (8, 8)], 4, 'edges'),
+    ('ragged-3lvl', 3, 5, 32, 37, [(7, 9), (3, 4), (2, 5)], 4, 'edges'),
+    ('one-level-big', 1, 2, 32, 700, [(40, 44)], 4, 'uniform'),       # 1760 rows x 128 B = 220 KB: just fits
+    ('too-big-level0', 1, 2, 32, 300, [(64, 64), (20, 20), (3, 3)], 4, 'edges'),  # level 0 stays on the L1 path
+]
+
+
+@pytest.mark.parametrize('cfg', SMEM_SHAPES, ids=[s[0] for s in SMEM_SHAPES])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['f32', 'bf16'])
+@pytest.mark.parametrize('threads', [512, 1024])
+def test_smem_forward_bit_identical(cfg, dtype, threads):
+    _, N, M, D, Lq, shapes, P, dist = cfg
+    g = _cuda(make_inputs(N, M, D, Lq, shapes, P, seed=21, dist=dist))
+    value = g['value'].to(dtype)
+    try:
+        _cabi.set_tuning(fwd_smem=1)
+        want = _cabi.forward(value, g['shapes'], g['lsi'], g['loc'], g['aw'], 64)
+        _cabi.set_tuning(fwd_smem=2, fwd_smem_threads=threads)
+        for chunks in (0, 1, 3):
+            _cabi.set_tuning(fwd_smem_chunks=chunks)
+            got = _cabi.forward(value, g['shapes'], g['lsi'], g['loc'], g['aw'], 64)
+            torch.cuda.synchronize()
+            assert torch.equal(got, want), 'chunks=%d' % chunks
+    finally:
+        _cabi.set_tuning(fwd_smem=0, fwd_smem_threads=0, fwd_smem_chunks=0)
+
+
+def test_host_shapes_cached_no_sync_in_steady_state():
+    g = _cuda(make_inputs(1, 2, 32, 8, [(4, 4)], 4, seed=2))
+    a = _cabi.host_shapes(g['shapes'])
+    b = _cabi.host_shapes(g['shapes'])
+    assert a is b and list(a) == [4, 4]
+    g['shapes'].add_(0)  # in-place op bumps the version counter -> re-read
+    assert _cabi.host_shapes(g['shapes']) is not a

@@ -22,6 +22,9 @@ def main():
     ap.add_argument('--steps', type=int, default=1)
     ap.add_argument('--batch', type=int, default=0)
     ap.add_argument('--ref', action='store_true', help="launch the reference's CUDA kernels instead")
+    ap.add_argument('--smem', type=int, default=0, help='fwd_smem tuning mode (0 auto, 1 off, 2 forced)')
+    ap.add_argument('--smem-threads', type=int, default=0)
+    ap.add_argument('--fwd-only', action='store_true')
     args = ap.parse_args()
     dev = torch.device('cuda', 0)
     batch = args.batch or VARIANTS[args.variant][3]
@@ -32,6 +35,7 @@ def main():
         calls.append({k: v.to(dev) for k, v in h.items()})
     if args.ref:
         from oracle import refcuda
+    _cabi.set_tuning(fwd_smem=args.smem, fwd_smem_threads=args.smem_threads)
     for _ in range(args.warm + args.steps):
         for d in calls:
             if args.ref:
@@ -39,7 +43,8 @@ def main():
                 refcuda.backward(d['value'], d['shapes'], d['lsi'], d['loc'], d['aw'], d['grad_out'])
             else:
                 _cabi.forward(d['value'], d['shapes'], d['lsi'], d['loc'], d['aw'], 64)
-                _cabi.backward(d['value'], d['shapes'], d['lsi'], d['loc'], d['aw'], d['grad_out'], 64)
+                if not args.fwd_only:
+                    _cabi.backward(d['value'], d['shapes'], d['lsi'], d['loc'], d['aw'], d['grad_out'], 64)
     torch.cuda.synchronize()
     print('ok')
 

@@ -16,10 +16,11 @@ bool vec_supported(int dtype, int D, int* G_out);
 cudaError_t launch_forward(const Params& p, int dtype, bool vec_ok, int G, int minb, cudaStream_t s);
 cudaError_t launch_backward(const Params& p, int dtype, bool vec_ok, int G, int minb, cudaStream_t s);
 cudaError_t launch_cvt_f32_bf16(const float* src, void* dst, size_t n, cudaStream_t s);
+cudaError_t launch_forward_smem(const Params& p, const SmemPlan& plan, int dtype, int G, int nt, cudaStream_t s);
 
 static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
-static std::atomic<int> g_qc_fwd{0}, g_qc_bwd{0}, g_minb_fwd{0}, g_minb_bwd{0};
+static std::atomic<int> g_qc_fwd{0}, g_qc_bwd{0}, g_minb_fwd{0}, g_minb_bwd{0}, g_smem_mode{0}, g_smem_nt{0}, g_smem_chunks{0};
 
 static int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -78,6 +79,76 @@ static int pick_chunk(const msda_dims* d, int per_iter, int override_qc) {
   return qc;
 }
 
+// Plan the shared-memory forward from host-known level shapes: the set of levels (smallest first) whose
+// [H*W, D] maps of one head fit the budget, and the number of query chunks per (b, m).
+// MEASURED OUTCOME (profiles/r1_fwd_smem_vs_l1.md): at the adapter shapes this variant is NOT faster than
+// the L1-path forward (B 512^2 bs16 fp32: 94 vs 92 us injector, 132-143 vs 122 us extractor). ncu shows why:
+// an LDS.128 that reads 4 different 128-byte rows costs 4 LSU data-pipe wavefronts, exactly like the
+// LDG.128 that hits in L1, and both kernels sit at ~76% of that pipe (26 wavefronts per 4 points: 16 for
+// the corner rows, 5 shuffles, the rest loc/weight loads and stores). So it is OPT-IN (tuning key
+// "fwd_smem" = 2) and kept for shapes / future kernels where L2 traffic, not the LSU pipe, is the limit.
+static bool plan_forward_smem(const msda_dims* d, int dtype, int G, const int64_t* hs, int nt, SmemPlan* plan,
+                              int* qc_out, int* nchunk_out) {
+  if (!hs) return false;
+  const int L = d->num_levels;
+  if (!((L == 3 || L == 1) && d->num_point == 4)) return false;
+  const int mode = g_smem_mode.load();
+  if (mode != 2) return false;  // opt-in only, see above
+  const unsigned rowB = (unsigned)G * 16u;
+  memset(plan, 0, sizeof(*plan));
+  int64_t start = 0;
+  int order[kMaxLevels];
+  int64_t bytes[kMaxLevels];
+  for (int l = 0; l < L; ++l) {
+    const int64_t H = hs[2 * l], W = hs[2 * l + 1];
+    if (H <= 0 || W <= 0 || H > (1 << 20) || W > (1 << 20)) return false;
+    plan->H[l] = (int)H; plan->W[l] = (int)W; plan->start[l] = (int)start;
+    start += H * W;
+    bytes[l] = H * W * (int64_t)rowB;
+    order[l] = l;
+  }
+  if (start != d->spatial_size) return false;  // host shapes do not describe this value tensor
+  for (int a = 0; a < L; ++a)
+    for (int b = a + 1; b < L; ++b)
+      if (bytes[order[b]] < bytes[order[a]]) { const int t = order[a]; order[a] = order[b]; order[b] = t; }
+  int64_t total = 0;
+  int nstaged = 0;
+  for (int a = 0; a < L; ++a) {
+    const int l = order[a];
+    if (total + bytes[l] > (int64_t)kSmemBudget) break;
+    plan->smem_off[l] = (unsigned)total;
+    plan->staged |= 1u << l;
+    total += bytes[l];
+    ++nstaged;
+  }
+  if (nstaged == 0) return false;
+  plan->total_bytes = (unsigned)total;
+
+  const int per_iter = (nt / 32) * (32 / G);
+  const double bm = (double)d->batch * d->num_heads;
+  const double g_smem = (double)d->num_query * nstaged * d->num_point * 4.0 * rowB;        // per (b,m), bytes
+  const double g_l1 = (double)d->num_query * (L - nstaged) * d->num_point * 4.0 * rowB;
+  const double t_l1_only = (g_smem + g_l1) / 62.0 * ceil(bm / 148.0 / 4.0) ;  // rough; only the ratio below matters
+  (void)t_l1_only;
+  int best_c = 0;
+  double best_t = 1e300;
+  const int max_c = d->num_query / per_iter > 0 ? d->num_query / per_iter : 1;
+  for (int c = 1; c <= 64 && c <= max_c; ++c) {
+    const double waves = ceil(bm * c / 148.0);
+    const double per_cta = (g_smem / 245.0 + g_l1 / 62.0) / c + (double)total / 80.0;
+    const double t = waves * per_cta;
+    if (t < best_t) { best_t = t; best_c = c; }
+  }
+  const int forced = g_smem_chunks.load();
+  if (forced > 0) best_c = forced < max_c ? forced : max_c;
+  if (best_c == 0) return false;
+  int qc = (d->num_query + best_c - 1) / best_c;
+  qc = ((qc + per_iter - 1) / per_iter) * per_iter;
+  *qc_out = qc;
+  *nchunk_out = (d->num_query + qc - 1) / qc;
+  return true;
+}
+
 static void fill_params(Params& p, const msda_dims* d) {
   memset(&p, 0, sizeof(p));
   p.N = d->batch; p.S = d->spatial_size; p.M = d->num_heads; p.D = d->channels;
@@ -112,11 +183,19 @@ const char* msda_last_error(void) { return g_err; }
 
 uint64_t msda_launch_count(void) { return g_launches.load(); }
 
-void msda_set_tuning(int32_t fwd_chunk, int32_t bwd_chunk, int32_t fwd_min_ctas, int32_t bwd_min_ctas) {
-  g_qc_fwd.store(fwd_chunk);
-  g_qc_bwd.store(bwd_chunk);
-  g_minb_fwd.store(fwd_min_ctas);
-  g_minb_bwd.store(bwd_min_ctas);
+int msda_set_tuning(const char* key, int32_t value) {
+  if (!key) return fail(MSDA_E_NULL, "msda_set_tuning: NULL key");
+  std::atomic<int>* slot = nullptr;
+  if (!strcmp(key, "fwd_chunk")) slot = &g_qc_fwd;
+  else if (!strcmp(key, "bwd_chunk")) slot = &g_qc_bwd;
+  else if (!strcmp(key, "fwd_min_ctas")) slot = &g_minb_fwd;
+  else if (!strcmp(key, "bwd_min_ctas")) slot = &g_minb_bwd;
+  else if (!strcmp(key, "fwd_smem")) slot = &g_smem_mode;
+  else if (!strcmp(key, "fwd_smem_threads")) slot = &g_smem_nt;
+  else if (!strcmp(key, "fwd_smem_chunks")) slot = &g_smem_chunks;
+  if (!slot) return fail(MSDA_E_NULL, "msda_set_tuning: unknown key '%s'", key);
+  slot->store(value);
+  return 0;
 }
 
 int msda_check_im2col_step(int32_t batch, int32_t im2col_step) {
@@ -129,6 +208,13 @@ int msda_check_im2col_step(int32_t batch, int32_t im2col_step) {
 int msda_forward(const msda_dims* dims, int dtype, const void* value, const int64_t* spatial_shapes,
                  const int64_t* level_start_index, const void* sampling_loc, const void* attn_weight,
                  void* out, void* stream) {
+  return msda_forward_ex(dims, dtype, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, out,
+                         nullptr, stream);
+}
+
+int msda_forward_ex(const msda_dims* dims, int dtype, const void* value, const int64_t* spatial_shapes,
+                    const int64_t* level_start_index, const void* sampling_loc, const void* attn_weight,
+                    void* out, const int64_t* spatial_shapes_host, void* stream) {
   if (int e = check_dims(dims, dtype)) return e;
   if (!value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight || !out)
     return fail(MSDA_E_NULL, "msda_forward: NULL tensor pointer");
@@ -145,6 +231,18 @@ int msda_forward(const msda_dims* dims, int dtype, const void* value, const int6
   int G = 0;
   bool vec = vec_supported(dtype, p.D, &G) && aligned(value, 16) && aligned(out, 16) &&
              aligned(sampling_loc, 8);
+  if (vec && spatial_shapes_host) {
+    SmemPlan plan;
+    const int nt = g_smem_nt.load() == 1024 ? 1024 : 512;
+    if (plan_forward_smem(dims, dtype, G, spatial_shapes_host, nt, &plan, &p.qc, &p.nchunk)) {
+      const cudaError_t es2 = launch_forward_smem(p, plan, dtype, G, nt, (cudaStream_t)stream);
+      if (es2 == cudaSuccess) {
+        g_launches.fetch_add(1);
+        return 0;
+      }
+      if (es2 != cudaErrorNotSupported) return cuda_fail(es2, "msda_forward (shared-memory variant) launch");
+    }
+  }
   const int per_iter = vec ? kWarps * (32 / G) : kWarps;
   p.qc = pick_chunk(dims, per_iter, g_qc_fwd.load());
   p.nchunk = (p.Lq + p.qc - 1) / p.qc;

@@ -95,6 +95,31 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_bwd_vec_kernel(const Para
   float* __restrict__ gloc = reinterpret_cast<float*>(p.grad_loc);
   float* __restrict__ gaw = reinterpret_cast<float*>(p.grad_aw);
 
+  // Software pipeline over the query loop (static variants): the next iteration's grad_out row, sampling
+  // locations and attention weights are fetched before the current iteration is processed, so their HBM
+  // latency is off the critical path.
+  constexpr int kRounds = kStatic ? (LT * PT + G - 1) / G : 1;
+  float2 nxy[kRounds];
+  float na[kRounds];
+  V ngo = V::zero();
+  auto fetch = [&](int qw_, float2 (&xy_)[kRounds], float (&a_)[kRounds], V& go_) {
+    const int q_ = qw_ + grp;
+    const bool act_ = q_ < bc.q_end;
+    const size_t pair_ = ((size_t)bc.b * p.Lq + (act_ ? q_ : bc.q_begin)) * p.M + bc.m;
+    go_ = act_ ? V::load(gout + pair_ * p.D + j * kCpl) : V::zero();
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+      const int pi_ = r * G + j;
+      xy_[r] = make_float2(0.f, 0.f);
+      a_[r] = 0.f;
+      if (pi_ < LP && act_) {
+        xy_[r] = __ldg(reinterpret_cast<const float2*>(loc + pair_ * LP * 2) + pi_);
+        a_[r] = __ldg(aw + pair_ * LP + pi_);
+      }
+    }
+  };
+  if (kStatic) fetch(bc.q_begin + warp * kGpw, nxy, na, ngo);
+
   for (int qw = bc.q_begin + warp * kGpw; qw < bc.q_end; qw += kWarps * kGpw) {
     const int q = qw + grp;
     const bool active = q < bc.q_end;
@@ -102,7 +127,17 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_bwd_vec_kernel(const Para
     const float* __restrict__ loc_pair = loc + pair * LP * 2;
     const float* __restrict__ aw_pair = aw + pair * LP;
 
-    const V go = active ? V::load(gout + pair * p.D + j * kCpl) : V::zero();
+    V go;
+    float2 cxy[kRounds];
+    float ca[kRounds];
+    if (kStatic) {
+      go = ngo;
+#pragma unroll
+      for (int r = 0; r < kRounds; ++r) { cxy[r] = nxy[r]; ca[r] = na[r]; }
+      if (qw + kWarps * kGpw < bc.q_end) fetch(qw + kWarps * kGpw, nxy, na, ngo);
+    } else {
+      go = active ? V::load(gout + pair * p.D + j * kCpl) : V::zero();
+    }
 
 #pragma unroll
     for (int r0 = 0; r0 < (kStatic ? LT * PT : LP); r0 += G) {
@@ -114,8 +149,14 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_bwd_vec_kernel(const Para
       if (mine) {
         const int l = pi / P;
         const int H = sH[l], W = sW[l];
-        const float2 xy = __ldg(reinterpret_cast<const float2*>(loc_pair) + pi);
-        a = __ldg(aw_pair + pi);
+        float2 xy;
+        if (kStatic) {
+          xy = cxy[r0 / G];
+          a = ca[r0 / G];
+        } else {
+          xy = __ldg(reinterpret_cast<const float2*>(loc_pair) + pi);
+          a = __ldg(aw_pair + pi);
+        }
         const PointGeom<float> g = point_geom<float>(xy.x, xy.y, H, W);
         lh = g.lh; lw = g.lw;
         const unsigned rl = (g.mask & 3u) != 0u, rh = (g.mask & 12u) != 0u;  // row h_low / h_high readable
@@ -147,10 +188,10 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_bwd_vec_kernel(const Para
           const unsigned dcol = (cl && ch) ? 1u : 0u;  // in tokens
           const unsigned drow = (rl && rh) ? wr : 0u;
           const unsigned t1 = tok, t2 = tok + dcol, t3 = tok + drow, t4 = tok + drow + dcol;
-          const V v1 = V::load(reinterpret_cast<const T*>(vb + t1 * MDb));
-          const V v2 = V::load(reinterpret_cast<const T*>(vb + t2 * MDb));
-          const V v3 = V::load(reinterpret_cast<const T*>(vb + t3 * MDb));
-          const V v4 = V::load(reinterpret_cast<const T*>(vb + t4 * MDb));
+          const V v1 = V::load(reinterpret_cast<const T*>(ptr_madd(vb, t1, MDb)));
+          const V v2 = V::load(reinterpret_cast<const T*>(ptr_madd(vb, t2, MDb)));
+          const V v3 = V::load(reinterpret_cast<const T*>(ptr_madd(vb, t3, MDb)));
+          const V v4 = V::load(reinterpret_cast<const T*>(ptr_madd(vb, t4, MDb)));
           float u1 = 0.f, u2 = 0.f, u3 = 0.f, u4 = 0.f;
 #pragma unroll
           for (int c = 0; c < kCpl; ++c) {
@@ -170,10 +211,10 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_bwd_vec_kernel(const Para
           const float a1 = w1 * fa, a2 = w2 * fa, a3 = w3 * fa, a4 = w4 * fa;
 #pragma unroll
           for (int c0 = 0; c0 < kCpl; c0 += 4) {
-            if (m1) red_add_v4(reinterpret_cast<float*>(gvb + t1 * MDf) + c0, a1 * go.v[c0], a1 * go.v[c0 + 1], a1 * go.v[c0 + 2], a1 * go.v[c0 + 3]);
-            if (m2) red_add_v4(reinterpret_cast<float*>(gvb + t2 * MDf) + c0, a2 * go.v[c0], a2 * go.v[c0 + 1], a2 * go.v[c0 + 2], a2 * go.v[c0 + 3]);
-            if (m3) red_add_v4(reinterpret_cast<float*>(gvb + t3 * MDf) + c0, a3 * go.v[c0], a3 * go.v[c0 + 1], a3 * go.v[c0 + 2], a3 * go.v[c0 + 3]);
-            if (m4) red_add_v4(reinterpret_cast<float*>(gvb + t4 * MDf) + c0, a4 * go.v[c0], a4 * go.v[c0 + 1], a4 * go.v[c0 + 2], a4 * go.v[c0 + 3]);
+            if (m1) red_add_v4(reinterpret_cast<float*>(const_cast<char*>(ptr_madd(gvb, t1, MDf))) + c0, a1 * go.v[c0], a1 * go.v[c0 + 1], a1 * go.v[c0 + 2], a1 * go.v[c0 + 3]);
+            if (m2) red_add_v4(reinterpret_cast<float*>(const_cast<char*>(ptr_madd(gvb, t2, MDf))) + c0, a2 * go.v[c0], a2 * go.v[c0 + 1], a2 * go.v[c0 + 2], a2 * go.v[c0 + 3]);
+            if (m3) red_add_v4(reinterpret_cast<float*>(const_cast<char*>(ptr_madd(gvb, t3, MDf))) + c0, a3 * go.v[c0], a3 * go.v[c0 + 1], a3 * go.v[c0 + 2], a3 * go.v[c0 + 3]);
+            if (m4) red_add_v4(reinterpret_cast<float*>(const_cast<char*>(ptr_madd(gvb, t4, MDf))) + c0, a4 * go.v[c0], a4 * go.v[c0 + 1], a4 * go.v[c0 + 2], a4 * go.v[c0 + 3]);
           }
         }
         if constexpr (kTranspose) {

@@ -37,6 +37,16 @@ struct Params {
   int nchunk;              // ceil(Lq / qc)
 };
 
+// Host-made plan for the shared-memory forward (msda_fwd_smem.cu): which levels' [H*W, D] maps of one
+// head are staged in shared memory, and where. Needs the level shapes on the HOST.
+constexpr unsigned kSmemBudget = 226u * 1024u;  // dynamic shared memory a CTA may use (227 KB max per CTA)
+struct SmemPlan {
+  unsigned staged;       // bit l = level l is staged
+  unsigned total_bytes;  // dynamic shared memory = sum of staged maps
+  int H[kMaxLevels], W[kMaxLevels], start[kMaxLevels];
+  unsigned smem_off[kMaxLevels];
+};
+
 // ---------------------------------------------------------------------------------------------
 // Geometry of one sampling point. Mirrors ms_deform_im2col_cuda.cuh:285-288 (coordinate + bounds
 // test) and :38-78 (floor, fractions, per-corner validity).
@@ -173,6 +183,41 @@ struct Vec<__nv_bfloat16> {
     *reinterpret_cast<uint4*>(p) = t;
   }
 };
+
+// 64-bit pointer + 32-bit offset in ONE instruction (IMAD.WIDE.U32) instead of IADD3 + IADD3.X: the
+// gather kernels are issue-bound, and every corner needs its own address.
+__device__ __forceinline__ const char* ptr_add(const char* base, unsigned off) {
+  unsigned long long r;
+  asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(r) : "r"(off), "l"(reinterpret_cast<unsigned long long>(base)));
+  return reinterpret_cast<const char*>(r);
+}
+// base + a * b (a, b 32-bit unsigned), one IMAD.WIDE.U32
+__device__ __forceinline__ const char* ptr_madd(const char* base, unsigned a, unsigned b) {
+  unsigned long long r;
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(reinterpret_cast<unsigned long long>(base)));
+  return reinterpret_cast<const char*>(r);
+}
+
+// acc[0..3] += a1*v1[0..3] + a2*v2[0..3] + a3*v3[0..3] + a4*v4[0..3], executed only when `on` != 0, as 16
+// PREDICATED FFMAs (no branch, no select): an out-of-range sample must contribute exactly nothing even if
+// the clamped rows it aliased hold Inf/NaN. Accumulation order per channel is corner 1,2,3,4.
+__device__ __forceinline__ void fma4x4_if(unsigned on, float* acc, float a1, float a2, float a3, float a4,
+                                          const float* v1, const float* v2, const float* v3, const float* v4) {
+  asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %24, 0;\n\t"
+      "@p fma.rn.f32 %0, %4, %8, %0;\n\t@p fma.rn.f32 %1, %4, %9, %1;\n\t"
+      "@p fma.rn.f32 %2, %4, %10, %2;\n\t@p fma.rn.f32 %3, %4, %11, %3;\n\t"
+      "@p fma.rn.f32 %0, %5, %12, %0;\n\t@p fma.rn.f32 %1, %5, %13, %1;\n\t"
+      "@p fma.rn.f32 %2, %5, %14, %2;\n\t@p fma.rn.f32 %3, %5, %15, %3;\n\t"
+      "@p fma.rn.f32 %0, %6, %16, %0;\n\t@p fma.rn.f32 %1, %6, %17, %1;\n\t"
+      "@p fma.rn.f32 %2, %6, %18, %2;\n\t@p fma.rn.f32 %3, %6, %19, %3;\n\t"
+      "@p fma.rn.f32 %0, %7, %20, %0;\n\t@p fma.rn.f32 %1, %7, %21, %1;\n\t"
+      "@p fma.rn.f32 %2, %7, %22, %2;\n\t@p fma.rn.f32 %3, %7, %23, %3;\n\t}"
+      : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3])
+      : "f"(a1), "f"(a2), "f"(a3), "f"(a4),
+        "f"(v1[0]), "f"(v1[1]), "f"(v1[2]), "f"(v1[3]), "f"(v2[0]), "f"(v2[1]), "f"(v2[2]), "f"(v2[3]),
+        "f"(v3[0]), "f"(v3[1]), "f"(v3[2]), "f"(v3[3]), "f"(v4[0]), "f"(v4[1]), "f"(v4[2]), "f"(v4[3]),
+        "r"(on));
+}
 
 // Vector reduction into global memory: one REDG.E.ADD.F32x4 per 16 bytes (sm_90+ PTX
 // `red.global.add.v4.f32`) instead of the reference's one scalar atomicAdd per channel per corner

@@ -57,12 +57,43 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_fwd_vec_kernel(const Para
   const float* __restrict__ aw = reinterpret_cast<const float*>(p.aw);
   T* __restrict__ out = reinterpret_cast<T*>(p.out);
 
+  // Software pipeline over the query loop: sampling_loc / attn_weight stream from HBM once, so their load
+  // latency (~800 cycles) would sit at the head of every iteration's dependency chain. The static
+  // variants fetch the NEXT iteration's locations and weights before working on the current one.
+  constexpr int kRounds = kStatic ? (LT * PT + G - 1) / G : 1;
+  float2 nxy[kRounds];
+  float na[kRounds];
+  auto fetch = [&](int qw_, float2 (&xy_)[kRounds], float (&a_)[kRounds]) {
+    const int q_ = qw_ + grp;
+    const bool act_ = q_ < bc.q_end;
+    const size_t pair_ = ((size_t)bc.b * p.Lq + (act_ ? q_ : bc.q_begin)) * p.M + bc.m;
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+      const int pi_ = r * G + j;
+      xy_[r] = make_float2(0.f, 0.f);
+      a_[r] = 0.f;
+      if (pi_ < LP && act_) {
+        xy_[r] = __ldg(reinterpret_cast<const float2*>(loc + pair_ * LP * 2) + pi_);
+        a_[r] = __ldg(aw + pair_ * LP + pi_);
+      }
+    }
+  };
+  if (kStatic) fetch(bc.q_begin + warp * kGpw, nxy, na);
+
   for (int qw = bc.q_begin + warp * kGpw; qw < bc.q_end; qw += kWarps * kGpw) {
     const int q = qw + grp;
     const bool active = q < bc.q_end;
     const size_t pair = ((size_t)bc.b * p.Lq + (active ? q : bc.q_begin)) * p.M + bc.m;
     const float* __restrict__ loc_pair = loc + pair * LP * 2;
     const float* __restrict__ aw_pair = aw + pair * LP;
+
+    float2 cxy[kRounds];
+    float ca[kRounds];
+    if (kStatic) {
+#pragma unroll
+      for (int r = 0; r < kRounds; ++r) { cxy[r] = nxy[r]; ca[r] = na[r]; }
+      if (qw + kWarps * kGpw < bc.q_end) fetch(qw + kWarps * kGpw, nxy, na);
+    }
 
     V acc = V::zero();
 
@@ -75,8 +106,15 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_fwd_vec_kernel(const Para
       tap.w[0] = tap.w[1] = tap.w[2] = tap.w[3] = 0.f;
       if (pi < LP && active) {
         const int l = pi / P;
-        const float2 xy = __ldg(reinterpret_cast<const float2*>(loc_pair) + pi);
-        const float a = __ldg(aw_pair + pi);
+        float2 xy;
+        float a;
+        if (kStatic) {
+          xy = cxy[r0 / G];
+          a = ca[r0 / G];
+        } else {
+          xy = __ldg(reinterpret_cast<const float2*>(loc_pair) + pi);
+          a = __ldg(aw_pair + pi);
+        }
         tap = point_tap(xy.x, xy.y, a, sH[l], sW[l], sStart[l], MDb);
       }
       // ---- consumers: every lane of the group gathers its 16 bytes for each prepared point ----
@@ -94,22 +132,19 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_fwd_vec_kernel(const Para
           } else {
             rs = __shfl_sync(0xffffffffu, tap.rowstep, jj, G);
           }
-          const unsigned o1 = of & ~15u;
-          const unsigned dcol = (of & 1u) ? MDb : 0u;
-          const unsigned drow = (of & 2u) ? rs : 0u;
-          const V v1 = V::load(reinterpret_cast<const T*>(vb + o1));
-          const V v2 = V::load(reinterpret_cast<const T*>(vb + (o1 + dcol)));
-          const V v3 = V::load(reinterpret_cast<const T*>(vb + (o1 + drow)));
-          const V v4 = V::load(reinterpret_cast<const T*>(vb + (o1 + drow + dcol)));
-          if (of & 4u) {  // the reference skips out-of-range samples entirely (:288)
+          // four corner addresses in 4 IMAD.WIDE (64-bit base + 32-bit offset / flag * step)
+          const char* p1 = ptr_add(vb, of & ~15u);
+          const char* p2 = ptr_madd(p1, of & 1u, MDb);
+          const char* p3 = ptr_madd(p1, (of >> 1) & 1u, rs);
+          const char* p4 = ptr_madd(p3, of & 1u, MDb);
+          const V v1 = V::load(reinterpret_cast<const T*>(p1));
+          const V v2 = V::load(reinterpret_cast<const T*>(p2));
+          const V v3 = V::load(reinterpret_cast<const T*>(p3));
+          const V v4 = V::load(reinterpret_cast<const T*>(p4));
+          // the reference skips out-of-range samples entirely (:288): predicated FMAs, no branch
 #pragma unroll
-            for (int c = 0; c < kCpl; ++c) {
-              acc.v[c] = fmaf(a1, v1.v[c], acc.v[c]);
-              acc.v[c] = fmaf(a2, v2.v[c], acc.v[c]);
-              acc.v[c] = fmaf(a3, v3.v[c], acc.v[c]);
-              acc.v[c] = fmaf(a4, v4.v[c], acc.v[c]);
-            }
-          }
+          for (int c0 = 0; c0 < kCpl; c0 += 4)
+            fma4x4_if(of & 4u, &acc.v[c0], a1, a2, a3, a4, &v1.v[c0], &v2.v[c0], &v3.v[c0], &v4.v[c0]);
         }
       }
     }

@@ -1,0 +1,240 @@
+// msda_fwd_smem.cu — forward with whole-level value maps staged in shared memory (sm_100a).
+//
+// EXPERIMENTAL, OPT-IN (tuning key "fwd_smem" = 2). Idea: when a level's map of one head ([H*W, D])
+// fits in shared memory, a CTA that owns (batch b, head m, a long chunk of queries) copies that map in
+// ONCE (token rows are 128-byte pieces strided by M*D in global memory; copied with 16-byte cp.async
+// (LDGSTS) by all threads — one 1-D TMA bulk copy (UBLKCP) per 128-byte row was measured 3x slower: the
+// bulk engine wants larger boxes) and then gathers from shared memory; levels that do not fit keep
+// the L1 path.
+// Measured outcome (profiles/r1_fwd_smem_vs_l1.md): bit-identical results, but NOT faster than
+// msda_fwd.cu at the adapter shapes — an LDS.128 over 4 different rows costs the same 4 LSU data-pipe
+// wavefronts as the L1-hitting LDG.128, and that pipe (~76% busy in both kernels) is the limiter, not
+// L1 misses or L2 bandwidth. It only removes L2->L1 traffic. Kept because the host-shape plan /
+// staging code is what a tiled backward would build on.
+// Typical plans (chosen on the host from the level shapes, see plan_forward_smem in msda_abi.cu):
+//   Extractor  512^2: the single 32x32 level (128 KB fp32)            -> all gathers from smem
+//   Injector   512^2: levels 1 and 2 (32x32 + 16x16 = 160 KB fp32)    -> 2/3 of the gathers from smem
+//   L 896^2 bf16 Extractor: the 56x56 level (196 KB)                  -> all gathers from smem
+// Arithmetic is identical to msda_fwd.cu (same point_geom / weights / accumulation order).
+#include "msda_common.cuh"
+
+namespace msda {
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// 16-byte asynchronous copy global -> shared (SASS: LDGSTS.E.BYPASS.128), L1-bypassing.
+__device__ __forceinline__ void cp_async_16(unsigned dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+template <typename T>
+__device__ __forceinline__ Vec<T> lds_vec(unsigned addr);
+template <>
+__device__ __forceinline__ Vec<float> lds_vec<float>(unsigned addr) {
+  Vec<float> r;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "r"(addr));
+  return r;
+}
+template <>
+__device__ __forceinline__ Vec<__nv_bfloat16> lds_vec<__nv_bfloat16>(unsigned addr) {
+  uint4 t;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "r"(addr));
+  Vec<__nv_bfloat16> r;
+  r.v[0] = __uint_as_float(t.x << 16); r.v[1] = __uint_as_float(t.x & 0xffff0000u);
+  r.v[2] = __uint_as_float(t.y << 16); r.v[3] = __uint_as_float(t.y & 0xffff0000u);
+  r.v[4] = __uint_as_float(t.z << 16); r.v[5] = __uint_as_float(t.z & 0xffff0000u);
+  r.v[6] = __uint_as_float(t.w << 16); r.v[7] = __uint_as_float(t.w & 0xffff0000u);
+  return r;
+}
+
+// T, G, LT, PT as in msda_fwd.cu; NT = threads per CTA (one CTA per SM: the maps use most of the smem).
+template <typename T, int G, int LT, int PT, int NT>
+__global__ void __launch_bounds__(NT, 1) msda_fwd_smem_kernel(const Params p, const SmemPlan plan) {
+  using V = Vec<T>;
+  constexpr int kCpl = V::kCpl;
+  constexpr int kGpw = 32 / G;
+  constexpr int kWarpsNT = NT / 32;
+  constexpr int LP = LT * PT;
+  constexpr unsigned kRowB = (unsigned)(G * 16);  // bytes of one head-row (D * sizeof(T))
+
+  extern __shared__ __align__(128) unsigned char smem[];
+
+  const int MD = p.M * p.D;
+  const unsigned MDb = (unsigned)MD * (unsigned)sizeof(T);
+  const BlockCoord bc = block_coord(p);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = lane / G, j = lane % G;
+
+  const char* __restrict__ slab = reinterpret_cast<const char*>(p.value) +
+                                  ((size_t)bc.b * p.S * MD + (size_t)bc.m * p.D) * sizeof(T);
+
+  // ---- stage the planned levels: 16-byte cp.async per lane, G lanes per token row -------------------
+#pragma unroll
+  for (int l = 0; l < LT; ++l) {
+    if (plan.staged & (1u << l)) {
+      const int rows = plan.H[l] * plan.W[l];
+      const char* src = slab + (size_t)plan.start[l] * MDb + (threadIdx.x % G) * 16;
+      const unsigned dst = smem_u32(smem) + plan.smem_off[l] + (threadIdx.x % G) * 16;
+      for (int r = threadIdx.x / G; r < rows; r += NT / G) cp_async_16(dst + (unsigned)r * kRowB, src + (size_t)r * MDb);
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+
+  unsigned rsl[LT];   // bytes between rows of a level: in the smem map (staged) or in global (not staged)
+  unsigned csl[LT];   // bytes between neighbouring tokens
+#pragma unroll
+  for (int l = 0; l < LT; ++l) {
+    const bool st = plan.staged & (1u << l);
+    csl[l] = st ? kRowB : MDb;
+    rsl[l] = (unsigned)plan.W[l] * csl[l];
+  }
+
+  const char* __restrict__ vb = slab + j * 16;
+  const unsigned sb = smem_u32(smem) + j * 16;
+  const float* __restrict__ loc = reinterpret_cast<const float*>(p.loc);
+  const float* __restrict__ aw = reinterpret_cast<const float*>(p.aw);
+  T* __restrict__ out = reinterpret_cast<T*>(p.out);
+
+  // software pipeline: fetch the next iteration's locations / weights before working on this one
+  constexpr int kRounds = (LP + G - 1) / G;
+  float2 nxy[kRounds];
+  float na[kRounds];
+  auto fetch = [&](int qw_, float2 (&xy_)[kRounds], float (&a_)[kRounds]) {
+    const int q_ = qw_ + grp;
+    const bool act_ = q_ < bc.q_end;
+    const size_t pair_ = ((size_t)bc.b * p.Lq + (act_ ? q_ : bc.q_begin)) * p.M + bc.m;
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+      const int pi_ = r * G + j;
+      xy_[r] = make_float2(0.f, 0.f);
+      a_[r] = 0.f;
+      if (pi_ < LP && act_) {
+        xy_[r] = __ldg(reinterpret_cast<const float2*>(loc + pair_ * LP * 2) + pi_);
+        a_[r] = __ldg(aw + pair_ * LP + pi_);
+      }
+    }
+  };
+  fetch(bc.q_begin + warp * kGpw, nxy, na);
+
+  // every warp waits for its own copies, then for everyone's (warps with no query in a clipped last
+  // chunk must still reach the barrier, so it sits outside the query loop)
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  for (int qw = bc.q_begin + warp * kGpw; qw < bc.q_end; qw += kWarpsNT * kGpw) {
+    const int q = qw + grp;
+    const bool active = q < bc.q_end;
+    const size_t pair = ((size_t)bc.b * p.Lq + (active ? q : bc.q_begin)) * p.M + bc.m;
+
+    float2 cxy[kRounds];
+    float ca[kRounds];
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) { cxy[r] = nxy[r]; ca[r] = na[r]; }
+    if (qw + kWarpsNT * kGpw < bc.q_end) fetch(qw + kWarpsNT * kGpw, nxy, na);
+
+    V acc = V::zero();
+#pragma unroll
+    for (int r0 = 0; r0 < LP; r0 += G) {
+      // ---- producer ------------------------------------------------------------------------------------
+      const int pi = r0 + j;
+      unsigned offf = 0u;
+      float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
+      if (pi < LP && active) {
+        const int l = pi / PT;
+        const int H = plan.H[l], W = plan.W[l];
+        const float2 xy = cxy[r0 / G];
+        const float a = ca[r0 / G];
+        const PointGeom<float> g = point_geom<float>(xy.x, xy.y, H, W);
+        const float hh = 1.f - g.lh, hw = 1.f - g.lw;
+        w0 = (g.mask & 1u) ? (hh * hw) * a : 0.f;
+        w1 = (g.mask & 2u) ? (hh * g.lw) * a : 0.f;
+        w2 = (g.mask & 4u) ? (g.lh * hw) * a : 0.f;
+        w3 = (g.mask & 8u) ? (g.lh * g.lw) * a : 0.f;
+        const bool st = plan.staged & (1u << l);
+        // staged: byte offset inside the level's smem map; else: byte offset inside the (b,m) slab in global
+        offf = st ? (tap_offset(g, H, W, 0, kRowB) + plan.smem_off[l]) : tap_offset(g, H, W, plan.start[l], MDb);
+      }
+      // ---- consumers -----------------------------------------------------------------------------------
+#pragma unroll
+      for (int jj = 0; jj < G; ++jj) {
+        if (r0 + jj < LP) {
+          constexpr int kDummy = 0;
+          (void)kDummy;
+          const int l = (r0 + jj) / PT;  // compile-time after unrolling
+          const unsigned of = __shfl_sync(0xffffffffu, offf, jj, G);
+          const float a1 = __shfl_sync(0xffffffffu, w0, jj, G);
+          const float a2 = __shfl_sync(0xffffffffu, w1, jj, G);
+          const float a3 = __shfl_sync(0xffffffffu, w2, jj, G);
+          const float a4 = __shfl_sync(0xffffffffu, w3, jj, G);
+          const unsigned o1 = of & ~15u;
+          const unsigned dcol = (of & 1u) ? csl[l] : 0u;
+          const unsigned drow = (of & 2u) ? rsl[l] : 0u;
+          V v1, v2, v3, v4;
+          if (plan.staged & (1u << l)) {  // uniform
+            v1 = lds_vec<T>(sb + o1);
+            v2 = lds_vec<T>(sb + o1 + dcol);
+            v3 = lds_vec<T>(sb + o1 + drow);
+            v4 = lds_vec<T>(sb + o1 + drow + dcol);
+          } else {
+            const char* p1 = ptr_add(vb, o1);
+            const char* p2 = ptr_add(p1, dcol);
+            const char* p3 = ptr_add(p1, drow);
+            const char* p4 = ptr_add(p3, dcol);
+            v1 = V::load(reinterpret_cast<const T*>(p1));
+            v2 = V::load(reinterpret_cast<const T*>(p2));
+            v3 = V::load(reinterpret_cast<const T*>(p3));
+            v4 = V::load(reinterpret_cast<const T*>(p4));
+          }
+#pragma unroll
+          for (int c0 = 0; c0 < kCpl; c0 += 4)
+            fma4x4_if(of & 4u, &acc.v[c0], a1, a2, a3, a4, &v1.v[c0], &v2.v[c0], &v3.v[c0], &v4.v[c0]);
+        }
+      }
+    }
+    if (active) acc.store(out + pair * p.D + j * kCpl);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Launcher. Returns cudaErrorNotSupported when no instantiation exists (caller falls back to the
+// L1-path kernel).
+// ---------------------------------------------------------------------------------------------
+template <typename T, int G, int LT, int PT, int NT>
+static cudaError_t launch_one(const Params& p, const SmemPlan& plan, dim3 grid, cudaStream_t s) {
+  auto kern = msda_fwd_smem_kernel<T, G, LT, PT, NT>;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (e != cudaSuccess) return e;
+    configured_dev = dev;
+  }
+  kern<<<grid, NT, plan.total_bytes, s>>>(p, plan);
+  return cudaGetLastError();
+}
+
+template <typename T, int G>
+static cudaError_t launch_g(const Params& p, const SmemPlan& plan, int nt, dim3 grid, cudaStream_t s) {
+  if (p.L == 3 && p.P == 4) {
+    return nt == 1024 ? launch_one<T, G, 3, 4, 1024>(p, plan, grid, s) : launch_one<T, G, 3, 4, 512>(p, plan, grid, s);
+  }
+  if (p.L == 1 && p.P == 4) {
+    return nt == 1024 ? launch_one<T, G, 1, 4, 1024>(p, plan, grid, s) : launch_one<T, G, 1, 4, 512>(p, plan, grid, s);
+  }
+  return cudaErrorNotSupported;
+}
+
+cudaError_t launch_forward_smem(const Params& p, const SmemPlan& plan, int dtype, int G, int nt, cudaStream_t s) {
+  const dim3 grid((unsigned)((size_t)p.N * p.nchunk * p.M));
+  if (dtype == MSDA_F32) {
+    if (G == 8) return launch_g<float, 8>(p, plan, nt, grid, s);
+    if (G == 16) return launch_g<float, 16>(p, plan, nt, grid, s);
+  } else if (dtype == MSDA_BF16) {
+    if (G == 4) return launch_g<__nv_bfloat16, 4>(p, plan, nt, grid, s);
+    if (G == 8) return launch_g<__nv_bfloat16, 8>(p, plan, nt, grid, s);
+  }
+  return cudaErrorNotSupported;
+}
+
+}  // namespace msda
