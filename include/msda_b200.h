@@ -156,6 +156,7 @@ uint64_t msda_launch_count(void);
  *   "fwd_min_ctas", "bwd_min_ctas"  min-resident-CTAs-per-SM variant (forward 3|4|6, backward 2|3|4)
  *   "fwd_smem"                      2 = use the shared-memory forward whenever a plan exists (default: never;
  *                                   measured no faster than the L1 path, see msda_abi.cu plan_forward_smem)
+ *   "fwd_wide"                      fp32 forward with 32-byte lanes (LDG.256): 1 = off, 2 = on
  *   "fwd_smem_threads"              512 | 1024 threads per CTA of the shared-memory forward
  *   "fwd_smem_chunks"               query chunks per (batch, head) of the shared-memory forward
  * Returns 0, or MSDA_E_NULL for an unknown key. */

@@ -385,3 +385,21 @@ def test_host_shapes_cached_no_sync_in_steady_state():
     assert a is b and list(a) == [4, 4]
     g['shapes'].add_(0)  # in-place op bumps the version counter -> re-read
     assert _cabi.host_shapes(g['shapes']) is not a
+
+
+@pytest.mark.parametrize('cfg', SMEM_SHAPES[:4], ids=[s[0] for s in SMEM_SHAPES[:4]])
+def test_wide_lane_forward_bit_identical(cfg):
+    """fp32 forward with 32-byte lanes (LDG.256): same arithmetic order per channel -> identical bits."""
+    _, N, M, D, Lq, shapes, P, dist = cfg
+    g = _cuda(make_inputs(N, M, D, Lq, shapes, P, seed=22, dist=dist))
+    try:
+        _cabi.set_tuning(fwd_wide=1)
+        want = _cabi.forward(g['value'], g['shapes'], g['lsi'], g['loc'], g['aw'], 64)
+        _cabi.set_tuning(fwd_wide=2)
+        for minb in (0, 3):
+            _cabi.set_tuning(fwd_min_ctas=minb)
+            got = _cabi.forward(g['value'], g['shapes'], g['lsi'], g['loc'], g['aw'], 64)
+            torch.cuda.synchronize()
+            assert torch.equal(got, want)
+    finally:
+        _cabi.set_tuning(fwd_wide=0, fwd_min_ctas=0)

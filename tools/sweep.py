@@ -44,6 +44,7 @@ def main():
     ap.add_argument('--qc', default='0', help='comma list of query-chunk overrides to try (0 = heuristic)')
     ap.add_argument('--minb', default='0:0', help='comma list of fwd:bwd min-CTAs-per-SM kernel variants (0 = default)')
     ap.add_argument('--smem', default='0', help='comma list of fwd_smem[:threads[:chunks]] settings (0 auto, 1 off, 2 forced)')
+    ap.add_argument('--wide', default='0', help='comma list of fwd_wide settings (0 auto, 1 off, 2 on)')
     ap.add_argument('--regimes', default='flushed,warm')
     ap.add_argument('--dtypes', default='f32,bf16')
     ap.add_argument('--no-ref', action='store_true')
@@ -71,12 +72,12 @@ def main():
                 if dtype not in args.dtypes.split(','):
                     continue
                 ab = algorithmic_bytes(N, Mh, Dh, Lq, shapes, es)
-                for qc, mb, sm in [(int(x), y, z) for x in args.qc.split(',') for y in args.minb.split(',') for z in args.smem.split(',')]:
+                for qc, mb, sm, wd in [(int(x), y, z, int(w)) for x in args.qc.split(',') for y in args.minb.split(',') for z in args.smem.split(',') for w in args.wide.split(',')]:
                     fmb, bmb = [int(v) for v in mb.split(':')]
                     smv = [int(v) for v in sm.split(':')] + [0, 0]
                     _cabi.set_tuning(fwd_chunk=qc, bwd_chunk=qc, fwd_min_ctas=fmb, bwd_min_ctas=bmb, fwd_smem=smv[0],
-                                     fwd_smem_threads=smv[1], fwd_smem_chunks=smv[2])
-                    mb = mb + '/s' + sm
+                                     fwd_smem_threads=smv[1], fwd_smem_chunks=smv[2], fwd_wide=wd)
+                    mb = mb + '/s' + sm + '/w%d' % wd
                     fw = lambda: _cabi.forward(d['value'], d['shapes'], d['lsi'], d['loc'], d['aw'], 64)
                     bw = lambda: _cabi.backward(d['value'], d['shapes'], d['lsi'], d['loc'], d['aw'], d['grad_out'], 64)
                     for regime, fl in (('flushed', flush), ('warm', None)):
@@ -92,7 +93,7 @@ def main():
                                      'bwd_frac': ab['bwd'] / (tb['med'] * 1e-3) / 1e9 / peak,
                                      'frac': (ab['fwd'] + ab['bwd']) / ((tf['med'] + tb['med']) * 1e-3) / 1e9 / peak})
                         print(json.dumps(rows[-1]), flush=True)
-                _cabi.set_tuning(fwd_chunk=0, bwd_chunk=0, fwd_min_ctas=0, bwd_min_ctas=0, fwd_smem=0, fwd_smem_threads=0, fwd_smem_chunks=0)
+                _cabi.set_tuning(fwd_chunk=0, bwd_chunk=0, fwd_min_ctas=0, bwd_min_ctas=0, fwd_smem=0, fwd_smem_threads=0, fwd_smem_chunks=0, fwd_wide=0)
             if refcuda.available() and not args.no_ref:
                 ab = algorithmic_bytes(N, Mh, Dh, Lq, shapes, 4)
                 fw = lambda: refcuda.forward(d32['value'], d32['shapes'], d32['lsi'], d32['loc'], d32['aw'])

@@ -16,11 +16,13 @@ bool vec_supported(int dtype, int D, int* G_out);
 cudaError_t launch_forward(const Params& p, int dtype, bool vec_ok, int G, int minb, cudaStream_t s);
 cudaError_t launch_backward(const Params& p, int dtype, bool vec_ok, int G, int minb, cudaStream_t s);
 cudaError_t launch_cvt_f32_bf16(const float* src, void* dst, size_t n, cudaStream_t s);
+cudaError_t launch_forward_wide(const Params& p, int G, int minb, cudaStream_t s);
 cudaError_t launch_forward_smem(const Params& p, const SmemPlan& plan, int dtype, int G, int nt, cudaStream_t s);
 
 static thread_local char g_err[512] = "";
+constexpr bool kFwdWideDefault = false;  // flipped once measured faster (tuning key "fwd_wide" = 2 forces it)
 static std::atomic<uint64_t> g_launches{0};
-static std::atomic<int> g_qc_fwd{0}, g_qc_bwd{0}, g_minb_fwd{0}, g_minb_bwd{0}, g_smem_mode{0}, g_smem_nt{0}, g_smem_chunks{0};
+static std::atomic<int> g_qc_fwd{0}, g_qc_bwd{0}, g_minb_fwd{0}, g_minb_bwd{0}, g_smem_mode{0}, g_smem_nt{0}, g_smem_chunks{0}, g_fwd_wide{0};
 
 static int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -193,6 +195,7 @@ int msda_set_tuning(const char* key, int32_t value) {
   else if (!strcmp(key, "fwd_smem")) slot = &g_smem_mode;
   else if (!strcmp(key, "fwd_smem_threads")) slot = &g_smem_nt;
   else if (!strcmp(key, "fwd_smem_chunks")) slot = &g_smem_chunks;
+  else if (!strcmp(key, "fwd_wide")) slot = &g_fwd_wide;
   if (!slot) return fail(MSDA_E_NULL, "msda_set_tuning: unknown key '%s'", key);
   slot->store(value);
   return 0;
@@ -243,6 +246,21 @@ int msda_forward_ex(const msda_dims* dims, int dtype, const void* value, const i
       if (es2 != cudaErrorNotSupported) return cuda_fail(es2, "msda_forward (shared-memory variant) launch");
     }
   }
+  // fp32 with 32-byte lanes (LDG.256): 8 channels per lane, G = D/8
+  const int wide_mode = g_fwd_wide.load();  // 0 auto, 1 off, 2 on
+  if (vec && dtype == MSDA_F32 && wide_mode != 1 && p.D % 8 == 0 && aligned(value, 32) && aligned(out, 32)) {
+    const int Gw = p.D / 8;
+    if (Gw >= 2 && Gw <= 8 && (Gw & (Gw - 1)) == 0 && (wide_mode == 2 || kFwdWideDefault)) {
+      p.qc = pick_chunk(dims, kWarps * (32 / Gw), g_qc_fwd.load());
+      p.nchunk = (p.Lq + p.qc - 1) / p.qc;
+      const cudaError_t ew = launch_forward_wide(p, Gw, g_minb_fwd.load(), (cudaStream_t)stream);
+      if (ew == cudaSuccess) {
+        g_launches.fetch_add(1);
+        return 0;
+      }
+      if (ew != cudaErrorNotSupported) return cuda_fail(ew, "msda_forward (32-byte lanes) launch");
+    }
+  }
   const int per_iter = vec ? kWarps * (32 / G) : kWarps;
   p.qc = pick_chunk(dims, per_iter, g_qc_fwd.load());
   p.nchunk = (p.Lq + p.qc - 1) / p.qc;
@@ -288,8 +306,10 @@ int msda_backward(const msda_dims* dims, int dtype, const void* value, const int
   const size_t accum_bytes = (dtype == MSDA_BF16) ? nvalue * sizeof(float) : nvalue * es;
   p.grad_value = accum;
 
-  int G = 0;
-  bool vec = vec_supported(dtype, p.D, &G) && aligned(value, 16) && aligned(grad_out, 16) &&
+  // backward lane layout: 4 channels per lane for both dtypes (see VecB in msda_bwd.cu)
+  int G = p.D / 4;
+  bool vec = (dtype == MSDA_F32 || dtype == MSDA_BF16) && p.D % 4 == 0 && G >= 2 && G <= 32 && (G & (G - 1)) == 0 &&
+             aligned(value, 16) && aligned(grad_out, 16) &&
              aligned(accum, 16) && aligned(sampling_loc, 8) && aligned(grad_sampling_loc, 8);
   const int per_iter = vec ? kWarps * (32 / G) : kWarps;
   p.qc = pick_chunk(dims, per_iter, g_qc_bwd.load());

@@ -184,6 +184,46 @@ struct Vec<__nv_bfloat16> {
   }
 };
 
+// Lane vectors by width: 16 bytes per lane (above) or 32 bytes per lane (fp32 only: 8 channels, one
+// LDG.E.ENL2.256 / STG.E.ENL2.256, the 256-bit global accesses new on sm_100). Wider lanes halve the lanes per
+// (b,q,m), so a warp serves twice as many queries per instruction: the per-point broadcast shuffles and the
+// address / weight arithmetic are amortised over 8 queries instead of 4.
+template <typename T, int LANE_BYTES>
+struct LaneVec;
+template <>
+struct LaneVec<float, 16> : Vec<float> {
+  __device__ __forceinline__ static LaneVec load(const float* p) { LaneVec r; static_cast<Vec<float>&>(r) = Vec<float>::load(p); return r; }
+  __device__ __forceinline__ static LaneVec zero() { LaneVec r; static_cast<Vec<float>&>(r) = Vec<float>::zero(); return r; }
+};
+template <>
+struct LaneVec<__nv_bfloat16, 16> : Vec<__nv_bfloat16> {
+  __device__ __forceinline__ static LaneVec load(const __nv_bfloat16* p) { LaneVec r; static_cast<Vec<__nv_bfloat16>&>(r) = Vec<__nv_bfloat16>::load(p); return r; }
+  __device__ __forceinline__ static LaneVec zero() { LaneVec r; static_cast<Vec<__nv_bfloat16>&>(r) = Vec<__nv_bfloat16>::zero(); return r; }
+};
+template <>
+struct LaneVec<float, 32> {
+  static constexpr int kCpl = 8;
+  float v[8];
+  __device__ __forceinline__ static LaneVec load(const float* p) {
+    LaneVec r;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+                 : "l"(p));
+    return r;
+  }
+  __device__ __forceinline__ static LaneVec zero() {
+    LaneVec r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = 0.f;
+    return r;
+  }
+  __device__ __forceinline__ void store(float* p) const {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+                 "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+  }
+};
+
 // 64-bit pointer + 32-bit offset in ONE instruction (IMAD.WIDE.U32) instead of IADD3 + IADD3.X: the
 // gather kernels are issue-bound, and every corner needs its own address.
 __device__ __forceinline__ const char* ptr_add(const char* base, unsigned off) {

@@ -21,9 +21,9 @@ namespace msda {
 // Vector kernel. T = float | __nv_bfloat16, G = lanes per (b,q,m) (D = G * Vec<T>::kCpl),
 // LT/PT = compile-time levels / points (0,0 = runtime), MINB = min resident CTAs per SM.
 // ---------------------------------------------------------------------------------------------
-template <typename T, int G, int LT, int PT, int MINB>
+template <typename T, int G, int LT, int PT, int MINB, int LB = 16>
 __global__ void __launch_bounds__(kThreads, MINB) msda_fwd_vec_kernel(const Params p) {
-  using V = Vec<T>;
+  using V = LaneVec<T, LB>;  // LB = bytes per lane: 16 (LDG.128) or 32 (LDG.256, fp32 only)
   constexpr int kCpl = V::kCpl;
   constexpr int kGpw = 32 / G;  // (b,q,m) groups per warp
   constexpr bool kStatic = (LT > 0);
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_fwd_vec_kernel(const Para
 
   // CTA-uniform slab base (batch b, head m) + this lane's 16 bytes inside a D-row
   const char* __restrict__ vb = reinterpret_cast<const char*>(p.value) +
-                                ((size_t)bc.b * p.S * MD + (size_t)bc.m * p.D) * sizeof(T) + j * 16;
+                                ((size_t)bc.b * p.S * MD + (size_t)bc.m * p.D) * sizeof(T) + j * LB;
   const float* __restrict__ loc = reinterpret_cast<const float*>(p.loc);
   const float* __restrict__ aw = reinterpret_cast<const float*>(p.aw);
   T* __restrict__ out = reinterpret_cast<T*>(p.out);
@@ -216,6 +216,31 @@ static cudaError_t launch_vec_g(const Params& p, int minb, dim3 grid, cudaStream
     case 3: return launch_vec_gm<T, G, 3>(p, grid, s);
     case 6: return launch_vec_gm<T, G, 6>(p, grid, s);
     default: return launch_vec_gm<T, G, 4>(p, grid, s);
+  }
+}
+
+// 32-byte lanes (fp32): G = D / 8
+template <int G>
+static cudaError_t launch_wide_g(const Params& p, int minb, dim3 grid, cudaStream_t s) {
+  if (p.L == 3 && p.P == 4) {
+    if (minb == 3) msda_fwd_vec_kernel<float, G, 3, 4, 3, 32><<<grid, kThreads, 0, s>>>(p);
+    else msda_fwd_vec_kernel<float, G, 3, 4, 4, 32><<<grid, kThreads, 0, s>>>(p);
+  } else if (p.L == 1 && p.P == 4) {
+    if (minb == 3) msda_fwd_vec_kernel<float, G, 1, 4, 3, 32><<<grid, kThreads, 0, s>>>(p);
+    else msda_fwd_vec_kernel<float, G, 1, 4, 4, 32><<<grid, kThreads, 0, s>>>(p);
+  } else {
+    msda_fwd_vec_kernel<float, G, 0, 0, 4, 32><<<grid, kThreads, 0, s>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_forward_wide(const Params& p, int G, int minb, cudaStream_t s) {
+  const dim3 grid((unsigned)((size_t)p.N * p.nchunk * p.M));
+  switch (G) {
+    case 2: return launch_wide_g<2>(p, minb, grid, s);
+    case 4: return launch_wide_g<4>(p, minb, grid, s);
+    case 8: return launch_wide_g<8>(p, minb, grid, s);
+    default: return cudaErrorNotSupported;
   }
 }
 
