@@ -239,7 +239,7 @@ def run_reference_arm(args):
         'e2e': {'value': value, 'unit': 'Gsamples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -354,41 +354,74 @@ def run_ours(args):
     value = world * pts_step / (ms_per_step * 1e-3) / 1e9
 
     # ---- e2e: public API (MSDeformAttnFunction.apply + autograd) from pinned HOST buffers -------------------
-    def step_e2e():
-        res = []
-        for c in calls:
-            h = c['host']
-            v = h['value'].to(dev, non_blocking=True).requires_grad_()
-            loc = h['loc'].to(dev, non_blocking=True).requires_grad_()
-            aw = h['aw'].to(dev, non_blocking=True).requires_grad_()
-            go = h['grad_out'].to(dev, non_blocking=True)
-            sh = h['shapes'].to(dev, non_blocking=True)
-            ls = h['lsi'].to(dev, non_blocking=True)
-            out = vab.MSDeformAttnFunction.apply(v, sh, ls, loc, aw, 64)
-            out.backward(go)
-            res.append([out.detach().to('cpu', non_blocking=True), v.grad.to('cpu', non_blocking=True),
-                        loc.grad.to('cpu', non_blocking=True), aw.grad.to('cpu', non_blocking=True)])
-        return res
+    # Every step copies ITS inputs host->device and ITS results (out + 3 gradients) device->host. The three
+    # phases run on three streams (copy-in / compute / copy-out) with double-buffered device inputs and pinned
+    # host result buffers, so step k+1's upload and step k-1's download overlap step k's kernels (full-duplex
+    # PCIe). Steady-state throughput; all bytes of every step are inside the timed region.
+    s_in, s_cmp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+    in_keys = ('value', 'loc', 'aw', 'grad_out', 'shapes', 'lsi')
+    dev_in = [[{k: torch.empty_like(c['host'][k], device=dev) for k in in_keys} for c in calls] for _ in range(2)]
+    host_out = [[[torch.empty(c['host']['grad_out'].shape, dtype=dtype).pin_memory(),
+                  torch.empty(c['host']['value'].shape, dtype=dtype).pin_memory(),
+                  torch.empty(c['host']['loc'].shape, dtype=torch.float32).pin_memory(),
+                  torch.empty(c['host']['aw'].shape, dtype=torch.float32).pin_memory()] for c in calls] for _ in range(2)]
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]     # compute finished reading dev_in[slot]
+    ev_outfree = [torch.cuda.Event() for _ in range(2)]  # copy-out finished with host_out[slot]
+    keep = [None, None]
 
-    h2d = sum(sum(c['host'][k].numel() * c['host'][k].element_size() for k in ('value', 'loc', 'aw', 'grad_out', 'shapes', 'lsi'))
-              for c in calls)
-    d2h = sum(c['host']['grad_out'].numel() * esize + c['host']['value'].numel() * esize + c['host']['loc'].numel() * 4
-              + c['host']['aw'].numel() * 4 for c in calls)
-    e2e_steps = max(2, min(K, 5))
-    step_e2e()
+    def run_e2e(nsteps):
+        for k in range(nsteps):
+            slot = k & 1
+            with torch.cuda.stream(s_in):
+                if k >= 2:
+                    s_in.wait_event(ev_free[slot])
+                for ci, c in enumerate(calls):
+                    for key in in_keys:
+                        dev_in[slot][ci][key].copy_(c['host'][key], non_blocking=True)
+                ev_in[slot].record(s_in)
+            with torch.cuda.stream(s_cmp):
+                s_cmp.wait_event(ev_in[slot])
+                results = []
+                for ci, c in enumerate(calls):
+                    d = dev_in[slot][ci]
+                    v = d['value'].detach().requires_grad_()
+                    loc = d['loc'].detach().requires_grad_()
+                    aw = d['aw'].detach().requires_grad_()
+                    out = vab.MSDeformAttnFunction.apply(v, d['shapes'], d['lsi'], loc, aw, 64)
+                    out.backward(d['grad_out'])
+                    results.append((out.detach(), v.grad, loc.grad, aw.grad))
+                ev_free[slot].record(s_cmp)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_free[slot])
+                if k >= 2:
+                    ev_outfree[slot].synchronize()  # the host may only reuse a pinned result buffer once it landed
+                for ci, res in enumerate(results):
+                    for dst, src in zip(host_out[slot][ci], res):
+                        src.record_stream(s_out)
+                        dst.copy_(src, non_blocking=True)
+                ev_outfree[slot].record(s_out)
+            keep[slot] = results
+        for st in (s_in, s_cmp, s_out):
+            st.synchronize()
+
+    h2d = sum(sum(c['host'][k].numel() * c['host'][k].element_size() for k in in_keys) for c in calls)
+    d2h = sum(sum(t.numel() * t.element_size() for t in bufs) for bufs in host_out[0])
+    e2e_steps = max(4, min(K, 10))
+    run_e2e(2)
     barrier()
     a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a0.record()
-    for _ in range(e2e_steps):
-        step_e2e()
+    run_e2e(e2e_steps)
     a1.record()
     barrier()
-    e2e_ms = a0.elapsed_time(a1)
+    e2e_ms = a0.elapsed_time(a1)  # device clock: a1 is recorded after run_e2e synchronised all three streams
     if world > 1:
         t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
     e2e_value = world * pts_step / (e2e_ms / e2e_steps * 1e-3) / 1e9
+    del dev_in, keep
 
     # ---- reference CUDA kernel on the same GPU, same inputs (fp32 only; informational) ---------------------
     ref_cuda = None
@@ -461,18 +494,45 @@ def run_ours(args):
             'config': workload_config(variant, batch, args.dtype),
             'roofline': roofline, 'cpu_baseline': cpu_baseline,
             'e2e': {'value': e2e_value, 'unit': 'Gsamples/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'ms_per_step': e2e_ms / e2e_steps, 'api': 'MSDeformAttnFunction.apply + autograd backward, pinned host buffers'},
+                    'ms_per_step': e2e_ms / e2e_steps, 'steps': e2e_steps, 'api': 'MSDeformAttnFunction.apply + autograd backward; pinned host buffers; copy-in / compute / copy-out on 3 streams, double-buffered'},
             'gpu_launches': launches, 'clocks': clocks, 'kernels': kernels, 'ref_cuda': ref_cuda,
             'points_per_step_per_gpu': pts_step,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
+class _StdoutGuard:
+    """Keep stdout clean: everything any library prints to fd 1 while we run (NCCL prints its version banner
+    there) goes to stderr; only emit() writes to the real stdout — exactly one JSON line."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.write(self.real, (line + '\n').encode())
+
+
+_GUARD = None
+
+
+def emit(obj):
+    line = json.dumps(obj)
+    if _GUARD is not None:
+        _GUARD.emit(line)
+    else:
+        print(line, flush=True)
+
+
 def main():
+    global _GUARD
+    _GUARD = _StdoutGuard()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)

@@ -163,6 +163,9 @@ def use_reference_cuda_core():
 
 
 def main():
+    sys.stdout.flush()
+    real_stdout = os.dup(1)   # NCCL prints its version banner on fd 1: keep stdout for the one JSON line
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
@@ -240,7 +243,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     if rank == 0:
-        print(json.dumps({
+        os.write(real_stdout, (json.dumps({
             'metric': 'vit_adapter_%s_%s_img_per_s' % (args.variant, args.mode), 'value': world * args.batch * args.steps / (ms * 1e-3),
             'unit': 'img/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'dtype': 'bf16-autocast' if args.amp else 'f32', 'data': 'synthetic',
@@ -250,8 +253,8 @@ def main():
                        'params_total': n_params, 'params_adapter': n_adapter, 'with_cp': args.with_cp,
                        'parallelism': 'dp%d (DDP all-reduce over NCCL, SyncBN)' % world if world > 1 else 'single GPU',
                        'note': 'ViT trunk and head are minimal stand-ins (mmcv/mmseg/timm absent); adapter path is the drop-in code'},
-            'final': float(out.float().mean()) if torch.is_tensor(out) else None,
-        }), flush=True)
+            'final': float(out.detach().float().mean()) if torch.is_tensor(out) else None,
+        }) + '\n').encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -167,24 +167,44 @@ def test_point_index_bit_exact(dist):
     assert torch.equal(got, want)
 
 
-def test_point_index_fma_sensitive_locations():
+def _fma_sensitive_locations(H):
+    """fp32 locations within 3 ulp of a texel centre (k+0.5)/H where floor(fmaf(loc,H,-0.5)) != floor(loc*H-0.5)."""
+    k = torch.arange(H, dtype=torch.float64)
+    base = ((k + 0.5) / H).float()
+    cands, up, dn = [base], base.clone(), base.clone()
+    for _ in range(3):
+        up = torch.nextafter(up, torch.tensor(2.0))
+        dn = torch.nextafter(dn, torch.tensor(-1.0))
+        cands += [up.clone(), dn.clone()]
+    c = torch.cat(cands)
+    fused = torch.floor((c.double() * H - 0.5).float())   # exact product, one rounding == fmaf
+    unfused = torch.floor(c * H - 0.5)                    # two roundings
+    sel = fused != unfused
+    return c[sel], fused[sel]
+
+
+@pytest.mark.parametrize('H', [100, 37])
+def test_point_index_fma_sensitive_locations(H):
     """Locations where fmaf(loc,H,-0.5) and (loc*H)-0.5 floor differently: the kernels must take the fused
-    result (what nvcc emits for the reference)."""
-    H = 112
-    cand = torch.rand(4_000_000, generator=torch.Generator().manual_seed(1)) * 1.0
-    fused = torch.floor(torch.addcmul(torch.tensor(-0.5, dtype=torch.float64), cand.double(), torch.tensor(float(H), dtype=torch.float64)).float())
-    unfused = torch.floor((cand * H) - 0.5)
-    sel = cand[fused != unfused][:64]
-    if sel.numel() == 0:
-        pytest.skip('no fma-sensitive location found')
+    result (what nvcc emits for the reference) — checked on the indices AND against the
+    reference's own CUDA kernel through the values it gathers."""
+    sel, fused_floor = _fma_sensitive_locations(H)
     n = sel.numel()
+    assert n >= 3, 'the construction must yield sensitive locations (H not a power-of-two multiple)'
     loc = torch.stack([sel, sel], -1).view(1, n, 1, 1, 1, 2).contiguous()
     shapes = torch.as_tensor([(H, H)], dtype=torch.long)
     lsi = torch.zeros(1, dtype=torch.long)
     want = c_oracle.point_index(shapes, lsi, loc, 1, 4)
     got = _cabi.debug_point_index(shapes.to(DEV), lsi.to(DEV), loc.to(DEV), 1, 4).cpu()
     assert torch.equal(got, want)
-    assert torch.equal(want[:, 0].float(), fused[fused != unfused][:64])
+    assert torch.equal(want[:, 0].float(), fused_floor) and torch.equal(want[:, 1].float(), fused_floor)
+    if refcuda.available():
+        # value[token] = token index: the forward output then reveals which rows each implementation read
+        value = torch.arange(H * H, dtype=torch.float32).view(1, H * H, 1, 1).repeat(1, 1, 1, 4).contiguous().to(DEV)
+        aw = torch.ones(1, n, 1, 1, 1, device=DEV)
+        ours = _cabi.forward(value, shapes.to(DEV), lsi.to(DEV), loc.to(DEV), aw, 64)
+        ref = refcuda.forward(value, shapes.to(DEV), lsi.to(DEV), loc.to(DEV), aw)
+        torch.testing.assert_close(ours, ref, rtol=1e-6, atol=1e-3)
 
 
 # ---------------------------------------------------------------------------------------------------
