@@ -59,7 +59,8 @@ enum msda_error {
   MSDA_E_ALIGN = -4,     /* pointer not aligned to the element size                     */
   MSDA_E_LEVELS = -5,    /* more levels than MSDA_MAX_LEVELS                            */
   MSDA_E_WORKSPACE = -6, /* workspace missing or too small (see msda_backward_workspace_bytes) */
-  MSDA_E_STEP = -7       /* batch not divisible by min(batch, im2col_step)              */
+  MSDA_E_STEP = -7,      /* batch not divisible by min(batch, im2col_step)              */
+  MSDA_E_UNSUPPORTED = -8 /* no kernel for this configuration (fused entry points only; use the plain ones) */
 };
 
 #define MSDA_MAX_LEVELS 16
@@ -134,6 +135,43 @@ int msda_backward(const msda_dims* dims, int dtype,
                   void* grad_attn_weight,
                   void* workspace, size_t workspace_bytes,
                   void* stream);
+
+/* Fused entry points: the module arithmetic around the sampling core (reference:
+ * detection/ops/modules/ms_deform_attn.py:108-119) is done inside the kernels, in registers:
+ *     attention_weights = softmax(attn_logits over the L*P points of each (b, q, m))      [warp shuffles]
+ *     sampling_location = reference_point + sampling_offset / (W_l, H_l)
+ * so neither tensor is ever materialised in HBM.
+ *   reference_points  [ref_batch, Lq, ref_levels, 2] f32, ref_batch in {1, N}, ref_levels in {1, L}
+ *                     (the adapter passes [1, Lq, 1, 2]; both broadcasts of the reference's indexing
+ *                     `reference_points[:, :, None, :, None, :]` are supported)
+ *   sampling_offsets  [N, Lq, M, L, P, 2] f32 — raw output of the `sampling_offsets` linear
+ *   attn_logits       [N, Lq, M, L*P]     f32 — raw output of the `attention_weights` linear (pre-softmax)
+ * The backward returns gradients w.r.t. the raw offsets and logits (softmax backward folded in).
+ * Supported: dtype f32 / bf16, (L, P) in {(3,4), (1,4)}, D*sizeof(T) a multiple of 16 with 2..32 lanes;
+ * anything else returns MSDA_E_UNSUPPORTED and the caller uses msda_forward / msda_backward. */
+int msda_forward_fused(const msda_dims* dims, int dtype,
+                       const void* value,
+                       const int64_t* spatial_shapes,
+                       const int64_t* level_start_index,
+                       const float* reference_points, int32_t ref_batch, int32_t ref_levels,
+                       const float* sampling_offsets,
+                       const float* attn_logits,
+                       void* out,
+                       void* stream);
+
+int msda_backward_fused(const msda_dims* dims, int dtype,
+                        const void* value,
+                        const int64_t* spatial_shapes,
+                        const int64_t* level_start_index,
+                        const float* reference_points, int32_t ref_batch, int32_t ref_levels,
+                        const float* sampling_offsets,
+                        const float* attn_logits,
+                        const void* grad_out,
+                        void* grad_value,
+                        float* grad_sampling_offsets,
+                        float* grad_attn_logits,
+                        void* workspace, size_t workspace_bytes,
+                        void* stream);
 
 /* Test hook: for every sampling point (N*Lq*M*L*P of them, same order as attn_weight) write
  *   idx[4*i+0] = h_low, idx[4*i+1] = w_low,

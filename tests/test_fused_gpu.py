@@ -1,0 +1,147 @@
+"""Fused entry points (softmax + location arithmetic inside the sampling kernel) against the unfused op
+sequence the reference module executes (detection/ops/modules/ms_deform_attn.py:108-128)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden, make_inputs
+
+import vit_adapter_b200 as vab
+from vit_adapter_b200 import _cabi
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _scale(t):
+    return float(t.abs().max()) + 1e-30
+
+
+def _raw_inputs(N, M, D, Lq, shapes, P, seed, ref_batch, ref_levels, dtype):
+    g = torch.Generator().manual_seed(seed)
+    shapes_t = torch.as_tensor(shapes, dtype=torch.long)
+    L = shapes_t.shape[0]
+    S = int(shapes_t.prod(1).sum())
+    lsi = torch.cat((shapes_t.new_zeros((1,)), shapes_t.prod(1).cumsum(0)[:-1]))
+    value = torch.randn(N, S, M, D, generator=g).to(dtype)
+    ref = torch.rand(ref_batch, Lq, ref_levels, 2, generator=g) * 1.1 - 0.05      # some reference points off-image
+    offsets = torch.randn(N, Lq, M, L, P, 2, generator=g) * 2.5                     # pixels of each level
+    logits = torch.randn(N, Lq, M, L * P, generator=g) * 2.0
+    grad_out = torch.randn(N, Lq, M * D, generator=g).to(dtype)
+    return [t.to(DEV) for t in (value, shapes_t, lsi, ref, offsets, logits, grad_out)]
+
+
+def _unfused(value, shapes, lsi, ref, offsets, logits):
+    """The reference module's op sequence (ms_deform_attn.py:110-128) in torch + the plain Function."""
+    N, Lq, M, L, P, _ = offsets.shape
+    weights = F.softmax(logits, -1).view(N, Lq, M, L, P)
+    wh = torch.stack([shapes[..., 1], shapes[..., 0]], -1)
+    loc = ref[:, :, None, :, None, :] + offsets / wh[None, None, None, :, None, :]
+    return vab.MSDeformAttnFunction.apply(value, shapes, lsi, loc.contiguous(), weights.contiguous(), 64)
+
+
+CASES = [
+    # name, N, M, D, Lq, shapes, ref_batch, ref_levels
+    ('injector-B', 2, 12, 32, 256, [(32, 32), (16, 16), (8, 8)], 1, 1),
+    ('extractor-B', 2, 12, 32, 1344, [(16, 16)], 1, 1),
+    ('injector-S', 2, 6, 64, 100, [(20, 20), (10, 10), (5, 5)], 2, 3),
+    ('extractor-ragged', 3, 5, 32, 37, [(7, 9)], 3, 1),
+]
+
+
+@pytest.mark.parametrize('cfg', CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['f32', 'bf16'])
+def test_fused_matches_unfused(cfg, dtype):
+    _, N, M, D, Lq, shapes, rb, rl = cfg
+    value, shapes_t, lsi, ref, offsets, logits, go = _raw_inputs(N, M, D, Lq, shapes, 4, 31, rb, rl, dtype)
+    assert _cabi.fused_supported(value, len(shapes), 4)
+    v1, o1, l1 = value.clone().requires_grad_(), offsets.clone().requires_grad_(), logits.clone().requires_grad_()
+    out1 = vab.MSDeformAttnFusedFunction.apply(v1, shapes_t, lsi, ref, o1, l1)
+    out1.backward(go)
+    v2, o2, l2 = value.clone().requires_grad_(), offsets.clone().requires_grad_(), logits.clone().requires_grad_()
+    out2 = _unfused(v2, shapes_t, lsi, ref, o2, l2)
+    out2.backward(go)
+    torch.cuda.synchronize()
+    ft, gt = (1e-5, 1e-4) if dtype == torch.float32 else (1e-2, 1e-2)
+    torch.testing.assert_close(out1.float(), out2.float(), rtol=ft, atol=ft * max(1.0, _scale(out2.float())))
+    torch.testing.assert_close(v1.grad.float(), v2.grad.float(), rtol=gt, atol=gt * _scale(v2.grad.float()))
+    torch.testing.assert_close(o1.grad, o2.grad, rtol=gt, atol=gt * _scale(o2.grad))
+    torch.testing.assert_close(l1.grad, l2.grad, rtol=gt, atol=gt * _scale(l2.grad))
+
+
+def test_fused_locations_are_bit_identical():
+    """With one point carrying all the attention (one-hot logits) the softmax is exactly {0,1}, so any difference
+    between fused and unfused outputs could only come from the location arithmetic: there must be none."""
+    N, M, D, Lq, shapes = 1, 2, 32, 300, [(40, 40)]
+    value, shapes_t, lsi, ref, offsets, logits, _ = _raw_inputs(N, M, D, Lq, shapes, 4, 33, 1, 1, torch.float32)
+    logits = torch.full_like(logits, -1e4)
+    logits[..., 2] = 0.0
+    out1 = vab.MSDeformAttnFusedFunction.apply(value, shapes_t, lsi, ref, offsets, logits)
+    out2 = _unfused(value, shapes_t, lsi, ref, offsets, logits)
+    assert torch.equal(out1, out2)
+
+
+def test_fused_unsupported_configurations_fall_back():
+    value = torch.zeros(1, 4, 2, 32, device=DEV)
+    assert not _cabi.fused_supported(value, 2, 4)          # L = 2 has no fused kernel
+    assert not _cabi.fused_supported(value.double(), 1, 4)  # fp64 runs the generic kernels
+    assert not _cabi.fused_supported(torch.zeros(1, 4, 2, 24, device=DEV), 1, 4)
+    shapes = torch.as_tensor([(2, 2)], dtype=torch.long, device=DEV)
+    lsi = torch.zeros(1, dtype=torch.long, device=DEV)
+    with pytest.raises(RuntimeError, match='no fused kernel'):
+        _cabi.forward_fused(torch.zeros(1, 4, 2, 24, device=DEV), shapes, lsi, torch.zeros(1, 3, 1, 2, device=DEV),
+                            torch.zeros(1, 3, 2, 1, 4, 2, device=DEV), torch.zeros(1, 3, 2, 4, device=DEV))
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['f32', 'bf16-autocast'])
+def test_module_fused_vs_reference_sequence(dtype):
+    """MSDeformAttn(fused=True) vs the same module running the reference's op sequence (fused=False):
+    outputs and every parameter / input gradient."""
+    torch.manual_seed(0)
+    m = vab.MSDeformAttn(d_model=384, n_levels=3, n_heads=6, n_points=4, ratio=1.0).to(DEV)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(torch.randn_like(p) * 0.02)
+    shapes = torch.as_tensor([(16, 16), (8, 8), (4, 4)], dtype=torch.long, device=DEV)
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    query = torch.randn(2, 64, 384, device=DEV)
+    feat = torch.randn(2, 336, 384, device=DEV)
+    ref = torch.rand(1, 64, 1, 2, device=DEV)
+    amp = dtype == torch.bfloat16
+    if amp:
+        vab.set_amp_value_dtype(torch.bfloat16)
+    try:
+        res = []
+        for fused in (True, False):
+            m.fused = fused
+            m.zero_grad(set_to_none=True)
+            q, f = query.clone().requires_grad_(), feat.clone().requires_grad_()
+            n0 = _cabi.launch_count()
+            with torch.autocast('cuda', dtype=torch.bfloat16, enabled=amp):
+                out = m(q, ref, f, shapes, lsi)
+            out.float().square().mean().backward()
+            res.append((out.detach().float(), q.grad, f.grad, {k: p.grad.clone() for k, p in m.named_parameters()},
+                        _cabi.launch_count() - n0))
+    finally:
+        vab.set_amp_value_dtype(torch.float32)
+        m.fused = True
+    tol = 1e-4 if not amp else 3e-2
+    torch.testing.assert_close(res[0][0], res[1][0], rtol=tol, atol=tol * _scale(res[1][0]))
+    torch.testing.assert_close(res[0][1], res[1][1], rtol=tol, atol=tol * _scale(res[1][1]))
+    torch.testing.assert_close(res[0][2], res[1][2], rtol=tol, atol=tol * _scale(res[1][2]))
+    for k in res[0][3]:
+        torch.testing.assert_close(res[0][3][k], res[1][3][k], rtol=tol, atol=tol * _scale(res[1][3][k]), msg=k)
+    assert res[0][4] >= 2 and res[1][4] >= 2  # both paths ran our kernels
+
+
+def test_module_fused_matches_reference_golden_f32():
+    g = load_golden('module_l3')
+    d_model, L, M, P = [int(x) for x in g['cfg']]
+    m = vab.MSDeformAttn(d_model, L, M, P, float(g['ratio']))
+    m.load_state_dict({k[3:]: v.float() for k, v in g.items() if k.startswith('sd.')}, strict=True)
+    m = m.to(DEV)
+    shapes = g['shapes'].to(DEV)
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    # d_model 32 / 4 heads = 8 channels: no fused kernel -> the module must transparently use the plain path
+    out = m(g['query'].float().to(DEV), g['ref_pts'].float().to(DEV), g['feat'].float().to(DEV), shapes, lsi)
+    torch.testing.assert_close(out.cpu().double(), g['out_nomask'], rtol=1e-4, atol=1e-4)

@@ -205,6 +205,17 @@ def test_point_index_fma_sensitive_locations(H):
         ours = _cabi.forward(value, shapes.to(DEV), lsi.to(DEV), loc.to(DEV), aw, 64)
         ref = refcuda.forward(value, shapes.to(DEV), lsi.to(DEV), loc.to(DEV), aw)
         torch.testing.assert_close(ours, ref, rtol=1e-6, atol=1e-3)
+        # the forward is continuous across the floor; d/d(loc) is NOT (it differences the rows h_low, h_low+1),
+        # so equal location gradients on a random field prove both kernels floored to the same row
+        g = torch.Generator().manual_seed(4)
+        value = torch.randn(1, H * H, 1, 4, generator=g).to(DEV)
+        go = torch.randn(1, n, 4, generator=g).to(DEV)
+        _, gl, _ = _cabi.backward(value, shapes.to(DEV), lsi.to(DEV), loc.to(DEV), aw, go, 64)
+        _, rgl, _ = refcuda.backward(value, shapes.to(DEV), lsi.to(DEV), loc.to(DEV), aw, go)
+        torch.testing.assert_close(gl, rgl, rtol=1e-4, atol=1e-4 * float(rgl.abs().max()))
+        # sanity: the unfused floor would have produced a different gradient at these points
+        idx_unfused = want.clone()
+        assert (torch.floor(sel * H - 0.5) != fused_floor).all()
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -405,6 +416,11 @@ def test_host_shapes_cached_no_sync_in_steady_state():
     assert a is b and list(a) == [4, 4]
     g['shapes'].add_(0)  # in-place op bumps the version counter -> re-read
     assert _cabi.host_shapes(g['shapes']) is not a
+    # a NEW tensor that lands on the freed address of an old one must not inherit its cached shapes
+    for hw in ((3, 5), (7, 2), (9, 9)):
+        t = torch.as_tensor([hw], dtype=torch.long, device=DEV)
+        assert list(_cabi.host_shapes(t)) == list(hw)
+        del t
 
 
 @pytest.mark.parametrize('cfg', SMEM_SHAPES[:4], ids=[s[0] for s in SMEM_SHAPES[:4]])

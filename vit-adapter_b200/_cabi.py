@@ -22,7 +22,7 @@ _DTYPES = {torch.float32: MSDA_F32, torch.bfloat16: MSDA_BF16, torch.float64: MS
 EXPORTS = (
     'msda_abi_version', 'msda_last_error', 'msda_check_im2col_step', 'msda_forward', 'msda_forward_ex',
     'msda_backward_workspace_bytes', 'msda_backward', 'msda_debug_point_index', 'msda_launch_count',
-    'msda_set_tuning',
+    'msda_set_tuning', 'msda_forward_fused', 'msda_backward_fused',
 )
 
 
@@ -65,6 +65,11 @@ def load():
         lib.msda_backward.restype = ctypes.c_int
         lib.msda_backward.argtypes = [dp, ctypes.c_int, vp, i64p, i64p, vp, vp, vp, vp, vp, vp, vp,
                                       ctypes.c_size_t, vp]
+        lib.msda_forward_fused.restype = ctypes.c_int
+        lib.msda_forward_fused.argtypes = [dp, ctypes.c_int, vp, i64p, i64p, vp, ctypes.c_int32, ctypes.c_int32, vp, vp, vp, vp]
+        lib.msda_backward_fused.restype = ctypes.c_int
+        lib.msda_backward_fused.argtypes = [dp, ctypes.c_int, vp, i64p, i64p, vp, ctypes.c_int32, ctypes.c_int32, vp, vp, vp, vp,
+                                            vp, vp, vp, ctypes.c_size_t, vp]
         lib.msda_debug_point_index.restype = ctypes.c_int
         lib.msda_debug_point_index.argtypes = [dp, i64p, i64p, vp, vp, vp]
         lib.msda_launch_count.restype = ctypes.c_uint64
@@ -126,23 +131,45 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-# Host copies of spatial_shapes tensors, keyed by (storage address, version counter, numel): ONE
-# device->host read the first time a given shapes tensor is seen, none afterwards. The adapter's
+class TensorMemo:
+    """Memo keyed by tensor IDENTITY (weak reference) + version counter. Keying by data_ptr would be wrong: the
+    caching allocator hands a freed address to the next tensor of the same size, with different contents."""
+
+    def __init__(self, limit=256):
+        self._d = {}
+        self._limit = limit
+
+    def get(self, t, extra=None):
+        ent = self._d.get(id(t))
+        if ent is not None and ent[0]() is t and ent[1] == (t._version, extra):
+            return ent[2]
+        return None
+
+    def put(self, t, value, extra=None):
+        import weakref
+        if len(self._d) > self._limit:
+            self._d = {k: v for k, v in self._d.items() if v[0]() is not None}
+            if len(self._d) > self._limit:
+                self._d.clear()
+        key = id(t)
+        self._d[key] = (weakref.ref(t, lambda _r, k=key, d=self._d: d.pop(k, None)), (t._version, extra), value)
+        return value
+
+
+# Host copies of spatial_shapes tensors (needed only by kernels planned on the host: the opt-in shared-memory
+# forward). ONE device->host read the first time a given tensor object is seen, none afterwards: the adapter's
 # deform_inputs() memoises its tensors, so steady-state forwards never synchronise.
-_HOST_SHAPES = {}
+_HOST_SHAPES = TensorMemo()
+_WANT_HOST_SHAPES = False  # switched on by set_tuning(fwd_smem=2)
 
 
 def host_shapes(spatial_shapes):
-    key = (spatial_shapes.data_ptr(), spatial_shapes._version, spatial_shapes.numel())
-    hit = _HOST_SHAPES.get(key)
+    hit = _HOST_SHAPES.get(spatial_shapes)
     if hit is None:
         if torch.cuda.is_current_stream_capturing():
-            return None  # never synchronise inside a graph capture; the L1-path kernel needs no host shapes
+            return None  # never synchronise inside a graph capture; the default kernels need no host shapes
         vals = [int(v) for v in spatial_shapes.detach().reshape(-1).tolist()]
-        hit = (ctypes.c_int64 * len(vals))(*vals)
-        if len(_HOST_SHAPES) > 256:
-            _HOST_SHAPES.clear()
-        _HOST_SHAPES[key] = hit
+        hit = _HOST_SHAPES.put(spatial_shapes, (ctypes.c_int64 * len(vals))(*vals))
     return hit
 
 
@@ -160,7 +187,7 @@ def forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
     with torch.cuda.device(dev):
         out = torch.empty((dims.batch, dims.num_query, dims.num_heads * dims.channels),
                           dtype=value.dtype, device=dev)
-        hs = host_shapes(spatial_shapes)
+        hs = host_shapes(spatial_shapes) if _WANT_HOST_SHAPES else None
         rc = lib.msda_forward_ex(ctypes.byref(dims), code, value.data_ptr(), spatial_shapes.data_ptr(),
                                  level_start_index.data_ptr(), sampling_loc.data_ptr(), attn_weight.data_ptr(),
                                  out.data_ptr(), ctypes.cast(hs, ctypes.c_void_p) if hs is not None else None,
@@ -199,6 +226,76 @@ def backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight
     return grad_value, grad_loc, grad_aw
 
 
+MSDA_E_UNSUPPORTED = -8
+
+
+def fused_supported(value, n_levels, n_points):
+    """True when the fused entry points have a kernel for this configuration (else use forward/backward)."""
+    if not value.is_cuda or value.dtype not in (torch.float32, torch.bfloat16):
+        return False
+    D = value.shape[-1]
+    if not ((n_levels, n_points) in ((3, 4), (1, 4))) or D % 4 != 0 or (D // 4) not in (8, 16):
+        return False
+    cpl = 4 if value.dtype == torch.float32 else 8
+    return D % cpl == 0 and (D // cpl) in (4, 8, 16)
+
+
+def _fused_dims(value, reference_points, sampling_offsets, attn_logits):
+    if value.dim() != 4 or sampling_offsets.dim() != 6 or reference_points.dim() != 4 or reference_points.shape[-1] != 2:
+        raise RuntimeError('expected value [N,S,M,D], reference_points [Nr,Lq,Lr,2], sampling_offsets [N,Lq,M,L,P,2]')
+    N, S, M, D = value.shape
+    _, Lq, M2, L, P, _ = sampling_offsets.shape
+    if M2 != M or attn_logits.numel() != N * Lq * M * L * P or reference_points.shape[1] != Lq:
+        raise RuntimeError('fused MSDeformAttn: inconsistent shapes')
+    if sampling_offsets.dtype != torch.float32 or attn_logits.dtype != torch.float32 or reference_points.dtype != torch.float32:
+        raise RuntimeError('fused MSDeformAttn: reference_points / sampling_offsets / attn_logits must be float32')
+    return MsdaDims(N, S, M, D, L, Lq, P), int(reference_points.shape[0]), int(reference_points.shape[2])
+
+
+def forward_fused(value, spatial_shapes, level_start_index, reference_points, sampling_offsets, attn_logits):
+    """out [N, Lq, M*D] from RAW offsets / logits: softmax and location arithmetic happen inside the kernel."""
+    lib = load()
+    dev = _check_cuda(value=value, spatial_shapes=spatial_shapes, level_start_index=level_start_index,
+                      reference_points=reference_points, sampling_offsets=sampling_offsets, attn_logits=attn_logits)
+    _check_meta(spatial_shapes, level_start_index)
+    dims, rb, rl = _fused_dims(value, reference_points, sampling_offsets, attn_logits)
+    code = _DTYPES.get(value.dtype)
+    with torch.cuda.device(dev):
+        out = torch.empty((dims.batch, dims.num_query, dims.num_heads * dims.channels), dtype=value.dtype, device=dev)
+        rc = lib.msda_forward_fused(ctypes.byref(dims), code, value.data_ptr(), spatial_shapes.data_ptr(),
+                                    level_start_index.data_ptr(), reference_points.data_ptr(), rb, rl,
+                                    sampling_offsets.data_ptr(), attn_logits.data_ptr(), out.data_ptr(), _stream())
+    if rc != 0:
+        _raise(rc, 'msda_forward_fused')
+    return out
+
+
+def backward_fused(value, spatial_shapes, level_start_index, reference_points, sampling_offsets, attn_logits, grad_output):
+    """(grad_value, grad_sampling_offsets, grad_attn_logits) of the fused entry."""
+    lib = load()
+    dev = _check_cuda(value=value, spatial_shapes=spatial_shapes, level_start_index=level_start_index,
+                      reference_points=reference_points, sampling_offsets=sampling_offsets, attn_logits=attn_logits,
+                      grad_output=grad_output)
+    dims, rb, rl = _fused_dims(value, reference_points, sampling_offsets, attn_logits)
+    code = _DTYPES.get(value.dtype)
+    if grad_output.dtype != value.dtype:
+        raise RuntimeError('grad_output dtype %s != value dtype %s' % (grad_output.dtype, value.dtype))
+    with torch.cuda.device(dev):
+        grad_value = torch.empty_like(value)
+        grad_off = torch.empty_like(sampling_offsets)
+        grad_logits = torch.empty_like(attn_logits)
+        ws_bytes = lib.msda_backward_workspace_bytes(ctypes.byref(dims), code)
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
+        rc = lib.msda_backward_fused(ctypes.byref(dims), code, value.data_ptr(), spatial_shapes.data_ptr(),
+                                     level_start_index.data_ptr(), reference_points.data_ptr(), rb, rl,
+                                     sampling_offsets.data_ptr(), attn_logits.data_ptr(), grad_output.data_ptr(),
+                                     grad_value.data_ptr(), grad_off.data_ptr(), grad_logits.data_ptr(),
+                                     ws.data_ptr() if ws is not None else None, ws_bytes, _stream())
+    if rc != 0:
+        _raise(rc, 'msda_backward_fused')
+    return grad_value, grad_off, grad_logits
+
+
 def debug_point_index(spatial_shapes, level_start_index, sampling_loc, num_heads, channels):
     """[N*Lq*M*L*P, 4] int32: (h_low, w_low, corner mask, corner-1 element offset) per point."""
     lib = load()
@@ -227,7 +324,10 @@ def launch_count():
 def set_tuning(**kv):
     """Benchmark knobs, e.g. set_tuning(fwd_chunk=64, fwd_smem=1); value 0 restores the heuristic.
     Keys: fwd_chunk, bwd_chunk, fwd_min_ctas, bwd_min_ctas, fwd_smem, fwd_smem_threads, fwd_smem_chunks."""
+    global _WANT_HOST_SHAPES
     lib = load()
     for k, v in kv.items():
         if lib.msda_set_tuning(k.encode(), int(v)) != 0:
             _raise(-1, 'msda_set_tuning')
+        if k == 'fwd_smem':
+            _WANT_HOST_SHAPES = int(v) == 2

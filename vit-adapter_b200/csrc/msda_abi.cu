@@ -16,6 +16,8 @@ bool vec_supported(int dtype, int D, int* G_out);
 cudaError_t launch_forward(const Params& p, int dtype, bool vec_ok, int G, int minb, cudaStream_t s);
 cudaError_t launch_backward(const Params& p, int dtype, bool vec_ok, int G, int minb, cudaStream_t s);
 cudaError_t launch_cvt_f32_bf16(const float* src, void* dst, size_t n, cudaStream_t s);
+cudaError_t launch_forward_fused(const Params& p, int dtype, int G, cudaStream_t s);
+cudaError_t launch_backward_fused(const Params& p, int dtype, int G, cudaStream_t s);
 cudaError_t launch_forward_wide(const Params& p, int G, int minb, cudaStream_t s);
 cudaError_t launch_forward_smem(const Params& p, const SmemPlan& plan, int dtype, int G, int nt, cudaStream_t s);
 
@@ -323,6 +325,93 @@ int msda_backward(const msda_dims* dims, int dtype, const void* value, const int
   if (dtype == MSDA_BF16) {
     e = launch_cvt_f32_bf16(reinterpret_cast<const float*>(accum), grad_value, nvalue, s);
     if (e != cudaSuccess) return cuda_fail(e, "msda_backward bf16 convert launch");
+    g_launches.fetch_add(1);
+  }
+  return 0;
+}
+
+static int fused_ref_params(Params& p, const msda_dims* d, const float* ref, int32_t ref_batch, int32_t ref_levels) {
+  if (!ref) return fail(MSDA_E_NULL, "fused entry: reference_points is NULL");
+  if (!(ref_batch == 1 || ref_batch == d->batch) || !(ref_levels == 1 || ref_levels == d->num_levels))
+    return fail(MSDA_E_DIMS, "fused entry: reference_points [%d, Lq, %d, 2] does not broadcast to N=%d, L=%d", ref_batch,
+                ref_levels, d->batch, d->num_levels);
+  if (!aligned(ref, 8)) return fail(MSDA_E_ALIGN, "fused entry: reference_points not 8-byte aligned");
+  p.ref = ref;
+  p.ref_qstride = ref_levels * 2;
+  p.ref_lstride = ref_levels == 1 ? 0 : 2;
+  p.ref_bstride = ref_batch == 1 ? 0 : (long long)d->num_query * ref_levels * 2;
+  return 0;
+}
+
+int msda_forward_fused(const msda_dims* dims, int dtype, const void* value, const int64_t* spatial_shapes,
+                       const int64_t* level_start_index, const float* reference_points, int32_t ref_batch,
+                       int32_t ref_levels, const float* sampling_offsets, const float* attn_logits, void* out,
+                       void* stream) {
+  if (int e = check_dims(dims, dtype)) return e;
+  if (!value || !spatial_shapes || !level_start_index || !sampling_offsets || !attn_logits || !out)
+    return fail(MSDA_E_NULL, "msda_forward_fused: NULL tensor pointer");
+  int G = 0;
+  if (!vec_supported(dtype, dims->channels, &G) || !((dims->num_levels == 3 || dims->num_levels == 1) && dims->num_point == 4))
+    return fail(MSDA_E_UNSUPPORTED, "msda_forward_fused: no fused kernel for dtype=%d D=%d L=%d P=%d", dtype, dims->channels,
+                dims->num_levels, dims->num_point);
+  if (!aligned(value, 16) || !aligned(out, 16) || !aligned(sampling_offsets, 8) || !aligned(attn_logits, 4) ||
+      !aligned(spatial_shapes, 8) || !aligned(level_start_index, 8))
+    return fail(MSDA_E_ALIGN, "msda_forward_fused: misaligned pointer");
+  Params p;
+  fill_params(p, dims);
+  p.value = value; p.shapes = spatial_shapes; p.lsi = level_start_index;
+  p.loc = sampling_offsets; p.aw = attn_logits; p.out = out;
+  if (int e = fused_ref_params(p, dims, reference_points, ref_batch, ref_levels)) return e;
+  p.qc = pick_chunk(dims, kWarps * (32 / G), g_qc_fwd.load());
+  p.nchunk = (p.Lq + p.qc - 1) / p.qc;
+  const cudaError_t e = launch_forward_fused(p, dtype, G, (cudaStream_t)stream);
+  if (e == cudaErrorNotSupported) return fail(MSDA_E_UNSUPPORTED, "msda_forward_fused: no fused kernel for G=%d", G);
+  if (e != cudaSuccess) return cuda_fail(e, "msda_forward_fused launch");
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+int msda_backward_fused(const msda_dims* dims, int dtype, const void* value, const int64_t* spatial_shapes,
+                        const int64_t* level_start_index, const float* reference_points, int32_t ref_batch,
+                        int32_t ref_levels, const float* sampling_offsets, const float* attn_logits,
+                        const void* grad_out, void* grad_value, float* grad_sampling_offsets, float* grad_attn_logits,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  if (int e = check_dims(dims, dtype)) return e;
+  if (!value || !spatial_shapes || !level_start_index || !sampling_offsets || !attn_logits || !grad_out || !grad_value ||
+      !grad_sampling_offsets || !grad_attn_logits)
+    return fail(MSDA_E_NULL, "msda_backward_fused: NULL tensor pointer");
+  const int G = dims->channels / 4;
+  if (!(dtype == MSDA_F32 || dtype == MSDA_BF16) || dims->channels % 4 != 0 || !(G == 8 || G == 16) ||
+      !((dims->num_levels == 3 || dims->num_levels == 1) && dims->num_point == 4))
+    return fail(MSDA_E_UNSUPPORTED, "msda_backward_fused: no fused kernel for dtype=%d D=%d L=%d P=%d", dtype, dims->channels,
+                dims->num_levels, dims->num_point);
+  const size_t need = msda_backward_workspace_bytes(dims, dtype);
+  if (need > 0 && (!workspace || workspace_bytes < need || !aligned(workspace, 16)))
+    return fail(MSDA_E_WORKSPACE, "msda_backward_fused: workspace of %zu bytes (16-byte aligned) required", need);
+  cudaStream_t s = (cudaStream_t)stream;
+  Params p;
+  fill_params(p, dims);
+  p.value = value; p.shapes = spatial_shapes; p.lsi = level_start_index;
+  p.loc = sampling_offsets; p.aw = attn_logits; p.grad_out = grad_out;
+  p.grad_loc = grad_sampling_offsets; p.grad_aw = grad_attn_logits;
+  if (int e = fused_ref_params(p, dims, reference_points, ref_batch, ref_levels)) return e;
+  const size_t nvalue = (size_t)p.N * p.S * p.M * p.D;
+  void* accum = (dtype == MSDA_BF16) ? workspace : grad_value;
+  p.grad_value = accum;
+  if (!aligned(value, 16) || !aligned(grad_out, 16) || !aligned(accum, 16) || !aligned(sampling_offsets, 8) ||
+      !aligned(grad_sampling_offsets, 8))
+    return fail(MSDA_E_ALIGN, "msda_backward_fused: misaligned pointer");
+  p.qc = pick_chunk(dims, kWarps * (32 / G), g_qc_bwd.load());
+  p.nchunk = (p.Lq + p.qc - 1) / p.qc;
+  cudaError_t e = cudaMemsetAsync(accum, 0, nvalue * 4u, s);
+  if (e != cudaSuccess) return cuda_fail(e, "msda_backward_fused memset(grad_value)");
+  e = launch_backward_fused(p, dtype, G, s);
+  if (e == cudaErrorNotSupported) return fail(MSDA_E_UNSUPPORTED, "msda_backward_fused: no fused kernel for G=%d", G);
+  if (e != cudaSuccess) return cuda_fail(e, "msda_backward_fused launch");
+  g_launches.fetch_add(1);
+  if (dtype == MSDA_BF16) {
+    e = launch_cvt_f32_bf16(reinterpret_cast<const float*>(accum), grad_value, nvalue, s);
+    if (e != cudaSuccess) return cuda_fail(e, "msda_backward_fused bf16 convert launch");
     g_launches.fetch_add(1);
   }
   return 0;

@@ -87,8 +87,11 @@ __device__ __forceinline__ void group_transpose_sum(float (&v)[NV], int j) {
 // ---------------------------------------------------------------------------------------------
 // Vector kernel (same work decomposition as the forward).
 // ---------------------------------------------------------------------------------------------
-template <typename T, int G, int LT, int PT, int MINB>
+// FUSED: `loc` / `aw` hold raw offsets / logits (see fused_resolve); grad_loc / grad_aw then receive the gradients
+// w.r.t. the raw offsets / logits (softmax backward and the 1/(W,H) scaling folded in).
+template <typename T, int G, int LT, int PT, int MINB, bool FUSED = false>
 __global__ void __launch_bounds__(kThreads, MINB) msda_bwd_vec_kernel(const Params p) {
+  static_assert(!FUSED || LT > 0, "the fused entry needs compile-time L, P");
   using V = VecB<T>;
   constexpr int kCpl = V::kCpl;
   constexpr int kGpw = 32 / G;
@@ -131,26 +134,31 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_bwd_vec_kernel(const Para
   // locations and attention weights are fetched before the current iteration is processed, so their HBM
   // latency is off the critical path.
   constexpr int kRounds = kStatic ? (LT * PT + G - 1) / G : 1;
-  float2 nxy[kRounds];
+  float2 nxy[kRounds], nrf[kRounds];
   float na[kRounds];
   V ngo = V::zero();
-  auto fetch = [&](int qw_, float2 (&xy_)[kRounds], float (&a_)[kRounds], V& go_) {
+  auto fetch = [&](int qw_, float2 (&xy_)[kRounds], float (&a_)[kRounds], float2 (&rf_)[kRounds], V& go_) {
     const int q_ = qw_ + grp;
     const bool act_ = q_ < bc.q_end;
-    const size_t pair_ = ((size_t)bc.b * p.Lq + (act_ ? q_ : bc.q_begin)) * p.M + bc.m;
+    const int qq_ = act_ ? q_ : bc.q_begin;
+    const size_t pair_ = ((size_t)bc.b * p.Lq + qq_) * p.M + bc.m;
     go_ = act_ ? V::load(gout + pair_ * p.D + j * kCpl) : V::zero();
 #pragma unroll
     for (int r = 0; r < kRounds; ++r) {
       const int pi_ = r * G + j;
       xy_[r] = make_float2(0.f, 0.f);
+      rf_[r] = make_float2(0.f, 0.f);
       a_[r] = 0.f;
       if (pi_ < LP && act_) {
         xy_[r] = __ldg(reinterpret_cast<const float2*>(loc + pair_ * LP * 2) + pi_);
         a_[r] = __ldg(aw + pair_ * LP + pi_);
+        if (FUSED)
+          rf_[r] = __ldg(reinterpret_cast<const float2*>(p.ref + (size_t)bc.b * p.ref_bstride + (size_t)qq_ * p.ref_qstride +
+                                                         (pi_ / (FUSED ? PT : 1)) * p.ref_lstride));
       }
     }
   };
-  if (kStatic) fetch(bc.q_begin + warp * kGpw, nxy, na, ngo);
+  if (kStatic) fetch(bc.q_begin + warp * kGpw, nxy, na, nrf, ngo);
 
   for (int qw = bc.q_begin + warp * kGpw; qw < bc.q_end; qw += kWarps * kGpw) {
     const int q = qw + grp;
@@ -160,13 +168,16 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_bwd_vec_kernel(const Para
     const float* __restrict__ aw_pair = aw + pair * LP;
 
     V go;
-    float2 cxy[kRounds];
+    float2 cxy[kRounds], crf[kRounds];
     float ca[kRounds];
+    float ga_keep[kRounds];  // fused: d/d(attention weight) of this lane's points, kept for the softmax backward
+    float dot_part = 0.f;    // fused: this lane's share of sum_p a_p * dL/da_p
     if (kStatic) {
       go = ngo;
 #pragma unroll
-      for (int r = 0; r < kRounds; ++r) { cxy[r] = nxy[r]; ca[r] = na[r]; }
-      if (qw + kWarps * kGpw < bc.q_end) fetch(qw + kWarps * kGpw, nxy, na, ngo);
+      for (int r = 0; r < kRounds; ++r) { cxy[r] = nxy[r]; ca[r] = na[r]; crf[r] = nrf[r]; ga_keep[r] = 0.f; }
+      if (qw + kWarps * kGpw < bc.q_end) fetch(qw + kWarps * kGpw, nxy, na, nrf, ngo);
+      if constexpr (FUSED) fused_resolve<G, kRounds, (FUSED ? PT : 1)>(cxy, ca, crf, sH, sW, j, LP);
     } else {
       go = active ? V::load(gout + pair * p.D + j * kCpl) : V::zero();
     }
@@ -262,9 +273,23 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_bwd_vec_kernel(const Para
         group_transpose_sum<G, 3 * G>(part, j);
         my_ga = part[0]; my_gw = part[1]; my_gh = part[2];
       }
-      if (mine) {
+      if constexpr (FUSED) {
+        // d loc / d offset = 1 / (W, H): the (W, H) factors of grad_sampling_loc cancel
+        if (mine) reinterpret_cast<float2*>(gloc)[pair * LP + pi] = make_float2(my_gw * a, my_gh * a);
+        ga_keep[r0 / G] = mine ? my_ga : 0.f;
+        dot_part = fmaf(a, ga_keep[r0 / G], dot_part);
+      } else if (mine) {
         gaw[pair * LP + pi] = my_ga;
         reinterpret_cast<float2*>(gloc)[pair * LP + pi] = make_float2(fW * my_gw * a, fH * my_gh * a);
+      }
+    }
+    if constexpr (FUSED) {
+      // softmax backward: d logit_p = a_p * (dL/da_p - sum_p' a_p' dL/da_p')
+      const float dot = group_sum<G>(dot_part);
+#pragma unroll
+      for (int r = 0; r < kRounds; ++r) {
+        const int pi = r * G + j;
+        if (pi < LP && active) gaw[pair * LP + pi] = ca[r] * (ga_keep[r] - dot);
       }
     }
   }
@@ -376,6 +401,27 @@ static cudaError_t launch_vec_g(const Params& p, int minb, dim3 grid, cudaStream
     case 4: return launch_vec_gm<T, G, 4>(p, grid, s);
     default: return launch_vec_gm<T, G, 3>(p, grid, s);
   }
+}
+
+template <typename T, int G>
+static cudaError_t launch_fused_g(const Params& p, dim3 grid, cudaStream_t s) {
+  if (p.L == 3 && p.P == 4) msda_bwd_vec_kernel<T, G, 3, 4, 3, true><<<grid, kThreads, 0, s>>>(p);
+  else if (p.L == 1 && p.P == 4) msda_bwd_vec_kernel<T, G, 1, 4, 3, true><<<grid, kThreads, 0, s>>>(p);
+  else return cudaErrorNotSupported;
+  return cudaGetLastError();
+}
+
+// fused entry: `p.grad_value` is the zero-filled fp32 accumulator (as in launch_backward)
+cudaError_t launch_backward_fused(const Params& p, int dtype, int G, cudaStream_t s) {
+  const dim3 grid((unsigned)((size_t)p.N * p.nchunk * p.M));
+  if (dtype == MSDA_F32) {
+    if (G == 8) return launch_fused_g<float, 8>(p, grid, s);
+    if (G == 16) return launch_fused_g<float, 16>(p, grid, s);
+  } else if (dtype == MSDA_BF16) {
+    if (G == 8) return launch_fused_g<__nv_bfloat16, 8>(p, grid, s);
+    if (G == 16) return launch_fused_g<__nv_bfloat16, 16>(p, grid, s);
+  }
+  return cudaErrorNotSupported;
 }
 
 template <typename T>

@@ -35,6 +35,12 @@ struct Params {
   int N, S, M, D, L, Lq, P;
   int qc;                  // queries per CTA chunk
   int nchunk;              // ceil(Lq / qc)
+  // fused entry points only: `loc` holds RAW sampling offsets, `aw` RAW attention logits, and the
+  // locations / softmax are formed in registers from the reference points below
+  const float* ref;        // reference points [Nr, Lq, Lr, 2]
+  long long ref_bstride;   // floats between batches (0 when Nr == 1: broadcast)
+  int ref_qstride;         // floats between queries (= Lr * 2)
+  int ref_lstride;         // floats between levels  (0 when Lr == 1: broadcast)
 };
 
 // Host-made plan for the shared-memory forward (msda_fwd_smem.cu): which levels' [H*W, D] maps of one
@@ -183,6 +189,43 @@ struct Vec<__nv_bfloat16> {
     *reinterpret_cast<uint4*>(p) = t;
   }
 };
+
+// Fused module arithmetic (reference: detection/ops/modules/ms_deform_attn.py:108-119), done in registers:
+//   attention_weights = softmax(logits over the L*P points of one (b,q,m))
+//   sampling_location = reference_point + sampling_offset / (W_l, H_l)
+// Lane j of a G-lane group holds points j, j+G, ... (R rounds): xy[r] = raw offset, a[r] = raw logit,
+// rf[r] = reference point of that point's level. On return xy[r] = location, a[r] = softmax weight.
+// The max / sum over the L*P points are warp-shuffle reductions inside the group (every lane of the warp
+// must call this). Division and addition are the same fp32 operations torch performs, so the locations —
+// and therefore the corner indices — are bit-identical to the unfused path.
+template <int G, int R, int PT>
+__device__ __forceinline__ void fused_resolve(float2 (&xy)[R], float (&a)[R], const float2 (&rf)[R],
+                                              const int* sH, const int* sW, int j, int LP) {
+  float m = -INFINITY;
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+    if (r * G + j < LP) m = fmaxf(m, a[r]);
+#pragma unroll
+  for (int s = G / 2; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s, G));
+  float sum = 0.f;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    a[r] = (r * G + j < LP) ? expf(a[r] - m) : 0.f;
+    sum += a[r];
+  }
+#pragma unroll
+  for (int s = G / 2; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s, G);
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    a[r] = __fdiv_rn(a[r], sum);
+    const int pi = r * G + j;
+    if (pi < LP) {
+      const int l = pi / PT;
+      xy[r].x = rf[r].x + __fdiv_rn(xy[r].x, (float)sW[l]);
+      xy[r].y = rf[r].y + __fdiv_rn(xy[r].y, (float)sH[l]);
+    }
+  }
+}
 
 // Lane vectors by width: 16 bytes per lane (above) or 32 bytes per lane (fp32 only: 8 channels, one
 // LDG.E.ENL2.256 / STG.E.ENL2.256, the 256-bit global accesses new on sm_100). Wider lanes halve the lanes per

@@ -21,8 +21,10 @@ namespace msda {
 // Vector kernel. T = float | __nv_bfloat16, G = lanes per (b,q,m) (D = G * Vec<T>::kCpl),
 // LT/PT = compile-time levels / points (0,0 = runtime), MINB = min resident CTAs per SM.
 // ---------------------------------------------------------------------------------------------
-template <typename T, int G, int LT, int PT, int MINB, int LB = 16>
+// FUSED: `loc` / `aw` hold raw offsets / logits; locations and the softmax are formed in registers (static L,P only).
+template <typename T, int G, int LT, int PT, int MINB, int LB = 16, bool FUSED = false>
 __global__ void __launch_bounds__(kThreads, MINB) msda_fwd_vec_kernel(const Params p) {
+  static_assert(!FUSED || LT > 0, "the fused entry needs compile-time L, P");
   using V = LaneVec<T, LB>;  // LB = bytes per lane: 16 (LDG.128) or 32 (LDG.256, fp32 only)
   constexpr int kCpl = V::kCpl;
   constexpr int kGpw = 32 / G;  // (b,q,m) groups per warp
@@ -61,24 +63,29 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_fwd_vec_kernel(const Para
   // latency (~800 cycles) would sit at the head of every iteration's dependency chain. The static
   // variants fetch the NEXT iteration's locations and weights before working on the current one.
   constexpr int kRounds = kStatic ? (LT * PT + G - 1) / G : 1;
-  float2 nxy[kRounds];
+  float2 nxy[kRounds], nrf[kRounds];
   float na[kRounds];
-  auto fetch = [&](int qw_, float2 (&xy_)[kRounds], float (&a_)[kRounds]) {
+  auto fetch = [&](int qw_, float2 (&xy_)[kRounds], float (&a_)[kRounds], float2 (&rf_)[kRounds]) {
     const int q_ = qw_ + grp;
     const bool act_ = q_ < bc.q_end;
-    const size_t pair_ = ((size_t)bc.b * p.Lq + (act_ ? q_ : bc.q_begin)) * p.M + bc.m;
+    const int qq_ = act_ ? q_ : bc.q_begin;
+    const size_t pair_ = ((size_t)bc.b * p.Lq + qq_) * p.M + bc.m;
 #pragma unroll
     for (int r = 0; r < kRounds; ++r) {
       const int pi_ = r * G + j;
       xy_[r] = make_float2(0.f, 0.f);
+      rf_[r] = make_float2(0.f, 0.f);
       a_[r] = 0.f;
       if (pi_ < LP && act_) {
         xy_[r] = __ldg(reinterpret_cast<const float2*>(loc + pair_ * LP * 2) + pi_);
         a_[r] = __ldg(aw + pair_ * LP + pi_);
+        if (FUSED)
+          rf_[r] = __ldg(reinterpret_cast<const float2*>(p.ref + (size_t)bc.b * p.ref_bstride + (size_t)qq_ * p.ref_qstride +
+                                                         (pi_ / (FUSED ? PT : 1)) * p.ref_lstride));
       }
     }
   };
-  if (kStatic) fetch(bc.q_begin + warp * kGpw, nxy, na);
+  if (kStatic) fetch(bc.q_begin + warp * kGpw, nxy, na, nrf);
 
   for (int qw = bc.q_begin + warp * kGpw; qw < bc.q_end; qw += kWarps * kGpw) {
     const int q = qw + grp;
@@ -87,12 +94,13 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_fwd_vec_kernel(const Para
     const float* __restrict__ loc_pair = loc + pair * LP * 2;
     const float* __restrict__ aw_pair = aw + pair * LP;
 
-    float2 cxy[kRounds];
+    float2 cxy[kRounds], crf[kRounds];
     float ca[kRounds];
     if (kStatic) {
 #pragma unroll
-      for (int r = 0; r < kRounds; ++r) { cxy[r] = nxy[r]; ca[r] = na[r]; }
-      if (qw + kWarps * kGpw < bc.q_end) fetch(qw + kWarps * kGpw, nxy, na);
+      for (int r = 0; r < kRounds; ++r) { cxy[r] = nxy[r]; ca[r] = na[r]; crf[r] = nrf[r]; }
+      if (qw + kWarps * kGpw < bc.q_end) fetch(qw + kWarps * kGpw, nxy, na, nrf);
+      if constexpr (FUSED) fused_resolve<G, kRounds, (FUSED ? PT : 1)>(cxy, ca, crf, sH, sW, j, LP);
     }
 
     V acc = V::zero();
@@ -242,6 +250,27 @@ cudaError_t launch_forward_wide(const Params& p, int G, int minb, cudaStream_t s
     case 8: return launch_wide_g<8>(p, minb, grid, s);
     default: return cudaErrorNotSupported;
   }
+}
+
+// fused entry (raw offsets + logits + reference points): static (L,P) in {(3,4),(1,4)} only
+template <typename T, int G>
+static cudaError_t launch_fused_g(const Params& p, dim3 grid, cudaStream_t s) {
+  if (p.L == 3 && p.P == 4) msda_fwd_vec_kernel<T, G, 3, 4, 4, 16, true><<<grid, kThreads, 0, s>>>(p);
+  else if (p.L == 1 && p.P == 4) msda_fwd_vec_kernel<T, G, 1, 4, 4, 16, true><<<grid, kThreads, 0, s>>>(p);
+  else return cudaErrorNotSupported;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_forward_fused(const Params& p, int dtype, int G, cudaStream_t s) {
+  const dim3 grid((unsigned)((size_t)p.N * p.nchunk * p.M));
+  if (dtype == MSDA_F32) {
+    if (G == 8) return launch_fused_g<float, 8>(p, grid, s);
+    if (G == 16) return launch_fused_g<float, 16>(p, grid, s);
+  } else if (dtype == MSDA_BF16) {
+    if (G == 4) return launch_fused_g<__nv_bfloat16, 4>(p, grid, s);
+    if (G == 8) return launch_fused_g<__nv_bfloat16, 8>(p, grid, s);
+  }
+  return cudaErrorNotSupported;
 }
 
 template <typename T>

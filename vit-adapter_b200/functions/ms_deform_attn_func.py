@@ -61,3 +61,42 @@ class MSDeformAttnFunction(Function):
         grad_value, grad_loc, grad_attn = _cabi.backward(
             value, shapes, level_start, loc, attn, grad_output, ctx.im2col_step)
         return grad_value, None, None, grad_loc, grad_attn, None
+
+
+class MSDeformAttnFusedFunction(Function):
+    """Sampling core + the module arithmetic around it in one kernel (no reference counterpart as a
+    separate Function: it fuses detection/ops/modules/ms_deform_attn.py:108-119 into the op):
+
+        apply(value, spatial_shapes, level_start_index, reference_points, sampling_offsets, attn_logits)
+
+    with RAW `sampling_offsets` [N,Lq,M,L,P,2] and RAW pre-softmax `attn_logits` [N,Lq,M,L*P]; the kernel forms
+    softmax(attn_logits) and reference_point + offset / (W_l, H_l) in registers, so neither tensor is written
+    to HBM, and the backward returns gradients w.r.t. the raw offsets / logits. `reference_points` is
+    [1|N, Lq, 1|L, 2] (no gradient, as in the adapter where it is a constant grid).
+    Same AMP policy as MSDeformAttnFunction. Use `_cabi.fused_supported` to check for a kernel."""
+
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, reference_points, sampling_offsets,
+                attn_logits):
+        if torch.is_autocast_enabled('cuda') and value.is_cuda:
+            value = value.to(_AMP_VALUE_DTYPE)
+        if value.dtype == torch.float16:
+            value = value.float()
+        reference_points = reference_points.float().contiguous()
+        sampling_offsets = sampling_offsets.float().contiguous()
+        attn_logits = attn_logits.float().contiguous()
+        output = _cabi.forward_fused(value, value_spatial_shapes, value_level_start_index, reference_points,
+                                     sampling_offsets, attn_logits)
+        ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index, reference_points,
+                              sampling_offsets, attn_logits)
+        return output
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, shapes, level_start, ref, offsets, logits = ctx.saved_tensors
+        if grad_output.dtype != value.dtype:
+            grad_output = grad_output.to(value.dtype)
+        grad_value, grad_off, grad_logits = _cabi.backward_fused(value, shapes, level_start, ref, offsets, logits,
+                                                                 grad_output.contiguous())
+        return grad_value, None, None, None, grad_off, grad_logits
