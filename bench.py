@@ -453,6 +453,46 @@ def run_ours(args):
         except Exception as e:  # informational only
             ref_cuda = {'error': repr(e)}
 
+    # ---- informational: the other BASELINE shapes (north star: ViT-Adapter-L 896^2), same protocol, rank 0 -------
+    other = None
+    if rank == 0 and not args.no_other_shapes:
+        other = []
+        flushbuf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        for ov, odt in (('L', 'bf16'), ('L', 'f32'), ('L64', 'bf16'), ('HTC', 'f32')):
+            oM, oD, oside, ob = VARIANTS[ov]
+            tdt = torch.float32 if odt == 'f32' else torch.bfloat16
+            tot_ms, tot_pts, tot_bytes = 0.0, 0, 0
+            for ci, (name, N_, M_, D_, Lq_, shp) in enumerate(call_shapes(ov, ob)):
+                hin = adapter_inputs(name, N_, M_, D_, Lq_, shp, seed=77 + ci, dtype=tdt)
+                din = {k: v.to(dev) for k, v in hin.items()}
+                ab = algorithmic_bytes(N_, M_, D_, Lq_, shp, 4 if odt == 'f32' else 2)
+                fw = lambda: _cabi.forward(din['value'], din['shapes'], din['lsi'], din['loc'], din['aw'], 64)
+                bw = lambda: _cabi.backward(din['value'], din['shapes'], din['lsi'], din['loc'], din['aw'], din['grad_out'], 64)
+                for fn, key in ((fw, 'fwd'), (bw, 'bwd')):
+                    if ov == 'HTC' and key == 'bwd':
+                        continue  # inference shape
+                    for _ in range(3):
+                        fn()
+                    ts = []
+                    for _ in range(10):
+                        flushbuf.zero_()
+                        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        x0.record()
+                        fn()
+                        x1.record()
+                        torch.cuda.synchronize()
+                        ts.append(x0.elapsed_time(x1))
+                    ts.sort()
+                    tot_ms += ts[len(ts) // 2]
+                    tot_bytes += ab[key]
+                tot_pts += n_points(N_, M_, Lq_, len(shp))
+            other.append({'variant': ov, 'dtype': odt, 'image': oside, 'batch': ob, 'heads': oM, 'channels': oD,
+                          'what': 'Injector+Extractor ' + ('fwd' if ov == 'HTC' else 'fwd+bwd') + ', L2 flushed, median of 10',
+                          'us': tot_ms * 1e3, 'gsamples_s': tot_pts / (tot_ms * 1e-3) / 1e9,
+                          'hbm_frac': tot_bytes / (tot_ms * 1e-3) / 1e9 / (float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'])
+                                                                     if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else 6650.0)})
+        del flushbuf
+
     # ---- roofline of the dominant kernel ------------------------------------------------------------------
     peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(peaks_path):
@@ -496,7 +536,7 @@ def run_ours(args):
             'e2e': {'value': e2e_value, 'unit': 'Gsamples/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': e2e_ms / e2e_steps, 'steps': e2e_steps, 'api': 'MSDeformAttnFunction.apply + autograd backward; pinned host buffers; copy-in / compute / copy-out on 3 streams, double-buffered'},
             'gpu_launches': launches, 'clocks': clocks, 'kernels': kernels, 'ref_cuda': ref_cuda,
-            'points_per_step_per_gpu': pts_step,
+            'points_per_step_per_gpu': pts_step, 'other_shapes': other,
         }
         emit(line)
     if world > 1:
@@ -543,6 +583,7 @@ def main():
     ap.add_argument('--batch', type=int, default=0, help='images per GPU (0 = the variant default)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-ref-cuda', action='store_true')
+    ap.add_argument('--no-other-shapes', action='store_true')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours':
         args.warmup = 3

@@ -20,19 +20,26 @@ DEV = torch.device('cuda', 0)
 
 
 def timeit(fn, iters, warm, flush):
+    """flushed: a 256 MB write precedes every timed call (it also keeps the GPU busy while the call is enqueued, so
+    no launch latency leaks into the events). warm: 10 back-to-back calls per event pair (the first call of an idle GPU
+    would otherwise add the host's ~15 us enqueue latency), reported per call."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
     ts = []
+    reps = 1 if flush is not None else 10
     for _ in range(iters):
         if flush is not None:
             flush.zero_()
+        else:
+            fn()  # keeps the queue non-empty when the first event is recorded
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        fn()
+        for _ in range(reps):
+            fn()
         e1.record()
         torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
+        ts.append(e0.elapsed_time(e1) / reps)
     ts.sort()
     return {'min': ts[0], 'med': ts[len(ts) // 2]}
 

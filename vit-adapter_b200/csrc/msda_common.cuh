@@ -328,6 +328,8 @@ __device__ __forceinline__ void st_scalar(double* p, double v) { *p = v; }
 struct BlockCoord {
   int b, m, q_begin, q_end;
 };
+// (Walking the batch back-to-front in the backward, so that the tail of the grad_value memset is still in L2
+// when its atomics arrive, was measured: no change — 240.6 vs 240.6 us on the 132 MB Injector tensor.)
 __device__ __forceinline__ BlockCoord block_coord(const Params& p) {
   BlockCoord c;
   const int bid = blockIdx.x;
