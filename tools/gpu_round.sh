@@ -1,0 +1,14 @@
+#!/bin/bash
+# One GPU-box pass: parity tests, smoke, headline bench (both arms), shape sweep, ncu launch list + full capture.
+#   gpurun --timeout 2400 -- 'bash tools/gpu_round.sh'
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/pytest_gpu.log
+timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench.err; echo "ref rc=$?"
+timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench.json 2>> gpurun_out/bench.err; echo "bench rc=$?"
+timeout 1200 python tools/sweep.py --variants B,S,T,L,L64,HTC --iters 30 --out gpurun_out/sweep.json > gpurun_out/sweep.log 2>&1; echo "sweep rc=$?"
+python tools/profile_step.py > gpurun_out/plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python tools/profile_step.py > gpurun_out/ncu_launches.log 2>&1
+python tools/profile_step.py > gpurun_out/plain.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:msda_ -s 8 -c 4 -o gpurun_out/prof python tools/profile_step.py > gpurun_out/ncu_full.log 2>&1
+ls -la gpurun_out

@@ -158,8 +158,6 @@ __global__ void __launch_bounds__(NT, 1) msda_fwd_smem_kernel(const Params p, co
 #pragma unroll
       for (int jj = 0; jj < G; ++jj) {
         if (r0 + jj < LP) {
-          constexpr int kDummy = 0;
-          (void)kDummy;
           const int l = (r0 + jj) / PT;  // compile-time after unrolling
           const unsigned of = __shfl_sync(0xffffffffu, offf, jj, G);
           const float a1 = __shfl_sync(0xffffffffu, w0, jj, G);
