@@ -384,7 +384,7 @@ SMEM_SHAPES = [
     ('B-injector', 2, 12, 32, 256, [(32, 32), (16, 16), (8, 8)], 4, 'adapter'),
     ('S-injector', 2, 6, 64, 256, [(32, 32), (16, 16), (8, 8)], 4, 'edges'),
     ('ragged-3lvl', 3, 5, 32, 37, [(7, 9), (3, 4), (2, 5)], 4, 'edges'),
-    ('one-level-big', 1, 2, 32, 700, [(40, 44)], 4, 'uniform'),       # 1760 rows x 128 B = 220 KB: just fits
+    ('one-level-big', 1, 2, 32, 700, [(38, 42)], 4, 'edges'),         # padded 40x44 rows x 128 B + null block: just fits
     ('too-big-level0', 1, 2, 32, 300, [(64, 64), (20, 20), (3, 3)], 4, 'edges'),  # level 0 stays on the L1 path
 ]
 

@@ -108,24 +108,37 @@ static bool plan_forward_smem(const msda_dims* d, int dtype, int G, const int64_
     if (H <= 0 || W <= 0 || H > (1 << 20) || W > (1 << 20)) return false;
     plan->H[l] = (int)H; plan->W[l] = (int)W; plan->start[l] = (int)start;
     start += H * W;
-    bytes[l] = H * W * (int64_t)rowB;
+    bytes[l] = (H + 2) * (W + 2) * (int64_t)rowB;  // zero-padded by one token on every side
     order[l] = l;
   }
   if (start != d->spatial_size) return false;  // host shapes do not describe this value tensor
   for (int a = 0; a < L; ++a)
     for (int b = a + 1; b < L; ++b)
       if (bytes[order[b]] < bytes[order[a]]) { const int t = order[a]; order[a] = order[b]; order[b] = t; }
-  int64_t total = 0;
+  // Layout: [null block of zeros | staged level maps]. The null block is where skipped samples point; it must
+  // cover the 2x2 footprint at the row stride of the widest staged level: (W + 2) + 2 rows.
   int nstaged = 0;
-  for (int a = 0; a < L; ++a) {
-    const int l = order[a];
-    if (total + bytes[l] > (int64_t)kSmemBudget) break;
-    plan->smem_off[l] = (unsigned)total;
-    plan->staged |= 1u << l;
-    total += bytes[l];
-    ++nstaged;
+  int64_t total = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    int64_t maxW = 0;
+    for (int l = 0; l < L; ++l)
+      if (plan->staged & (1u << l)) maxW = plan->W[l] > maxW ? plan->W[l] : maxW;
+    const int64_t null_bytes = pass == 0 ? 0 : (maxW + 4) * (int64_t)rowB;
+    plan->staged = 0;
+    nstaged = 0;
+    total = null_bytes;
+    for (int a = 0; a < L; ++a) {
+      const int l = order[a];
+      // pass 0 sizes the candidate set without the null block; pass 1 re-fits with it (may drop the largest)
+      const int64_t reserve = pass == 0 ? (int64_t)(plan->W[l] + 4) * rowB : 0;
+      if (total + bytes[l] + reserve > (int64_t)kSmemBudget) break;
+      plan->smem_off[l] = (unsigned)total;
+      plan->staged |= 1u << l;
+      total += bytes[l];
+      ++nstaged;
+    }
+    if (nstaged == 0) return false;
   }
-  if (nstaged == 0) return false;
   plan->total_bytes = (unsigned)total;
 
   const int per_iter = (nt / 32) * (32 / G);

@@ -1,21 +1,27 @@
 // msda_fwd_smem.cu — forward with whole-level value maps staged in shared memory (sm_100a).
 //
-// EXPERIMENTAL, OPT-IN (tuning key "fwd_smem" = 2). Idea: when a level's map of one head ([H*W, D])
-// fits in shared memory, a CTA that owns (batch b, head m, a long chunk of queries) copies that map in
-// ONCE (token rows are 128-byte pieces strided by M*D in global memory; copied with 16-byte cp.async
-// (LDGSTS) by all threads — one 1-D TMA bulk copy (UBLKCP) per 128-byte row was measured 3x slower: the
-// bulk engine wants larger boxes) and then gathers from shared memory; levels that do not fit keep
-// the L1 path.
-// Measured outcome (profiles/r1_fwd_smem_vs_l1.md): bit-identical results, but NOT faster than
-// msda_fwd.cu at the adapter shapes — an LDS.128 over 4 different rows costs the same 4 LSU data-pipe
-// wavefronts as the L1-hitting LDG.128, and that pipe (~76% busy in both kernels) is the limiter, not
-// L1 misses or L2 bandwidth. It only removes L2->L1 traffic. Kept because the host-shape plan /
-// staging code is what a tiled backward would build on.
-// Typical plans (chosen on the host from the level shapes, see plan_forward_smem in msda_abi.cu):
-//   Extractor  512^2: the single 32x32 level (128 KB fp32)            -> all gathers from smem
-//   Injector   512^2: levels 1 and 2 (32x32 + 16x16 = 160 KB fp32)    -> 2/3 of the gathers from smem
-//   L 896^2 bf16 Extractor: the 56x56 level (196 KB)                  -> all gathers from smem
-// Arithmetic is identical to msda_fwd.cu (same point_geom / weights / accumulation order).
+// OPT-IN (tuning key "fwd_smem" = 2); needs the level shapes on the host (msda_forward_ex).
+// Why: the L1 serves this op's gather pattern (8 lanes x 16 B per 128-byte row, rows at unrelated
+// addresses) at ~0.49 rows per SM-cycle (142 rows/ns chip-wide; the texture path is no better), and
+// the L1-path forward (msda_fwd.cu) sits on that ceiling; from shared memory the same pattern costs one
+// LSU wavefront (~1 cycle) per row.
+// Measured outcome (profiles/r1_fwd_smem_vs_l1.md): with the gathers at 1 cycle per row the 5 broadcast
+// shuffles per point (also LSU wavefronts) become 1/4 of the pipe load, and the kernel ends up at ~79 % of
+// the same LSU data pipe: ViT-Adapter-B bs16 Extractor 115.6 vs 121.8 us fp32, 77.8 vs 97.3 us bf16;
+// Injector (levels 1+2 staged, level 0 still through L1) 98-115 vs 97 us. Not a robust win, so opt-in.
+//
+// Design. A CTA owns (batch b, head m, a long chunk of queries). For every level that fits
+// (plan made on the host, plan_forward_smem in msda_abi.cu) it copies that head's [H*W, D] map into
+// shared memory ONCE with 16-byte cp.async (LDGSTS; one 1-D TMA bulk copy per 128-byte row was
+// measured 3x slower — the bulk engine wants bigger boxes than a strided token row), into a map
+// that is ZERO-PADDED by one token on every side. The halo makes the op's zero-padding rule
+// (ms_deform_im2col_cuda.cuh:56-78: corners outside the level read as 0) a property of the data:
+// no corner masks, no clamping, no predicates — a point is just base + 4 LDS.128 at fixed deltas
+// (+rowB, +rowstride, +both) and 16 FFMAs. Samples that fail the bounds test (:288) point at an
+// all-zero block with zero weights. Levels that do not fit keep the L1 path of msda_fwd.cu
+// (clamped rows, packed flags) inside the same kernel.
+// Results are bit-identical to msda_fwd.cu (tests/test_op_gpu.py::test_smem_forward_bit_identical):
+// a corner the L1 path multiplies by a zeroed weight is here a zero value times the weight.
 #include "msda_common.cuh"
 
 namespace msda {
@@ -48,6 +54,8 @@ __device__ __forceinline__ Vec<__nv_bfloat16> lds_vec<__nv_bfloat16>(unsigned ad
 }
 
 // T, G, LT, PT as in msda_fwd.cu; NT = threads per CTA (one CTA per SM: the maps use most of the smem).
+// Shared-memory layout (bytes): [0, plan.null_bytes) all zeros; then per staged level l at plan.smem_off[l]
+// a (H+2) x (W+2) grid of kRowB-byte rows, interior = the level's tokens, border = zeros.
 template <typename T, int G, int LT, int PT, int NT>
 __global__ void __launch_bounds__(NT, 1) msda_fwd_smem_kernel(const Params p, const SmemPlan plan) {
   using V = Vec<T>;
@@ -68,26 +76,28 @@ __global__ void __launch_bounds__(NT, 1) msda_fwd_smem_kernel(const Params p, co
   const char* __restrict__ slab = reinterpret_cast<const char*>(p.value) +
                                   ((size_t)bc.b * p.S * MD + (size_t)bc.m * p.D) * sizeof(T);
 
-  // ---- stage the planned levels: 16-byte cp.async per lane, G lanes per token row -------------------
+  // ---- zero everything (null block + halos), then stage the interiors with cp.async -----------------
+  for (unsigned o = threadIdx.x * 16u; o < plan.total_bytes; o += NT * 16u)
+    *reinterpret_cast<uint4*>(smem + o) = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
 #pragma unroll
   for (int l = 0; l < LT; ++l) {
     if (plan.staged & (1u << l)) {
-      const int rows = plan.H[l] * plan.W[l];
+      const int W = plan.W[l], rows = plan.H[l] * W;
       const char* src = slab + (size_t)plan.start[l] * MDb + (threadIdx.x % G) * 16;
       const unsigned dst = smem_u32(smem) + plan.smem_off[l] + (threadIdx.x % G) * 16;
-      for (int r = threadIdx.x / G; r < rows; r += NT / G) cp_async_16(dst + (unsigned)r * kRowB, src + (size_t)r * MDb);
+      for (int r = threadIdx.x / G; r < rows; r += NT / G) {
+        const int h = r / W, w = r - h * W;
+        cp_async_16(dst + (unsigned)((h + 1) * (W + 2) + (w + 1)) * kRowB, src + (size_t)r * MDb);
+      }
     }
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
 
-  unsigned rsl[LT];   // bytes between rows of a level: in the smem map (staged) or in global (not staged)
-  unsigned csl[LT];   // bytes between neighbouring tokens
+  unsigned rsl[LT];  // bytes between rows: padded smem map (staged) or global (not staged)
 #pragma unroll
-  for (int l = 0; l < LT; ++l) {
-    const bool st = plan.staged & (1u << l);
-    csl[l] = st ? kRowB : MDb;
-    rsl[l] = (unsigned)plan.W[l] * csl[l];
-  }
+  for (int l = 0; l < LT; ++l)
+    rsl[l] = (plan.staged & (1u << l)) ? (unsigned)(plan.W[l] + 2) * kRowB : (unsigned)plan.W[l] * MDb;
 
   const char* __restrict__ vb = slab + j * 16;
   const unsigned sb = smem_u32(smem) + j * 16;
@@ -137,22 +147,31 @@ __global__ void __launch_bounds__(NT, 1) msda_fwd_smem_kernel(const Params p, co
     for (int r0 = 0; r0 < LP; r0 += G) {
       // ---- producer ------------------------------------------------------------------------------------
       const int pi = r0 + j;
-      unsigned offf = 0u;
+      unsigned offf = 0u;  // staged: smem byte offset of the (h_low, w_low) row of the padded map (null block if skipped)
+                           // not staged: packed clamped global offset | flags, as in msda_fwd.cu
       float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
       if (pi < LP && active) {
         const int l = pi / PT;
         const int H = plan.H[l], W = plan.W[l];
         const float2 xy = cxy[r0 / G];
         const float a = ca[r0 / G];
-        const PointGeom<float> g = point_geom<float>(xy.x, xy.y, H, W);
-        const float hh = 1.f - g.lh, hw = 1.f - g.lw;
-        w0 = (g.mask & 1u) ? (hh * hw) * a : 0.f;
-        w1 = (g.mask & 2u) ? (hh * g.lw) * a : 0.f;
-        w2 = (g.mask & 4u) ? (g.lh * hw) * a : 0.f;
-        w3 = (g.mask & 8u) ? (g.lh * g.lw) * a : 0.f;
-        const bool st = plan.staged & (1u << l);
-        // staged: byte offset inside the level's smem map; else: byte offset inside the (b,m) slab in global
-        offf = st ? (tap_offset(g, H, W, 0, kRowB) + plan.smem_off[l]) : tap_offset(g, H, W, plan.start[l], MDb);
+        if (plan.staged & (1u << l)) {
+          const float h_im = fmaf(xy.y, (float)H, -0.5f), w_im = fmaf(xy.x, (float)W, -0.5f);
+          if (h_im > -1.f && w_im > -1.f && h_im < (float)H && w_im < (float)W) {
+            const float hf = floorf(h_im), wf = floorf(w_im);
+            const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw = 1.f - lw;
+            w0 = (hh * hw) * a; w1 = (hh * lw) * a; w2 = (lh * hw) * a; w3 = (lh * lw) * a;
+            offf = plan.smem_off[l] + (unsigned)(((int)hf + 1) * (W + 2) + ((int)wf + 1)) * kRowB;
+          }
+        } else {
+          const PointGeom<float> g = point_geom<float>(xy.x, xy.y, H, W);
+          const float hh = 1.f - g.lh, hw = 1.f - g.lw;
+          w0 = (g.mask & 1u) ? (hh * hw) * a : 0.f;
+          w1 = (g.mask & 2u) ? (hh * g.lw) * a : 0.f;
+          w2 = (g.mask & 4u) ? (g.lh * hw) * a : 0.f;
+          w3 = (g.mask & 8u) ? (g.lh * g.lw) * a : 0.f;
+          offf = tap_offset(g, H, W, plan.start[l], MDb);
+        }
       }
       // ---- consumers -----------------------------------------------------------------------------------
 #pragma unroll
@@ -164,28 +183,32 @@ __global__ void __launch_bounds__(NT, 1) msda_fwd_smem_kernel(const Params p, co
           const float a2 = __shfl_sync(0xffffffffu, w1, jj, G);
           const float a3 = __shfl_sync(0xffffffffu, w2, jj, G);
           const float a4 = __shfl_sync(0xffffffffu, w3, jj, G);
-          const unsigned o1 = of & ~15u;
-          const unsigned dcol = (of & 1u) ? csl[l] : 0u;
-          const unsigned drow = (of & 2u) ? rsl[l] : 0u;
-          V v1, v2, v3, v4;
           if (plan.staged & (1u << l)) {  // uniform
-            v1 = lds_vec<T>(sb + o1);
-            v2 = lds_vec<T>(sb + o1 + dcol);
-            v3 = lds_vec<T>(sb + o1 + drow);
-            v4 = lds_vec<T>(sb + o1 + drow + dcol);
-          } else {
-            const char* p1 = ptr_add(vb, o1);
-            const char* p2 = ptr_add(p1, dcol);
-            const char* p3 = ptr_add(p1, drow);
-            const char* p4 = ptr_add(p3, dcol);
-            v1 = V::load(reinterpret_cast<const T*>(p1));
-            v2 = V::load(reinterpret_cast<const T*>(p2));
-            v3 = V::load(reinterpret_cast<const T*>(p3));
-            v4 = V::load(reinterpret_cast<const T*>(p4));
-          }
+            const unsigned s1 = sb + of, s3 = s1 + rsl[l];
+            const V v1 = lds_vec<T>(s1);
+            const V v2 = lds_vec<T>(s1 + kRowB);
+            const V v3 = lds_vec<T>(s3);
+            const V v4 = lds_vec<T>(s3 + kRowB);
 #pragma unroll
-          for (int c0 = 0; c0 < kCpl; c0 += 4)
-            fma4x4_if(of & 4u, &acc.v[c0], a1, a2, a3, a4, &v1.v[c0], &v2.v[c0], &v3.v[c0], &v4.v[c0]);
+            for (int c = 0; c < kCpl; ++c) {
+              acc.v[c] = fmaf(a1, v1.v[c], acc.v[c]);
+              acc.v[c] = fmaf(a2, v2.v[c], acc.v[c]);
+              acc.v[c] = fmaf(a3, v3.v[c], acc.v[c]);
+              acc.v[c] = fmaf(a4, v4.v[c], acc.v[c]);
+            }
+          } else {
+            const char* p1 = ptr_add(vb, of & ~15u);
+            const char* p2 = ptr_madd(p1, of & 1u, MDb);
+            const char* p3 = ptr_madd(p1, (of >> 1) & 1u, rsl[l]);
+            const char* p4 = ptr_madd(p3, of & 1u, MDb);
+            const V v1 = V::load(reinterpret_cast<const T*>(p1));
+            const V v2 = V::load(reinterpret_cast<const T*>(p2));
+            const V v3 = V::load(reinterpret_cast<const T*>(p3));
+            const V v4 = V::load(reinterpret_cast<const T*>(p4));
+#pragma unroll
+            for (int c0 = 0; c0 < kCpl; c0 += 4)
+              fma4x4_if(of & 4u, &acc.v[c0], a1, a2, a3, a4, &v1.v[c0], &v2.v[c0], &v3.v[c0], &v4.v[c0]);
+          }
         }
       }
     }
