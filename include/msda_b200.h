@@ -146,6 +146,10 @@ int msda_backward(const msda_dims* dims, int dtype,
  *                     `reference_points[:, :, None, :, None, :]` are supported)
  *   sampling_offsets  [N, Lq, M, L, P, 2] f32 — raw output of the `sampling_offsets` linear
  *   attn_logits       [N, Lq, M, L*P]     f32 — raw output of the `attention_weights` linear (pre-softmax)
+ *   offsets_row_stride / logits_row_stride: floats between consecutive (b, q) rows of the two tensors; 0 = dense
+ *                     (M*L*P*2 and M*L*P). Non-dense strides let both be column blocks of ONE merged GEMM output
+ *                     [N*Lq, M*L*P*3] (`sampling_offsets` and `attention_weights` share the same input); the
+ *                     gradients are written with the same strides, so they form the merged GEMM's output gradient.
  * The backward returns gradients w.r.t. the raw offsets and logits (softmax backward folded in).
  * Supported: dtype f32 / bf16, (L, P) in {(3,4), (1,4)}, D*sizeof(T) a multiple of 16 with 2..32 lanes;
  * anything else returns MSDA_E_UNSUPPORTED and the caller uses msda_forward / msda_backward. */
@@ -156,6 +160,7 @@ int msda_forward_fused(const msda_dims* dims, int dtype,
                        const float* reference_points, int32_t ref_batch, int32_t ref_levels,
                        const float* sampling_offsets,
                        const float* attn_logits,
+                       int64_t offsets_row_stride, int64_t logits_row_stride,
                        void* out,
                        void* stream);
 
@@ -166,6 +171,7 @@ int msda_backward_fused(const msda_dims* dims, int dtype,
                         const float* reference_points, int32_t ref_batch, int32_t ref_levels,
                         const float* sampling_offsets,
                         const float* attn_logits,
+                        int64_t offsets_row_stride, int64_t logits_row_stride,
                         const void* grad_out,
                         void* grad_value,
                         float* grad_sampling_offsets,

@@ -69,6 +69,29 @@ def test_fused_matches_unfused(cfg, dtype):
     torch.testing.assert_close(l1.grad, l2.grad, rtol=gt, atol=gt * _scale(l2.grad))
 
 
+@pytest.mark.parametrize('cfg', CASES[:3], ids=[c[0] for c in CASES[:3]])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['f32', 'bf16'])
+def test_merged_gemm_layout_is_bit_identical_to_separate_tensors(cfg, dtype):
+    """Offsets and logits read in place from one [N, Lq, M*L*P*3] buffer (the merged GEMM output) must give exactly
+    the results of the two separate tensors, and the merged gradient must be their concatenation."""
+    _, N, M, D, Lq, shapes, rb, rl = cfg
+    L = len(shapes)
+    value, shapes_t, lsi, ref, offsets, logits, go = _raw_inputs(N, M, D, Lq, shapes, 4, 35, rb, rl, dtype)
+    merged = torch.cat([offsets.reshape(N, Lq, -1), logits.reshape(N, Lq, -1)], -1).contiguous()
+    v1, o1, l1 = value.clone().requires_grad_(), offsets.clone().requires_grad_(), logits.clone().requires_grad_()
+    out1 = vab.MSDeformAttnFusedFunction.apply(v1, shapes_t, lsi, ref, o1, l1)
+    out1.backward(go)
+    v2, m2 = value.clone().requires_grad_(), merged.clone().requires_grad_()
+    out2 = vab.MSDeformAttnMergedFunction.apply(v2, shapes_t, lsi, ref, m2, L, 4)
+    out2.backward(go)
+    torch.cuda.synchronize()
+    assert torch.equal(out1, out2)
+    want = torch.cat([o1.grad.reshape(N, Lq, -1), l1.grad.reshape(N, Lq, -1)], -1)
+    assert torch.equal(m2.grad, want)
+    gt = 1e-4 if dtype == torch.float32 else 1e-2  # atomic order (+ one bf16 rounding of the converted result)
+    torch.testing.assert_close(v1.grad.float(), v2.grad.float(), rtol=gt, atol=gt * _scale(v2.grad.float()))
+
+
 def test_fused_locations_are_bit_identical():
     """With one point carrying all the attention (one-hot logits) the softmax is exactly {0,1}, so any difference
     between fused and unfused outputs could only come from the location arithmetic: there must be none."""
@@ -112,8 +135,9 @@ def test_module_fused_vs_reference_sequence(dtype):
         vab.set_amp_value_dtype(torch.bfloat16)
     try:
         res = []
-        for fused in (True, False):
+        for fused, merge in ((True, True), (False, False), (True, False)):
             m.fused = fused
+            m.merge_query_linears = merge
             m.zero_grad(set_to_none=True)
             q, f = query.clone().requires_grad_(), feat.clone().requires_grad_()
             n0 = _cabi.launch_count()
@@ -125,13 +149,15 @@ def test_module_fused_vs_reference_sequence(dtype):
     finally:
         vab.set_amp_value_dtype(torch.float32)
         m.fused = True
+        m.merge_query_linears = True
     tol = 1e-4 if not amp else 3e-2
-    torch.testing.assert_close(res[0][0], res[1][0], rtol=tol, atol=tol * _scale(res[1][0]))
-    torch.testing.assert_close(res[0][1], res[1][1], rtol=tol, atol=tol * _scale(res[1][1]))
-    torch.testing.assert_close(res[0][2], res[1][2], rtol=tol, atol=tol * _scale(res[1][2]))
-    for k in res[0][3]:
-        torch.testing.assert_close(res[0][3][k], res[1][3][k], rtol=tol, atol=tol * _scale(res[1][3][k]), msg=k)
-    assert res[0][4] >= 2 and res[1][4] >= 2  # both paths ran our kernels
+    for other in (0, 2):  # merged-GEMM fused path and separate-linears fused path, each vs the reference sequence
+        torch.testing.assert_close(res[other][0], res[1][0], rtol=tol, atol=tol * _scale(res[1][0]))
+        torch.testing.assert_close(res[other][1], res[1][1], rtol=tol, atol=tol * _scale(res[1][1]))
+        torch.testing.assert_close(res[other][2], res[1][2], rtol=tol, atol=tol * _scale(res[1][2]))
+        for k in res[other][3]:
+            torch.testing.assert_close(res[other][3][k], res[1][3][k], rtol=tol, atol=tol * _scale(res[1][3][k]), msg=k)
+    assert all(r[4] >= 2 for r in res)  # every path ran our kernels
 
 
 def test_module_fused_matches_reference_golden_f32():

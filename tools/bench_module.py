@@ -38,8 +38,9 @@ def main():
         f = torch.randn(args.batch, nf, d, device=dev, requires_grad=True)
         for amp in (False, True):
             vab.set_amp_value_dtype(torch.bfloat16 if amp else torch.float32)
-            for fused in (False, True):
+            for fused, merge in ((False, False), (True, False), (True, True)):
                 m.fused = fused
+                m.merge_query_linears = merge
 
                 def step():
                     with torch.autocast('cuda', dtype=torch.bfloat16, enabled=amp):
@@ -57,7 +58,7 @@ def main():
                     torch.cuda.synchronize()
                     ts.append(e0.elapsed_time(e1))
                 ts.sort()
-                print(json.dumps({'variant': args.variant, 'call': name, 'batch': args.batch, 'amp_bf16': amp, 'fused': fused,
+                print(json.dumps({'variant': args.variant, 'call': name, 'batch': args.batch, 'amp_bf16': amp, 'fused': fused, 'merged_gemm': merge,
                                   'module_fwd_bwd_ms': ts[len(ts) // 2]}), flush=True)
     vab.set_amp_value_dtype(torch.float32)
 

@@ -15,7 +15,8 @@ repo root) or put this directory on sys.path under the reference's own name `ops
 `from ops.functions import MSDeformAttnFunction` work exactly as in the reference.
 """
 from . import _cabi  # noqa: F401
-from .functions import MSDeformAttnFunction, MSDeformAttnFusedFunction, set_amp_value_dtype  # noqa: F401
+from .functions import (MSDeformAttnFunction, MSDeformAttnFusedFunction, MSDeformAttnMergedFunction,  # noqa: F401
+                        set_amp_value_dtype)
 from .modules import MSDeformAttn  # noqa: F401
 
-__all__ = ['MSDeformAttnFunction', 'MSDeformAttnFusedFunction', 'MSDeformAttn', 'set_amp_value_dtype']
+__all__ = ['MSDeformAttnFunction', 'MSDeformAttnFusedFunction', 'MSDeformAttnMergedFunction', 'MSDeformAttn', 'set_amp_value_dtype']

@@ -66,10 +66,11 @@ def load():
         lib.msda_backward.argtypes = [dp, ctypes.c_int, vp, i64p, i64p, vp, vp, vp, vp, vp, vp, vp,
                                       ctypes.c_size_t, vp]
         lib.msda_forward_fused.restype = ctypes.c_int
-        lib.msda_forward_fused.argtypes = [dp, ctypes.c_int, vp, i64p, i64p, vp, ctypes.c_int32, ctypes.c_int32, vp, vp, vp, vp]
+        lib.msda_forward_fused.argtypes = [dp, ctypes.c_int, vp, i64p, i64p, vp, ctypes.c_int32, ctypes.c_int32, vp, vp,
+                                           ctypes.c_int64, ctypes.c_int64, vp, vp]
         lib.msda_backward_fused.restype = ctypes.c_int
-        lib.msda_backward_fused.argtypes = [dp, ctypes.c_int, vp, i64p, i64p, vp, ctypes.c_int32, ctypes.c_int32, vp, vp, vp, vp,
-                                            vp, vp, vp, ctypes.c_size_t, vp]
+        lib.msda_backward_fused.argtypes = [dp, ctypes.c_int, vp, i64p, i64p, vp, ctypes.c_int32, ctypes.c_int32, vp, vp,
+                                            ctypes.c_int64, ctypes.c_int64, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
         lib.msda_debug_point_index.restype = ctypes.c_int
         lib.msda_debug_point_index.argtypes = [dp, i64p, i64p, vp, vp, vp]
         lib.msda_launch_count.restype = ctypes.c_uint64
@@ -264,10 +265,66 @@ def forward_fused(value, spatial_shapes, level_start_index, reference_points, sa
         out = torch.empty((dims.batch, dims.num_query, dims.num_heads * dims.channels), dtype=value.dtype, device=dev)
         rc = lib.msda_forward_fused(ctypes.byref(dims), code, value.data_ptr(), spatial_shapes.data_ptr(),
                                     level_start_index.data_ptr(), reference_points.data_ptr(), rb, rl,
-                                    sampling_offsets.data_ptr(), attn_logits.data_ptr(), out.data_ptr(), _stream())
+                                    sampling_offsets.data_ptr(), attn_logits.data_ptr(), 0, 0, out.data_ptr(), _stream())
     if rc != 0:
         _raise(rc, 'msda_forward_fused')
     return out
+
+
+def _merged_dims(value, reference_points, merged, n_levels, n_points):
+    N, S, M, D = value.shape
+    Lq = reference_points.shape[1]
+    width = M * n_levels * n_points * 3
+    if merged.dim() != 3 or merged.shape != (N, Lq, width) or merged.dtype != torch.float32 or reference_points.dtype != torch.float32:
+        raise RuntimeError('fused MSDeformAttn (merged): expected float32 [N, Lq, M*L*P*3] offsets|logits, got %s' % (tuple(merged.shape),))
+    return MsdaDims(N, S, M, D, n_levels, Lq, n_points), int(reference_points.shape[0]), int(reference_points.shape[2]), width
+
+
+def forward_fused_merged(value, spatial_shapes, level_start_index, reference_points, merged, n_levels, n_points):
+    """Fused forward reading offsets and logits from ONE buffer [N, Lq, M*L*P*3] — the output of a single GEMM whose
+    weight is cat(sampling_offsets.weight, attention_weights.weight): columns [0, M*L*P*2) are the raw offsets,
+    columns [M*L*P*2, M*L*P*3) the raw logits."""
+    lib = load()
+    dev = _check_cuda(value=value, spatial_shapes=spatial_shapes, level_start_index=level_start_index,
+                      reference_points=reference_points, merged=merged)
+    _check_meta(spatial_shapes, level_start_index)
+    dims, rb, rl, width = _merged_dims(value, reference_points, merged, n_levels, n_points)
+    code = _DTYPES.get(value.dtype)
+    with torch.cuda.device(dev):
+        out = torch.empty((dims.batch, dims.num_query, dims.num_heads * dims.channels), dtype=value.dtype, device=dev)
+        rc = lib.msda_forward_fused(ctypes.byref(dims), code, value.data_ptr(), spatial_shapes.data_ptr(),
+                                    level_start_index.data_ptr(), reference_points.data_ptr(), rb, rl,
+                                    merged.data_ptr(), merged.data_ptr() + 4 * (width // 3) * 2, width, width,
+                                    out.data_ptr(), _stream())
+    if rc != 0:
+        _raise(rc, 'msda_forward_fused')
+    return out
+
+
+def backward_fused_merged(value, spatial_shapes, level_start_index, reference_points, merged, n_levels, n_points, grad_output):
+    """(grad_value, grad_merged): grad_merged has the layout of `merged`, i.e. it is the merged GEMM's output gradient."""
+    lib = load()
+    dev = _check_cuda(value=value, spatial_shapes=spatial_shapes, level_start_index=level_start_index,
+                      reference_points=reference_points, merged=merged, grad_output=grad_output)
+    dims, rb, rl, width = _merged_dims(value, reference_points, merged, n_levels, n_points)
+    code = _DTYPES.get(value.dtype)
+    if grad_output.dtype != value.dtype:
+        raise RuntimeError('grad_output dtype %s != value dtype %s' % (grad_output.dtype, value.dtype))
+    with torch.cuda.device(dev):
+        grad_value = torch.empty_like(value)
+        grad_merged = torch.empty_like(merged)
+        ws_bytes = lib.msda_backward_workspace_bytes(ctypes.byref(dims), code)
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
+        off_logits = 4 * (width // 3) * 2
+        rc = lib.msda_backward_fused(ctypes.byref(dims), code, value.data_ptr(), spatial_shapes.data_ptr(),
+                                     level_start_index.data_ptr(), reference_points.data_ptr(), rb, rl,
+                                     merged.data_ptr(), merged.data_ptr() + off_logits, width, width,
+                                     grad_output.data_ptr(), grad_value.data_ptr(), grad_merged.data_ptr(),
+                                     grad_merged.data_ptr() + off_logits,
+                                     ws.data_ptr() if ws is not None else None, ws_bytes, _stream())
+    if rc != 0:
+        _raise(rc, 'msda_backward_fused')
+    return grad_value, grad_merged
 
 
 def backward_fused(value, spatial_shapes, level_start_index, reference_points, sampling_offsets, attn_logits, grad_output):
@@ -288,7 +345,7 @@ def backward_fused(value, spatial_shapes, level_start_index, reference_points, s
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
         rc = lib.msda_backward_fused(ctypes.byref(dims), code, value.data_ptr(), spatial_shapes.data_ptr(),
                                      level_start_index.data_ptr(), reference_points.data_ptr(), rb, rl,
-                                     sampling_offsets.data_ptr(), attn_logits.data_ptr(), grad_output.data_ptr(),
+                                     sampling_offsets.data_ptr(), attn_logits.data_ptr(), 0, 0, grad_output.data_ptr(),
                                      grad_value.data_ptr(), grad_off.data_ptr(), grad_logits.data_ptr(),
                                      ws.data_ptr() if ws is not None else None, ws_bytes, _stream())
     if rc != 0:

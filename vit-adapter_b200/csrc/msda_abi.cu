@@ -85,12 +85,10 @@ static int pick_chunk(const msda_dims* d, int per_iter, int override_qc) {
 
 // Plan the shared-memory forward from host-known level shapes: the set of levels (smallest first) whose
 // [H*W, D] maps of one head fit the budget, and the number of query chunks per (b, m).
-// MEASURED OUTCOME (profiles/r1_fwd_smem_vs_l1.md): at the adapter shapes this variant is NOT faster than
-// the L1-path forward (B 512^2 bs16 fp32: 94 vs 92 us injector, 132-143 vs 122 us extractor). ncu shows why:
-// an LDS.128 that reads 4 different 128-byte rows costs 4 LSU data-pipe wavefronts, exactly like the
-// LDG.128 that hits in L1, and both kernels sit at ~76% of that pipe (26 wavefronts per 4 points: 16 for
-// the corner rows, 5 shuffles, the rest loc/weight loads and stores). So it is OPT-IN (tuning key
-// "fwd_smem" = 2) and kept for shapes / future kernels where L2 traffic, not the LSU pipe, is the limit.
+// MEASURED OUTCOME (profiles/r1_fwd_smem_vs_l1.md): not a robust win over the L1-path forward at the adapter
+// shapes (B 512^2 bs16 Extractor 115.6 vs 121.8 us fp32, 77.8 vs 97.3 us bf16; Injector 98-115 vs 97 us): with
+// the row gathers down to one LSU wavefront each, the 5 broadcast shuffles per point keep the kernel at ~79 % of
+// the same LSU data pipe. So it is OPT-IN (tuning key "fwd_smem" = 2).
 static bool plan_forward_smem(const msda_dims* d, int dtype, int G, const int64_t* hs, int nt, SmemPlan* plan,
                               int* qc_out, int* nchunk_out) {
   if (!hs) return false;
@@ -343,7 +341,14 @@ int msda_backward(const msda_dims* dims, int dtype, const void* value, const int
   return 0;
 }
 
-static int fused_ref_params(Params& p, const msda_dims* d, const float* ref, int32_t ref_batch, int32_t ref_levels) {
+static int fused_ref_params(Params& p, const msda_dims* d, const float* ref, int32_t ref_batch, int32_t ref_levels,
+                            int64_t off_rowstride, int64_t logit_rowstride) {
+  const int64_t mlp = (int64_t)d->num_heads * d->num_levels * d->num_point;
+  p.off_rowstride = off_rowstride > 0 ? off_rowstride : mlp * 2;
+  p.logit_rowstride = logit_rowstride > 0 ? logit_rowstride : mlp;
+  if (p.off_rowstride < mlp * 2 || p.logit_rowstride < mlp || (p.off_rowstride & 1))
+    return fail(MSDA_E_DIMS, "fused entry: row strides (%lld, %lld) smaller than a row or odd", (long long)p.off_rowstride,
+                (long long)p.logit_rowstride);
   if (!ref) return fail(MSDA_E_NULL, "fused entry: reference_points is NULL");
   if (!(ref_batch == 1 || ref_batch == d->batch) || !(ref_levels == 1 || ref_levels == d->num_levels))
     return fail(MSDA_E_DIMS, "fused entry: reference_points [%d, Lq, %d, 2] does not broadcast to N=%d, L=%d", ref_batch,
@@ -358,8 +363,8 @@ static int fused_ref_params(Params& p, const msda_dims* d, const float* ref, int
 
 int msda_forward_fused(const msda_dims* dims, int dtype, const void* value, const int64_t* spatial_shapes,
                        const int64_t* level_start_index, const float* reference_points, int32_t ref_batch,
-                       int32_t ref_levels, const float* sampling_offsets, const float* attn_logits, void* out,
-                       void* stream) {
+                       int32_t ref_levels, const float* sampling_offsets, const float* attn_logits,
+                       int64_t offsets_row_stride, int64_t logits_row_stride, void* out, void* stream) {
   if (int e = check_dims(dims, dtype)) return e;
   if (!value || !spatial_shapes || !level_start_index || !sampling_offsets || !attn_logits || !out)
     return fail(MSDA_E_NULL, "msda_forward_fused: NULL tensor pointer");
@@ -374,7 +379,7 @@ int msda_forward_fused(const msda_dims* dims, int dtype, const void* value, cons
   fill_params(p, dims);
   p.value = value; p.shapes = spatial_shapes; p.lsi = level_start_index;
   p.loc = sampling_offsets; p.aw = attn_logits; p.out = out;
-  if (int e = fused_ref_params(p, dims, reference_points, ref_batch, ref_levels)) return e;
+  if (int e = fused_ref_params(p, dims, reference_points, ref_batch, ref_levels, offsets_row_stride, logits_row_stride)) return e;
   p.qc = pick_chunk(dims, kWarps * (32 / G), g_qc_fwd.load());
   p.nchunk = (p.Lq + p.qc - 1) / p.qc;
   const cudaError_t e = launch_forward_fused(p, dtype, G, (cudaStream_t)stream);
@@ -387,6 +392,7 @@ int msda_forward_fused(const msda_dims* dims, int dtype, const void* value, cons
 int msda_backward_fused(const msda_dims* dims, int dtype, const void* value, const int64_t* spatial_shapes,
                         const int64_t* level_start_index, const float* reference_points, int32_t ref_batch,
                         int32_t ref_levels, const float* sampling_offsets, const float* attn_logits,
+                        int64_t offsets_row_stride, int64_t logits_row_stride,
                         const void* grad_out, void* grad_value, float* grad_sampling_offsets, float* grad_attn_logits,
                         void* workspace, size_t workspace_bytes, void* stream) {
   if (int e = check_dims(dims, dtype)) return e;
@@ -407,7 +413,7 @@ int msda_backward_fused(const msda_dims* dims, int dtype, const void* value, con
   p.value = value; p.shapes = spatial_shapes; p.lsi = level_start_index;
   p.loc = sampling_offsets; p.aw = attn_logits; p.grad_out = grad_out;
   p.grad_loc = grad_sampling_offsets; p.grad_aw = grad_attn_logits;
-  if (int e = fused_ref_params(p, dims, reference_points, ref_batch, ref_levels)) return e;
+  if (int e = fused_ref_params(p, dims, reference_points, ref_batch, ref_levels, offsets_row_stride, logits_row_stride)) return e;
   const size_t nvalue = (size_t)p.N * p.S * p.M * p.D;
   void* accum = (dtype == MSDA_BF16) ? workspace : grad_value;
   p.grad_value = accum;

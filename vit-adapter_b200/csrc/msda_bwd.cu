@@ -150,8 +150,14 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_bwd_vec_kernel(const Para
       rf_[r] = make_float2(0.f, 0.f);
       a_[r] = 0.f;
       if (pi_ < LP && act_) {
-        xy_[r] = __ldg(reinterpret_cast<const float2*>(loc + pair_ * LP * 2) + pi_);
-        a_[r] = __ldg(aw + pair_ * LP + pi_);
+        if (FUSED) {  // explicit row strides: offsets / logits may be column blocks of one merged GEMM output
+          const size_t row_ = (size_t)bc.b * p.Lq + qq_;
+          xy_[r] = __ldg(reinterpret_cast<const float2*>(loc + row_ * p.off_rowstride + (size_t)bc.m * LP * 2) + pi_);
+          a_[r] = __ldg(aw + row_ * p.logit_rowstride + (size_t)bc.m * LP + pi_);
+        } else {
+          xy_[r] = __ldg(reinterpret_cast<const float2*>(loc + pair_ * LP * 2) + pi_);
+          a_[r] = __ldg(aw + pair_ * LP + pi_);
+        }
         if (FUSED)
           rf_[r] = __ldg(reinterpret_cast<const float2*>(p.ref + (size_t)bc.b * p.ref_bstride + (size_t)qq_ * p.ref_qstride +
                                                          (pi_ / (FUSED ? PT : 1)) * p.ref_lstride));
@@ -275,7 +281,10 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_bwd_vec_kernel(const Para
       }
       if constexpr (FUSED) {
         // d loc / d offset = 1 / (W, H): the (W, H) factors of grad_sampling_loc cancel
-        if (mine) reinterpret_cast<float2*>(gloc)[pair * LP + pi] = make_float2(my_gw * a, my_gh * a);
+        if (mine) {
+          const size_t row = (size_t)bc.b * p.Lq + q;
+          *reinterpret_cast<float2*>(gloc + row * p.off_rowstride + (size_t)bc.m * LP * 2 + 2 * pi) = make_float2(my_gw * a, my_gh * a);
+        }
         ga_keep[r0 / G] = mine ? my_ga : 0.f;
         dot_part = fmaf(a, ga_keep[r0 / G], dot_part);
       } else if (mine) {
@@ -289,7 +298,8 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_bwd_vec_kernel(const Para
 #pragma unroll
       for (int r = 0; r < kRounds; ++r) {
         const int pi = r * G + j;
-        if (pi < LP && active) gaw[pair * LP + pi] = ca[r] * (ga_keep[r] - dot);
+        if (pi < LP && active)
+          gaw[((size_t)bc.b * p.Lq + q) * p.logit_rowstride + (size_t)bc.m * LP + pi] = ca[r] * (ga_keep[r] - dot);
       }
     }
   }

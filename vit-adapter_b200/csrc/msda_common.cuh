@@ -41,6 +41,8 @@ struct Params {
   long long ref_bstride;   // floats between batches (0 when Nr == 1: broadcast)
   int ref_qstride;         // floats between queries (= Lr * 2)
   int ref_lstride;         // floats between levels  (0 when Lr == 1: broadcast)
+  long long off_rowstride;   // floats between the offsets of consecutive (b,q) rows (dense: M*L*P*2); same for their gradient
+  long long logit_rowstride; // floats between the logits  of consecutive (b,q) rows (dense: M*L*P);   same for their gradient
 };
 
 // Host-made plan for the shared-memory forward (msda_fwd_smem.cu): which levels' [H*W, D] maps of one

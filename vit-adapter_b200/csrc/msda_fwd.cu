@@ -77,8 +77,14 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_fwd_vec_kernel(const Para
       rf_[r] = make_float2(0.f, 0.f);
       a_[r] = 0.f;
       if (pi_ < LP && act_) {
-        xy_[r] = __ldg(reinterpret_cast<const float2*>(loc + pair_ * LP * 2) + pi_);
-        a_[r] = __ldg(aw + pair_ * LP + pi_);
+        if (FUSED) {  // raw offsets / logits may be two column blocks of ONE merged GEMM output: explicit row strides
+          const size_t row_ = (size_t)bc.b * p.Lq + qq_;
+          xy_[r] = __ldg(reinterpret_cast<const float2*>(loc + row_ * p.off_rowstride + (size_t)bc.m * LP * 2) + pi_);
+          a_[r] = __ldg(aw + row_ * p.logit_rowstride + (size_t)bc.m * LP + pi_);
+        } else {
+          xy_[r] = __ldg(reinterpret_cast<const float2*>(loc + pair_ * LP * 2) + pi_);
+          a_[r] = __ldg(aw + pair_ * LP + pi_);
+        }
         if (FUSED)
           rf_[r] = __ldg(reinterpret_cast<const float2*>(p.ref + (size_t)bc.b * p.ref_bstride + (size_t)qq_ * p.ref_qstride +
                                                          (pi_ / (FUSED ? PT : 1)) * p.ref_lstride));

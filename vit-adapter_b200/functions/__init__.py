@@ -1,1 +1,2 @@
-from .ms_deform_attn_func import MSDeformAttnFunction, MSDeformAttnFusedFunction, set_amp_value_dtype  # noqa: F401
+from .ms_deform_attn_func import (MSDeformAttnFunction, MSDeformAttnFusedFunction, MSDeformAttnMergedFunction,  # noqa: F401
+                                   set_amp_value_dtype)

@@ -100,3 +100,35 @@ class MSDeformAttnFusedFunction(Function):
         grad_value, grad_off, grad_logits = _cabi.backward_fused(value, shapes, level_start, ref, offsets, logits,
                                                                  grad_output.contiguous())
         return grad_value, None, None, None, grad_off, grad_logits
+
+
+class MSDeformAttnMergedFunction(Function):
+    """Fused entry fed by ONE GEMM: `merged` [N, Lq, M*L*P*3] = query @ cat(W_offsets, W_logits)^T + cat(b_offsets, b_logits)
+    (both linears of the reference module read the same `query`, ms_deform_attn.py:108-111). The kernels read the two
+    column blocks in place and write their gradient in the same layout, so the backward is also one GEMM.
+
+        apply(value, spatial_shapes, level_start_index, reference_points, merged, n_levels, n_points)"""
+
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, reference_points, merged, n_levels, n_points):
+        if torch.is_autocast_enabled('cuda') and value.is_cuda:
+            value = value.to(_AMP_VALUE_DTYPE)
+        if value.dtype == torch.float16:
+            value = value.float()
+        reference_points = reference_points.float().contiguous()
+        merged = merged.float().contiguous()
+        ctx.lp = (int(n_levels), int(n_points))
+        output = _cabi.forward_fused_merged(value, value_spatial_shapes, value_level_start_index, reference_points,
+                                            merged, *ctx.lp)
+        ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index, reference_points, merged)
+        return output
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, shapes, level_start, ref, merged = ctx.saved_tensors
+        if grad_output.dtype != value.dtype:
+            grad_output = grad_output.to(value.dtype)
+        grad_value, grad_merged = _cabi.backward_fused_merged(value, shapes, level_start, ref, merged, *ctx.lp,
+                                                              grad_output.contiguous())
+        return grad_value, None, None, None, grad_merged, None, None

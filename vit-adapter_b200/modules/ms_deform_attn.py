@@ -19,7 +19,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .. import _cabi
-from ..functions import MSDeformAttnFunction, MSDeformAttnFusedFunction
+from ..functions import MSDeformAttnFunction, MSDeformAttnFusedFunction, MSDeformAttnMergedFunction
 
 
 def _is_power_of_2(n):
@@ -54,6 +54,7 @@ class MSDeformAttn(nn.Module):
         # points, CUDA, fp32/bf16, (L,P) in {(3,4),(1,4)}); results differ from the unfused path only by the
         # rounding of the softmax normalisation. Set to False to force the reference's op sequence.
         self.fused = True
+        self.merge_query_linears = True
         self._reset_parameters()
 
     def _reset_parameters(self):
@@ -99,10 +100,19 @@ class MSDeformAttn(nn.Module):
         value = value.view(N, len_in, M, int(self.ratio * self.d_model) // M)
 
         if self.fused and reference_points.shape[-1] == 2 and _cabi.fused_supported(value, L, P):
-            offsets = self.sampling_offsets(query).view(N, Lq, M, L, P, 2)
-            logits = self.attention_weights(query).view(N, Lq, M, L * P)
-            output = MSDeformAttnFusedFunction.apply(value, input_spatial_shapes, input_level_start_index,
-                                                     reference_points, offsets, logits)
+            if self.merge_query_linears:
+                # sampling_offsets and attention_weights read the same query: ONE GEMM over the concatenated weights
+                # (state-dict keys untouched); the kernels consume its output in place
+                w = torch.cat([self.sampling_offsets.weight, self.attention_weights.weight], 0)
+                b = torch.cat([self.sampling_offsets.bias, self.attention_weights.bias], 0)
+                merged = F.linear(query, w, b)
+                output = MSDeformAttnMergedFunction.apply(value, input_spatial_shapes, input_level_start_index,
+                                                          reference_points, merged, L, P)
+            else:
+                offsets = self.sampling_offsets(query).view(N, Lq, M, L, P, 2)
+                logits = self.attention_weights(query).view(N, Lq, M, L * P)
+                output = MSDeformAttnFusedFunction.apply(value, input_spatial_shapes, input_level_start_index,
+                                                         reference_points, offsets, logits)
             return self.output_proj(output)
 
         offsets = self.sampling_offsets(query).view(N, Lq, M, L, P, 2)
