@@ -179,6 +179,22 @@ int msda_backward_fused(const msda_dims* dims, int dtype,
                         void* workspace, size_t workspace_bytes,
                         void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Adapter ConvFFN depth-wise 3x3 convolution on the token layout.
+ * Replaces DWConv.forward of the reference (adapter_modules.py:73-87: slice the [B, 21n, C] sequence into the
+ * three maps 2Hx2W / HxW / (H/2)x(W/2), transpose each to NCHW, nn.Conv2d(C, C, 3, 1, 1, groups=C), transpose
+ * back, concatenate) with one kernel that reads and writes the tokens in place (channels-last).
+ *   x, y, grad_y, grad_x   [B, n_tokens, C]  dtype T (f32 | bf16 | f64), n_tokens = 21 * H * W / 4, H and W even
+ *   weight                 [C, 1, 3, 3]      dtype T ;  bias [C] dtype T or NULL
+ *   grad_weight [C*9], grad_bias [C]: fp32 accumulators for T in {f32, bf16}, fp64 for T = f64 (zero-filled here)
+ * ------------------------------------------------------------------------------------------------ */
+int adapter_dwconv_forward(int dtype, const void* x, const void* weight, const void* bias, void* y,
+                           int32_t batch, int32_t n_tokens, int32_t channels, int32_t H, int32_t W, void* stream);
+int adapter_dwconv_backward_input(int dtype, const void* grad_y, const void* weight, void* grad_x,
+                                  int32_t batch, int32_t n_tokens, int32_t channels, int32_t H, int32_t W, void* stream);
+int adapter_dwconv_backward_weight(int dtype, const void* x, const void* grad_y, void* grad_weight, void* grad_bias,
+                                   int32_t batch, int32_t n_tokens, int32_t channels, int32_t H, int32_t W, void* stream);
+
 /* Test hook: for every sampling point (N*Lq*M*L*P of them, same order as attn_weight) write
  *   idx[4*i+0] = h_low, idx[4*i+1] = w_low,
  *   idx[4*i+2] = corner-validity mask (bit k = corner k+1 is read; 0 = sample skipped),

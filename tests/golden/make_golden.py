@@ -169,6 +169,22 @@ def adapter_case(ref_adapter, name, dim, heads, ratio, H, W, N, seed):
     print(name)
 
 
+def dwconv_case(ref_adapter, name, C, H, W, B, seed):
+    """The reference's DWConv module on a packed [B, 21n, C] token sequence: output and autograd gradients (fp64)."""
+    torch.manual_seed(seed)
+    m = ref_adapter.DWConv(C).double()
+    n = (H // 2) * (W // 2)
+    x = torch.randn(B, 21 * n, C, dtype=torch.double, requires_grad=True)
+    gy = torch.randn(B, 21 * n, C, dtype=torch.double)
+    y = m(x, H, W)
+    y.backward(gy)
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), x=x.detach().numpy(), weight=m.dwconv.weight.detach().numpy(),
+                        bias=m.dwconv.bias.detach().numpy(), y=y.detach().numpy(), grad_y=gy.numpy(), grad_x=x.grad.numpy(),
+                        grad_weight=m.dwconv.weight.grad.numpy(), grad_bias=m.dwconv.bias.grad.numpy(),
+                        cfg=np.array([C, H, W, B], dtype=np.int64))
+    print(name)
+
+
 def main():
     ref_func, ref_mod, ref_adapter = load_reference()
     # 1. the reference's own test fixture (detection/ops/test.py:16-37), seed 3 == SURVEY App. A.4 KAT
@@ -189,6 +205,9 @@ def main():
     init_case(ref_mod, 'module_init_bias')
     # 6. adapter level
     adapter_case(ref_adapter, 'adapter_block', dim=32, heads=4, ratio=0.5, H=64, W=96, N=2, seed=31)
+    # 7. ConvFFN's depth-wise conv on the token layout (C = 12: vector path for fp32; C = 6: scalar path)
+    dwconv_case(ref_adapter, 'dwconv_tokens', C=12, H=4, W=6, B=2, seed=41)
+    dwconv_case(ref_adapter, 'dwconv_tokens_c6', C=6, H=2, W=2, B=1, seed=42)
 
 
 if __name__ == '__main__':

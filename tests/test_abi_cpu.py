@@ -16,7 +16,7 @@ from vit_adapter_b200 import _cabi
 def _declared_functions():
     text = open(os.path.join(ROOT, 'include', 'msda_b200.h')).read()
     text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
-    return sorted(set(re.findall(r'\b(msda_[a-z0-9_]+)\s*\(', text)))
+    return sorted(set(re.findall(r'\b((?:msda|adapter)_[a-z0-9_]+)\s*\(', text)))
 
 
 def test_library_exports_every_declared_symbol():

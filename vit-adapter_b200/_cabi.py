@@ -23,6 +23,7 @@ EXPORTS = (
     'msda_abi_version', 'msda_last_error', 'msda_check_im2col_step', 'msda_forward', 'msda_forward_ex',
     'msda_backward_workspace_bytes', 'msda_backward', 'msda_debug_point_index', 'msda_launch_count',
     'msda_set_tuning', 'msda_forward_fused', 'msda_backward_fused',
+    'adapter_dwconv_forward', 'adapter_dwconv_backward_input', 'adapter_dwconv_backward_weight',
 )
 
 
@@ -71,6 +72,13 @@ def load():
         lib.msda_backward_fused.restype = ctypes.c_int
         lib.msda_backward_fused.argtypes = [dp, ctypes.c_int, vp, i64p, i64p, vp, ctypes.c_int32, ctypes.c_int32, vp, vp,
                                             ctypes.c_int64, ctypes.c_int64, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
+        i32 = ctypes.c_int32
+        lib.adapter_dwconv_forward.restype = ctypes.c_int
+        lib.adapter_dwconv_forward.argtypes = [ctypes.c_int, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
+        lib.adapter_dwconv_backward_input.restype = ctypes.c_int
+        lib.adapter_dwconv_backward_input.argtypes = [ctypes.c_int, vp, vp, vp, i32, i32, i32, i32, i32, vp]
+        lib.adapter_dwconv_backward_weight.restype = ctypes.c_int
+        lib.adapter_dwconv_backward_weight.argtypes = [ctypes.c_int, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
         lib.msda_debug_point_index.restype = ctypes.c_int
         lib.msda_debug_point_index.argtypes = [dp, i64p, i64p, vp, vp, vp]
         lib.msda_launch_count.restype = ctypes.c_uint64
@@ -351,6 +359,50 @@ def backward_fused(value, spatial_shapes, level_start_index, reference_points, s
     if rc != 0:
         _raise(rc, 'msda_backward_fused')
     return grad_value, grad_off, grad_logits
+
+
+def dwconv_supported(x, weight, H, W):
+    """True when the token-layout depth-wise 3x3 kernel applies (else the module runs the reference's op sequence)."""
+    return (x.is_cuda and x.dtype in _DTYPES and weight.dtype == x.dtype and x.dim() == 3 and H % 2 == 0 and W % 2 == 0
+            and x.shape[1] == 21 * (H // 2) * (W // 2) and x.shape[2] <= 1024 and tuple(weight.shape) == (x.shape[2], 1, 3, 3))
+
+
+def dwconv_forward(x, weight, bias, H, W):
+    lib = load()
+    dev = _check_cuda(x=x, weight=weight) if bias is None else _check_cuda(x=x, weight=weight, bias=bias)
+    B, n, C = x.shape
+    with torch.cuda.device(dev):
+        y = torch.empty_like(x)
+        rc = lib.adapter_dwconv_forward(_DTYPES[x.dtype], x.data_ptr(), weight.data_ptr(),
+                                        bias.data_ptr() if bias is not None else None, y.data_ptr(), B, n, C, H, W, _stream())
+    if rc != 0:
+        _raise(rc, 'adapter_dwconv_forward')
+    return y
+
+
+def dwconv_backward(x, weight, grad_y, H, W, need_input=True, need_weight=True):
+    """(grad_x or None, grad_weight [C,1,3,3] or None, grad_bias [C] or None) in x.dtype."""
+    lib = load()
+    dev = _check_cuda(x=x, weight=weight, grad_y=grad_y)
+    B, n, C = x.shape
+    code = _DTYPES[x.dtype]
+    gx = gw = gb = None
+    with torch.cuda.device(dev):
+        if need_input:
+            gx = torch.empty_like(x)
+            rc = lib.adapter_dwconv_backward_input(code, grad_y.data_ptr(), weight.data_ptr(), gx.data_ptr(), B, n, C, H, W, _stream())
+            if rc != 0:
+                _raise(rc, 'adapter_dwconv_backward_input')
+        if need_weight:
+            adt = torch.float64 if x.dtype == torch.float64 else torch.float32
+            gw = torch.empty((C, 1, 3, 3), dtype=adt, device=dev)
+            gb = torch.empty((C,), dtype=adt, device=dev)
+            rc = lib.adapter_dwconv_backward_weight(code, x.data_ptr(), grad_y.data_ptr(), gw.data_ptr(), gb.data_ptr(),
+                                                    B, n, C, H, W, _stream())
+            if rc != 0:
+                _raise(rc, 'adapter_dwconv_backward_weight')
+            gw, gb = gw.to(weight.dtype), gb.to(weight.dtype)
+    return gx, gw, gb
 
 
 def debug_point_index(spatial_shapes, level_start_index, sampling_loc, num_heads, channels):

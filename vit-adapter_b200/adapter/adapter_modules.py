@@ -19,6 +19,7 @@ import torch
 import torch.nn as nn
 import torch.utils.checkpoint as cp
 
+from .. import _cabi
 from ..modules import MSDeformAttn
 
 
@@ -84,15 +85,44 @@ def deform_inputs(x):
     return out
 
 
+class _DWConvTokens(torch.autograd.Function):
+    """Depth-wise 3x3 on the [B, 21n, C] token layout in one kernel (csrc/adapter_dwconv.cu) instead of the
+    reference's slice / transpose / conv2d / transpose / cat sequence."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, H, W):
+        x = x.contiguous()
+        ctx.save_for_backward(x, weight)
+        ctx.hw = (int(H), int(W))
+        ctx.has_bias = bias is not None
+        return _cabi.dwconv_forward(x, weight.contiguous(), bias.contiguous() if bias is not None else None, int(H), int(W))
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_y):
+        x, weight = ctx.saved_tensors
+        gx, gw, gb = _cabi.dwconv_backward(x, weight.contiguous(), grad_y.contiguous(), *ctx.hw,
+                                           need_input=ctx.needs_input_grad[0],
+                                           need_weight=ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
+        return gx, gw, (gb if ctx.has_bias else None), None, None
+
+
 class DWConv(nn.Module):
     """Depth-wise 3x3 over the three token maps packed in one sequence of 21n tokens
-    (16n at H/8, 4n at H/16, n at H/32); reference adapter_modules.py:73-87."""
+    (16n at H/8, 4n at H/16, n at H/32); reference adapter_modules.py:73-87. Same parameter (`dwconv.weight`,
+    `dwconv.bias`); on CUDA the token-layout kernel is used, otherwise the reference's op sequence."""
 
     def __init__(self, dim=768):
         super().__init__()
         self.dwconv = nn.Conv2d(dim, dim, 3, 1, 1, bias=True, groups=dim)
+        self.token_kernel = True
 
     def forward(self, x, H, W):
+        w, b = self.dwconv.weight, self.dwconv.bias
+        if self.token_kernel and _cabi.dwconv_supported(x, w.to(x.dtype) if w.dtype != x.dtype else w, H, W):
+            if w.dtype != x.dtype:  # autocast: activations bf16, parameters fp32
+                w, b = w.to(x.dtype), (b.to(x.dtype) if b is not None else None)
+            return _DWConvTokens.apply(x, w, b, H, W)
         B, N, C = x.shape
         n = N // 21
         outs = []

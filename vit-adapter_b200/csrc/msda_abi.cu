@@ -18,6 +18,15 @@ cudaError_t launch_backward(const Params& p, int dtype, bool vec_ok, int G, int 
 cudaError_t launch_cvt_f32_bf16(const float* src, void* dst, size_t n, cudaStream_t s);
 cudaError_t launch_forward_fused(const Params& p, int dtype, int G, cudaStream_t s);
 cudaError_t launch_backward_fused(const Params& p, int dtype, int G, cudaStream_t s);
+struct DwParams {
+  const void* x;
+  const void* w;
+  const void* bias;
+  void* y;
+  int B, Ntok, C, H, W;
+};
+cudaError_t launch_dwconv(const DwParams& p, int dtype, bool flip, cudaStream_t s);
+cudaError_t launch_dwconv_wgrad(const DwParams& p, int dtype, const void* grad_y, void* gw, void* gb, cudaStream_t s);
 cudaError_t launch_forward_wide(const Params& p, int G, int minb, cudaStream_t s);
 cudaError_t launch_forward_smem(const Params& p, const SmemPlan& plan, int dtype, int G, int nt, cudaStream_t s);
 
@@ -433,6 +442,48 @@ int msda_backward_fused(const msda_dims* dims, int dtype, const void* value, con
     if (e != cudaSuccess) return cuda_fail(e, "msda_backward_fused bf16 convert launch");
     g_launches.fetch_add(1);
   }
+  return 0;
+}
+
+static int dw_check(int dtype, int32_t B, int32_t n_tokens, int32_t C, int32_t H, int32_t W) {
+  if (elem_size(dtype) == 0) return fail(MSDA_E_DTYPE, "adapter_dwconv: unknown dtype %d", dtype);
+  if (B <= 0 || n_tokens <= 0 || C <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1) ||
+      (int64_t)n_tokens != 21ll * (H / 2) * (W / 2) || C > 1024 || (int64_t)B * n_tokens * C >= (1ll << 40))
+    return fail(MSDA_E_DIMS, "adapter_dwconv: need n_tokens == 21*H*W/4 with even H, W and C <= 1024 (B=%d n=%d C=%d H=%d W=%d)",
+                B, n_tokens, C, H, W);
+  return 0;
+}
+
+int adapter_dwconv_forward(int dtype, const void* x, const void* weight, const void* bias, void* y, int32_t batch,
+                           int32_t n_tokens, int32_t channels, int32_t H, int32_t W, void* stream) {
+  if (int e = dw_check(dtype, batch, n_tokens, channels, H, W)) return e;
+  if (!x || !weight || !y) return fail(MSDA_E_NULL, "adapter_dwconv_forward: NULL tensor pointer");
+  DwParams p{x, weight, bias, y, batch, n_tokens, channels, H, W};
+  const cudaError_t e = launch_dwconv(p, dtype, false, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "adapter_dwconv_forward launch");
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+int adapter_dwconv_backward_input(int dtype, const void* grad_y, const void* weight, void* grad_x, int32_t batch,
+                                  int32_t n_tokens, int32_t channels, int32_t H, int32_t W, void* stream) {
+  if (int e = dw_check(dtype, batch, n_tokens, channels, H, W)) return e;
+  if (!grad_y || !weight || !grad_x) return fail(MSDA_E_NULL, "adapter_dwconv_backward_input: NULL tensor pointer");
+  DwParams p{grad_y, weight, nullptr, grad_x, batch, n_tokens, channels, H, W};
+  const cudaError_t e = launch_dwconv(p, dtype, true, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "adapter_dwconv_backward_input launch");
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+int adapter_dwconv_backward_weight(int dtype, const void* x, const void* grad_y, void* grad_weight, void* grad_bias,
+                                   int32_t batch, int32_t n_tokens, int32_t channels, int32_t H, int32_t W, void* stream) {
+  if (int e = dw_check(dtype, batch, n_tokens, channels, H, W)) return e;
+  if (!x || !grad_y || !grad_weight || !grad_bias) return fail(MSDA_E_NULL, "adapter_dwconv_backward_weight: NULL tensor pointer");
+  DwParams p{x, nullptr, nullptr, nullptr, batch, n_tokens, channels, H, W};
+  const cudaError_t e = launch_dwconv_wgrad(p, dtype, grad_y, grad_weight, grad_bias, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "adapter_dwconv_backward_weight launch");
+  g_launches.fetch_add(1);
   return 0;
 }
 
