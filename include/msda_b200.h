@@ -186,14 +186,19 @@ int msda_backward_fused(const msda_dims* dims, int dtype,
  * back, concatenate) with one kernel that reads and writes the tokens in place (channels-last).
  *   x, y, grad_y, grad_x   [B, n_tokens, C]  dtype T (f32 | bf16 | f64), n_tokens = 21 * H * W / 4, H and W even
  *   weight                 [C, 1, 3, 3]      dtype T ;  bias [C] dtype T or NULL
- *   grad_weight [C*9], grad_bias [C]: fp32 accumulators for T in {f32, bf16}, fp64 for T = f64 (zero-filled here)
+ *   grad_weight [C*9], grad_bias [C]: fp32 accumulators for T in {f32, bf16}, fp64 for T = f64 (fully written here)
+ *   workspace: adapter_dwconv_backward_weight_workspace_bytes(...) bytes of device scratch (per-CTA partial sums of the
+ *   deterministic two-stage reduction); 0 = none needed (generic path: f64 or C % 4 != 0, reduced with atomics).
  * ------------------------------------------------------------------------------------------------ */
 int adapter_dwconv_forward(int dtype, const void* x, const void* weight, const void* bias, void* y,
                            int32_t batch, int32_t n_tokens, int32_t channels, int32_t H, int32_t W, void* stream);
 int adapter_dwconv_backward_input(int dtype, const void* grad_y, const void* weight, void* grad_x,
                                   int32_t batch, int32_t n_tokens, int32_t channels, int32_t H, int32_t W, void* stream);
+size_t adapter_dwconv_backward_weight_workspace_bytes(int dtype, int32_t batch, int32_t n_tokens, int32_t channels,
+                                                      int32_t H, int32_t W);
 int adapter_dwconv_backward_weight(int dtype, const void* x, const void* grad_y, void* grad_weight, void* grad_bias,
-                                   int32_t batch, int32_t n_tokens, int32_t channels, int32_t H, int32_t W, void* stream);
+                                   int32_t batch, int32_t n_tokens, int32_t channels, int32_t H, int32_t W,
+                                   void* workspace, size_t workspace_bytes, void* stream);
 
 /* Test hook: for every sampling point (N*Lq*M*L*P of them, same order as attn_weight) write
  *   idx[4*i+0] = h_low, idx[4*i+1] = w_low,

@@ -24,6 +24,7 @@ EXPORTS = (
     'msda_backward_workspace_bytes', 'msda_backward', 'msda_debug_point_index', 'msda_launch_count',
     'msda_set_tuning', 'msda_forward_fused', 'msda_backward_fused',
     'adapter_dwconv_forward', 'adapter_dwconv_backward_input', 'adapter_dwconv_backward_weight',
+    'adapter_dwconv_backward_weight_workspace_bytes',
 )
 
 
@@ -78,7 +79,9 @@ def load():
         lib.adapter_dwconv_backward_input.restype = ctypes.c_int
         lib.adapter_dwconv_backward_input.argtypes = [ctypes.c_int, vp, vp, vp, i32, i32, i32, i32, i32, vp]
         lib.adapter_dwconv_backward_weight.restype = ctypes.c_int
-        lib.adapter_dwconv_backward_weight.argtypes = [ctypes.c_int, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
+        lib.adapter_dwconv_backward_weight.argtypes = [ctypes.c_int, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, ctypes.c_size_t, vp]
+        lib.adapter_dwconv_backward_weight_workspace_bytes.restype = ctypes.c_size_t
+        lib.adapter_dwconv_backward_weight_workspace_bytes.argtypes = [ctypes.c_int, i32, i32, i32, i32, i32]
         lib.msda_debug_point_index.restype = ctypes.c_int
         lib.msda_debug_point_index.argtypes = [dp, i64p, i64p, vp, vp, vp]
         lib.msda_launch_count.restype = ctypes.c_uint64
@@ -397,8 +400,10 @@ def dwconv_backward(x, weight, grad_y, H, W, need_input=True, need_weight=True):
             adt = torch.float64 if x.dtype == torch.float64 else torch.float32
             gw = torch.empty((C, 1, 3, 3), dtype=adt, device=dev)
             gb = torch.empty((C,), dtype=adt, device=dev)
+            ws_bytes = lib.adapter_dwconv_backward_weight_workspace_bytes(code, B, n, C, H, W)
+            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
             rc = lib.adapter_dwconv_backward_weight(code, x.data_ptr(), grad_y.data_ptr(), gw.data_ptr(), gb.data_ptr(),
-                                                    B, n, C, H, W, _stream())
+                                                    B, n, C, H, W, ws.data_ptr() if ws is not None else None, ws_bytes, _stream())
             if rc != 0:
                 _raise(rc, 'adapter_dwconv_backward_weight')
             gw, gb = gw.to(weight.dtype), gb.to(weight.dtype)

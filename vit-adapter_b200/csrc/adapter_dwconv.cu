@@ -169,9 +169,273 @@ __global__ void __launch_bounds__(256) adapter_dwconv_wgrad_kernel(const DwParam
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Sliding-window kernels (fp32 / bf16, C % 4 == 0): the fast path.
+//
+// The kernels above read nine neighbours per output token; at 16 bytes per lane that is nine L1 row gathers per
+// 128 output bytes, and the measured L1 gather ceiling (profiles/r1_microbench.md, ~0.49 rows/cycle/SM) caps them at
+// ~1/3 of the HBM roofline. Here a thread owns 4 channels and a RUN of kRun consecutive tokens of one map row and
+// carries the 3x3 window in registers: per output it loads only the three tokens of the next column (3.75 loads per
+// output with the two halo columns of a run, instead of 9), and the taps live in registers, so there is no shared-
+// memory traffic at all in the forward / grad_x kernels. A work item is (batch, map, row, run); lanes of a warp are
+// adjacent channel quads of the same item, so each load instruction covers one contiguous token row.
+constexpr int kRun = 8;
+
+struct DwRunGeom {
+  int seg[3];       // runs per row of each map
+  int items[3];     // rows * runs of each map (per batch)
+  int per_batch;    // sum of items
+  int total;        // per_batch * B
+};
+
+static DwRunGeom dw_run_geom(const DwParams& p) {
+  DwRunGeom g;
+  const int mh[3] = {2 * p.H, p.H, p.H / 2}, mw[3] = {2 * p.W, p.W, p.W / 2};
+  g.per_batch = 0;
+  for (int i = 0; i < 3; ++i) {
+    g.seg[i] = (mw[i] + kRun - 1) / kRun;
+    g.items[i] = mh[i] * g.seg[i];
+    g.per_batch += g.items[i];
+  }
+  g.total = g.per_batch * p.B;
+  return g;
+}
+
+// work item -> batch, first token of the map, map height / width, row, first column of the run
+__device__ __forceinline__ void dw_run_locate(int item, const DwParams& p, const DwRunGeom& g, int& b, int& t0, int& mh, int& mw,
+                                              int& h, int& w0) {
+  b = item / g.per_batch;
+  int r = item - b * g.per_batch;
+  int seg;
+  if (r < g.items[0]) { t0 = 0; mh = 2 * p.H; mw = 2 * p.W; seg = g.seg[0]; }
+  else if (r < g.items[0] + g.items[1]) { r -= g.items[0]; t0 = 4 * p.H * p.W; mh = p.H; mw = p.W; seg = g.seg[1]; }
+  else { r -= g.items[0] + g.items[1]; t0 = 5 * p.H * p.W; mh = p.H / 2; mw = p.W / 2; seg = g.seg[2]; }
+  h = r / seg;
+  w0 = (r - h * seg) * kRun;
+}
+
+template <typename T> struct Quad;  // 4 consecutive channels of one token: raw 8/16-byte load, fp32 view
+template <> struct Quad<float> {
+  using Raw = float4;
+  static __device__ __forceinline__ Raw ld(const float* p, bool ok) {
+    Raw q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok) q = __ldg(reinterpret_cast<const float4*>(p));
+    return q;
+  }
+  static __device__ __forceinline__ void unpack(const Raw& q, float (&v)[4]) { v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+  static __device__ __forceinline__ void st(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <> struct Quad<__nv_bfloat16> {
+  using Raw = uint2;
+  static __device__ __forceinline__ Raw ld(const __nv_bfloat16* p, bool ok) {
+    Raw q = make_uint2(0u, 0u);
+    if (ok) q = __ldg(reinterpret_cast<const uint2*>(p));
+    return q;
+  }
+  static __device__ __forceinline__ void unpack(const Raw& q, float (&v)[4]) {
+    v[0] = __uint_as_float(q.x << 16); v[1] = __uint_as_float(q.x & 0xffff0000u);
+    v[2] = __uint_as_float(q.y << 16); v[3] = __uint_as_float(q.y & 0xffff0000u);
+  }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, const float (&v)[4]) {
+    uint2 o;
+    o.x = Vec<__nv_bfloat16>::pack2(v[0], v[1]); o.y = Vec<__nv_bfloat16>::pack2(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = o;
+  }
+};
+
+// the kRun + 2 tokens (columns w0-1 .. w0+kRun) of one map row, zero outside the map: all loads issued back to back
+template <typename T>
+__device__ __forceinline__ void dw_load_row(const T* row, int C, int w0, int mw, bool row_ok, typename Quad<T>::Raw (&raw)[kRun + 2]) {
+#pragma unroll
+  for (int jj = 0; jj < kRun + 2; ++jj) {
+    const int w = w0 - 1 + jj;
+    raw[jj] = Quad<T>::ld(row + (ptrdiff_t)w * C, row_ok && w >= 0 && w < mw);
+  }
+}
+
+// y = dwconv3x3(x) (+ bias), or with FLIP grad_x = dwconv3x3(grad_y, taps rotated by 180 degrees).
+// blockDim.x = cvec * ty_count (cvec = C / 4): thread -> (channel quad cv, item slot ty). Per item the three input
+// rows are processed one after the other, each as kRun + 2 independent loads (memory-level parallelism: 10 loads of
+// 512 B per warp in flight instead of 3 when walking column by column); bf16 keeps the next row in flight too.
+template <typename T, bool FLIP>
+__global__ void __launch_bounds__(256, 2) adapter_dwconv_run_kernel(const DwParams p, const DwRunGeom g, int cvec, int ty_count) {
+  using Raw = typename Quad<T>::Raw;
+  constexpr bool kAhead = sizeof(T) == 2;
+  const int cv = threadIdx.x % cvec, ty = threadIdx.x / cvec;
+  const T* __restrict__ x = reinterpret_cast<const T*>(p.x);
+  T* __restrict__ y = reinterpret_cast<T*>(p.y);
+  float tp[9][4], bias[4];
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    const T* wv = reinterpret_cast<const T*>(p.w) + (cv * 4 + v) * 9;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) tp[FLIP ? 8 - k : k][v] = dw_ld<T>(wv + k);
+    bias[v] = (!FLIP && p.bias) ? dw_ld<T>(reinterpret_cast<const T*>(p.bias) + cv * 4 + v) : 0.f;
+  }
+  for (int item = blockIdx.x * ty_count + ty; item < g.total; item += gridDim.x * ty_count) {
+    int b, t0, mh, mw, h, w0;
+    dw_run_locate(item, p, g, b, t0, mh, mw, h, w0);
+    const size_t row_tok = (size_t)b * p.Ntok + t0 + h * mw;  // token index of (h, 0)
+    const T* xr = x + row_tok * p.C + cv * 4;
+    T* yr = y + row_tok * p.C + cv * 4;
+    const ptrdiff_t rs = (ptrdiff_t)mw * p.C;  // one map row in elements
+    const bool rok[3] = {h > 0, true, h + 1 < mh};
+    float acc[kRun][4];
+#pragma unroll
+    for (int j = 0; j < kRun; ++j)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) acc[j][v] = bias[v];
+    Raw cur[kRun + 2], nxt[kRun + 2];
+    dw_load_row<T>(xr - rs, p.C, w0, mw, rok[0], cur);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      if (kAhead && r < 2) dw_load_row<T>(xr + (r == 0 ? 0 : rs), p.C, w0, mw, rok[r + 1], nxt);
+#pragma unroll
+      for (int jj = 0; jj < kRun + 2; ++jj) {
+        float val[4];
+        Quad<T>::unpack(cur[jj], val);
+#pragma unroll
+        for (int dx = 2; dx >= 0; --dx) {   // token jj is column dx of output j = jj - dx; dx descending keeps the
+          const int j = jj - dx;            // per-output order (row-major over the taps)
+          if (j < 0 || j >= kRun) continue;
+#pragma unroll
+          for (int v = 0; v < 4; ++v) acc[j][v] = fmaf(val[v], tp[r * 3 + dx][v], acc[j][v]);
+        }
+      }
+      if (r < 2) {
+        if (kAhead) {
+#pragma unroll
+          for (int jj = 0; jj < kRun + 2; ++jj) cur[jj] = nxt[jj];
+        } else {
+          dw_load_row<T>(xr + (r == 0 ? 0 : rs), p.C, w0, mw, rok[r + 1], cur);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kRun; ++j)
+      if (w0 + j < mw) Quad<T>::st(yr + (ptrdiff_t)(w0 + j) * p.C, acc[j]);
+  }
+}
+
+// grad_weight / grad_bias with the same run decomposition: per item the grad_y quads of the run stay in registers and
+// each of the three x rows is loaded as kRun + 2 independent quads; 40 partial sums per thread, reduced over the CTA's
+// item slots in shared memory and written as one partial row per CTA (no atomics: the second kernel sums the rows in a
+// fixed order, so grad_weight is deterministic).
+template <typename T>
+__global__ void __launch_bounds__(256, 2) adapter_dwconv_wgrad_run_kernel(const DwParams p, const DwRunGeom g, const void* grad_y_,
+                                                                          float* partial, int cvec, int ty_count) {
+  using Raw = typename Quad<T>::Raw;
+  extern __shared__ __align__(16) unsigned char dw_smem[];
+  float* red = reinterpret_cast<float*>(dw_smem);  // [ty_count][40][cvec]
+  const int cv = threadIdx.x % cvec, ty = threadIdx.x / cvec;
+  const T* __restrict__ x = reinterpret_cast<const T*>(p.x);
+  const T* __restrict__ gy = reinterpret_cast<const T*>(grad_y_);
+  float s[10][4];
+#pragma unroll
+  for (int k = 0; k < 10; ++k)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) s[k][v] = 0.f;
+  for (int item = blockIdx.x * ty_count + ty; item < g.total; item += gridDim.x * ty_count) {
+    int b, t0, mh, mw, h, w0;
+    dw_run_locate(item, p, g, b, t0, mh, mw, h, w0);
+    const size_t row_tok = (size_t)b * p.Ntok + t0 + h * mw;
+    const T* xr = x + row_tok * p.C + cv * 4;
+    const T* gr = gy + row_tok * p.C + cv * 4;
+    const ptrdiff_t rs = (ptrdiff_t)mw * p.C;
+    const bool rok[3] = {h > 0, true, h + 1 < mh};
+    Raw graw[kRun];
+#pragma unroll
+    for (int j = 0; j < kRun; ++j) graw[j] = Quad<T>::ld(gr + (ptrdiff_t)(w0 + j) * p.C, w0 + j < mw);
+    Raw cur[kRun + 2];
+    dw_load_row<T>(xr - rs, p.C, w0, mw, rok[0], cur);
+#pragma unroll
+    for (int j = 0; j < kRun; ++j) {
+      float gq[4];
+      Quad<T>::unpack(graw[j], gq);
+#pragma unroll
+      for (int v = 0; v < 4; ++v) s[9][v] += gq[v];
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int j = 0; j < kRun; ++j) {
+        float gq[4];
+        Quad<T>::unpack(graw[j], gq);
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          float val[4];
+          Quad<T>::unpack(cur[j + dx], val);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) s[r * 3 + dx][v] = fmaf(gq[v], val[v], s[r * 3 + dx][v]);
+        }
+      }
+      if (r < 2) dw_load_row<T>(xr + (r == 0 ? 0 : rs), p.C, w0, mw, rok[r + 1], cur);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 10; ++k)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) red[(ty * 40 + k * 4 + v) * cvec + cv] = s[k][v];
+  __syncthreads();
+  float* mine = partial + (size_t)blockIdx.x * 40 * cvec;
+  for (int i = threadIdx.x; i < 40 * cvec; i += blockDim.x) {
+    float tot = 0.f;
+    for (int yy = 0; yy < ty_count; ++yy) tot += red[yy * 40 * cvec + i];
+    mine[i] = tot;
+  }
+}
+
+// second stage: sum the per-CTA partial rows; i = (tap * 4 + v) * cvec + cv -> grad_weight[(cv*4+v)*9 + tap] / grad_bias
+__global__ void __launch_bounds__(256) adapter_dwconv_wgrad_sum_kernel(const float* __restrict__ partial, int rows, int cvec,
+                                                                       float* __restrict__ gw, float* __restrict__ gb) {
+  __shared__ float red[8][32];
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  const int n = 40 * cvec;
+  float tot = 0.f;
+  if (i < n)
+    for (int r = threadIdx.y; r < rows; r += 8) tot += partial[(size_t)r * n + i];
+  red[threadIdx.y][threadIdx.x] = tot;
+  __syncthreads();
+  if (threadIdx.y == 0 && i < n) {
+#pragma unroll
+    for (int yy = 1; yy < 8; ++yy) tot += red[yy][threadIdx.x];
+    const int kv = i / cvec, cvi = i - kv * cvec;
+    const int k = kv >> 2, ch = cvi * 4 + (kv & 3);
+    if (k < 9) gw[ch * 9 + k] = tot; else gb[ch] = tot;
+  }
+}
+
+// fast-path eligibility + launch shape: blockDim = cvec * ty_count <= 256
+template <typename T>
+static bool dw_run_shape(const DwParams& p, const void* extra, int& cvec, int& ty_count) {
+  if (p.C % 4 != 0 || p.C / 4 > 256) return false;
+  const uintptr_t al = 4 * sizeof(T) - 1;
+  if ((reinterpret_cast<uintptr_t>(p.x) & al) || (reinterpret_cast<uintptr_t>(p.y) & al) || (reinterpret_cast<uintptr_t>(extra) & al))
+    return false;
+  cvec = p.C / 4;
+  ty_count = 256 / cvec;
+  return true;
+}
+
+static unsigned dw_run_grid(const DwRunGeom& g, int ty_count) {
+  const unsigned need = (unsigned)((g.total + ty_count - 1) / ty_count);
+  const unsigned resident = 148u * 2u;
+  return need < resident ? (need ? need : 1u) : resident;
+}
+
 template <typename T, bool FLIP>
 static cudaError_t launch_dw(const DwParams& p, cudaStream_t s) {
   using A = typename DwAcc<T>::type;
+  if constexpr (sizeof(T) <= 4) {
+    int cvec, ty_count;
+    if (dw_run_shape<T>(p, nullptr, cvec, ty_count)) {
+      const DwRunGeom g = dw_run_geom(p);
+      adapter_dwconv_run_kernel<T, FLIP><<<dw_run_grid(g, ty_count), cvec * ty_count, 0, s>>>(p, g, cvec, ty_count);
+      return cudaGetLastError();
+    }
+  }
   const size_t smem = (size_t)p.C * 9 * sizeof(A);
   constexpr int kVec = 16 / (int)sizeof(T);
   const bool vec = sizeof(T) <= 4 && p.C % kVec == 0 && (reinterpret_cast<uintptr_t>(p.x) % 16 == 0) &&
@@ -198,9 +462,37 @@ cudaError_t launch_dwconv(const DwParams& p, int dtype, bool flip, cudaStream_t 
   }
 }
 
-// grad_weight / grad_bias accumulators: fp32 for f32/bf16 inputs, fp64 for f64 (both [C*9] / [C], zero-filled here).
-cudaError_t launch_dwconv_wgrad(const DwParams& p, int dtype, const void* grad_y, void* gw, void* gb, cudaStream_t s) {
+// bytes of the per-CTA partial rows the deterministic two-stage reduction needs (0: the generic atomic path is used)
+size_t dwconv_wgrad_workspace_bytes(const DwParams& p, int dtype) {
+  if ((dtype != MSDA_F32 && dtype != MSDA_BF16) || p.C % 4 != 0 || p.C / 4 > 256) return 0;
+  const int cvec = p.C / 4;
+  return (size_t)dw_run_grid(dw_run_geom(p), 256 / cvec) * 40 * cvec * sizeof(float);
+}
+
+// grad_weight / grad_bias accumulators: fp32 for f32/bf16 inputs, fp64 for f64 (both [C*9] / [C]).
+cudaError_t launch_dwconv_wgrad(const DwParams& p, int dtype, const void* grad_y, void* gw, void* gb, void* workspace,
+                                size_t workspace_bytes, int* launches, cudaStream_t s) {
   const size_t asz = dtype == MSDA_F64 ? 8 : 4;
+  if (dtype == MSDA_F32 || dtype == MSDA_BF16) {
+    int cvec, ty_count;
+    const bool ok = dtype == MSDA_F32 ? dw_run_shape<float>(p, grad_y, cvec, ty_count) : dw_run_shape<__nv_bfloat16>(p, grad_y, cvec, ty_count);
+    if (ok && workspace && workspace_bytes >= dwconv_wgrad_workspace_bytes(p, dtype)) {
+      const DwRunGeom g = dw_run_geom(p);
+      const unsigned grid = dw_run_grid(g, ty_count);
+      const size_t smem = (size_t)ty_count * 40 * cvec * sizeof(float);  // <= 256 * 40 * 4 = 40 KB
+      float* partial = reinterpret_cast<float*>(workspace);
+      if (dtype == MSDA_F32)
+        adapter_dwconv_wgrad_run_kernel<float><<<grid, cvec * ty_count, smem, s>>>(p, g, grad_y, partial, cvec, ty_count);
+      else
+        adapter_dwconv_wgrad_run_kernel<__nv_bfloat16><<<grid, cvec * ty_count, smem, s>>>(p, g, grad_y, partial, cvec, ty_count);
+      cudaError_t e2 = cudaGetLastError();
+      if (e2 != cudaSuccess) return e2;
+      adapter_dwconv_wgrad_sum_kernel<<<(40 * cvec + 31) / 32, dim3(32, 8), 0, s>>>(partial, (int)grid, cvec, (float*)gw, (float*)gb);
+      *launches = 2;
+      return cudaGetLastError();
+    }
+  }
+  *launches = 1;
   cudaError_t e = cudaMemsetAsync(gw, 0, (size_t)p.C * 9 * asz, s);
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(gb, 0, (size_t)p.C * asz, s);

@@ -26,7 +26,9 @@ struct DwParams {
   int B, Ntok, C, H, W;
 };
 cudaError_t launch_dwconv(const DwParams& p, int dtype, bool flip, cudaStream_t s);
-cudaError_t launch_dwconv_wgrad(const DwParams& p, int dtype, const void* grad_y, void* gw, void* gb, cudaStream_t s);
+size_t dwconv_wgrad_workspace_bytes(const DwParams& p, int dtype);
+cudaError_t launch_dwconv_wgrad(const DwParams& p, int dtype, const void* grad_y, void* gw, void* gb, void* workspace,
+                                size_t workspace_bytes, int* launches, cudaStream_t s);
 cudaError_t launch_forward_wide(const Params& p, int G, int minb, cudaStream_t s);
 cudaError_t launch_forward_smem(const Params& p, const SmemPlan& plan, int dtype, int G, int nt, cudaStream_t s);
 
@@ -476,14 +478,28 @@ int adapter_dwconv_backward_input(int dtype, const void* grad_y, const void* wei
   return 0;
 }
 
+size_t adapter_dwconv_backward_weight_workspace_bytes(int dtype, int32_t batch, int32_t n_tokens, int32_t channels, int32_t H,
+                                                      int32_t W) {
+  if (dw_check(dtype, batch, n_tokens, channels, H, W)) return 0;
+  DwParams p{nullptr, nullptr, nullptr, nullptr, batch, n_tokens, channels, H, W};
+  return dwconv_wgrad_workspace_bytes(p, dtype);
+}
+
 int adapter_dwconv_backward_weight(int dtype, const void* x, const void* grad_y, void* grad_weight, void* grad_bias,
-                                   int32_t batch, int32_t n_tokens, int32_t channels, int32_t H, int32_t W, void* stream) {
+                                   int32_t batch, int32_t n_tokens, int32_t channels, int32_t H, int32_t W, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
   if (int e = dw_check(dtype, batch, n_tokens, channels, H, W)) return e;
   if (!x || !grad_y || !grad_weight || !grad_bias) return fail(MSDA_E_NULL, "adapter_dwconv_backward_weight: NULL tensor pointer");
   DwParams p{x, nullptr, nullptr, nullptr, batch, n_tokens, channels, H, W};
-  const cudaError_t e = launch_dwconv_wgrad(p, dtype, grad_y, grad_weight, grad_bias, (cudaStream_t)stream);
+  const size_t need = dwconv_wgrad_workspace_bytes(p, dtype);
+  if (need && (!workspace || workspace_bytes < need))
+    return fail(MSDA_E_WORKSPACE, "adapter_dwconv_backward_weight: workspace of %zu bytes required, got %zu", need,
+                workspace ? workspace_bytes : (size_t)0);
+  int launches = 0;
+  const cudaError_t e = launch_dwconv_wgrad(p, dtype, grad_y, grad_weight, grad_bias, workspace, workspace_bytes, &launches,
+                                            (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "adapter_dwconv_backward_weight launch");
-  g_launches.fetch_add(1);
+  g_launches.fetch_add(launches);
   return 0;
 }
 
