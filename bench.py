@@ -37,6 +37,7 @@ VARIANTS = {
     'L': (16, 32, 896, 1),     # ViT-Adapter-L as configured by the reference (deform_ratio 0.5 -> 32 ch)
     'L64': (16, 64, 896, 1),   # ViT-Adapter-L as BASELINE.json words it (16 x 64)
     'HTC': (16, 32, 1024, 1),  # HTC++ inference shape (21 504 value tokens)
+    'M2F': (32, 32, 896, 1),   # Mask2Former pixel decoder's deformable encoder (..._large_896_...ss.py:50-61)
 }
 P = 4
 
@@ -45,6 +46,8 @@ def call_shapes(variant, batch):
     """The two operator calls of one adapter interaction: (name, N, M, D, Lq, level shapes)."""
     M, D, side, _ = VARIANTS[variant]
     l8, l16, l32 = side // 8, side // 16, side // 32
+    if variant == 'M2F':  # one self-attention call over the three levels' tokens
+        return [('encoder', batch, M, D, l8 * l8 + l16 * l16 + l32 * l32, [(l8, l8), (l16, l16), (l32, l32)])]
     inj = ('injector', batch, M, D, l16 * l16, [(l8, l8), (l16, l16), (l32, l32)])
     ext = ('extractor', batch, M, D, l8 * l8 + l16 * l16 + l32 * l32, [(l16, l16)])
     return [inj, ext]
@@ -77,6 +80,8 @@ def adapter_inputs(name, N, M, D, Lq, shapes, seed, dtype):
     # reference points: the query grid(s) — injector queries are the H/16 grid, extractor queries the 3 levels
     if name == 'injector':
         grids = [shapes[1]]
+    elif name == 'encoder':
+        grids = list(shapes)
     else:
         h, w = shapes[0]
         grids = [(2 * h, 2 * w), (h, w), (h // 2, w // 2)]
@@ -458,7 +463,7 @@ def run_ours(args):
     if rank == 0 and not args.no_other_shapes:
         other = []
         flushbuf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-        for ov, odt in (('L', 'bf16'), ('L', 'f32'), ('L64', 'bf16'), ('HTC', 'f32')):
+        for ov, odt in (('L', 'bf16'), ('L', 'f32'), ('L64', 'bf16'), ('HTC', 'f32'), ('M2F', 'bf16'), ('M2F', 'f32')):
             oM, oD, oside, ob = VARIANTS[ov]
             tdt = torch.float32 if odt == 'f32' else torch.bfloat16
             tot_ms, tot_pts, tot_bytes = 0.0, 0, 0
@@ -487,7 +492,7 @@ def run_ours(args):
                     tot_bytes += ab[key]
                 tot_pts += n_points(N_, M_, Lq_, len(shp))
             other.append({'variant': ov, 'dtype': odt, 'image': oside, 'batch': ob, 'heads': oM, 'channels': oD,
-                          'what': 'Injector+Extractor ' + ('fwd' if ov == 'HTC' else 'fwd+bwd') + ', L2 flushed, median of 10',
+                          'what': ('encoder self-attention ' if ov == 'M2F' else 'Injector+Extractor ') + ('fwd' if ov == 'HTC' else 'fwd+bwd') + ', L2 flushed, median of 10',
                           'us': tot_ms * 1e3, 'gsamples_s': tot_pts / (tot_ms * 1e-3) / 1e9,
                           'hbm_frac': tot_bytes / (tot_ms * 1e-3) / 1e9 / (float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'])
                                                                      if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else 6650.0)})

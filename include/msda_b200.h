@@ -200,6 +200,26 @@ int adapter_dwconv_backward_weight(int dtype, const void* x, const void* grad_y,
                                    int32_t batch, int32_t n_tokens, int32_t channels, int32_t H, int32_t W,
                                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Adapter LayerNorm prologues.
+ * Replaces the nn.LayerNorm(dim, eps=1e-6) calls in front of every Linear of the Injector / Extractor
+ * (adapter_modules.py:101-103,110-116,133-134,142-145: query_norm, feat_norm, ffn_norm):
+ *   y = (x - mean(x)) / sqrt(var(x) + eps) * gamma + beta   per row of C channels, biased variance,
+ * with y written directly in the consumer's dtype (bf16 under AMP: torch writes fp32 and the Linear casts it
+ * with another full pass) and mean / rstd saved for the backward.
+ *   x, grad_x [rows, C] in_dtype ; y, grad_y [rows, C] out_dtype ; (in, out) in {(f32,f32), (f32,bf16), (bf16,bf16)}
+ *   gamma, beta [C] fp32 (beta may be NULL) ; mean, rstd [rows] fp32 ; grad_gamma, grad_beta [C] fp32 (fully written)
+ *   C % 4 == 0 and C <= 1024, else MSDA_E_UNSUPPORTED (the caller keeps torch's LayerNorm)
+ *   workspace: adapter_layernorm_backward_workspace_bytes(rows, C) bytes, 16-byte aligned (per-CTA partial sums of the
+ *   deterministic two-stage grad_gamma / grad_beta reduction).
+ * ------------------------------------------------------------------------------------------------ */
+int adapter_layernorm_forward(int in_dtype, int out_dtype, const void* x, const void* gamma, const void* beta, void* y,
+                              float* mean, float* rstd, int64_t rows, int32_t channels, float eps, void* stream);
+size_t adapter_layernorm_backward_workspace_bytes(int64_t rows, int32_t channels);
+int adapter_layernorm_backward(int in_dtype, int out_dtype, const void* grad_y, const void* x, const void* gamma,
+                               const float* mean, const float* rstd, void* grad_x, float* grad_gamma, float* grad_beta,
+                               int64_t rows, int32_t channels, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Test hook: for every sampling point (N*Lq*M*L*P of them, same order as attn_weight) write
  *   idx[4*i+0] = h_low, idx[4*i+1] = w_low,
  *   idx[4*i+2] = corner-validity mask (bit k = corner k+1 is read; 0 = sample skipped),

@@ -15,4 +15,4 @@ Three independent checkers:
 Parity pin: tests/test_oracle_golden.py checks c_oracle and core_pytorch against golden vectors made
 by tests/golden/make_golden.py, which imports the real reference Python from /root/reference.
 """
-from . import c_oracle, core_pytorch, dwconv_ref, mmcv_msda_ref, refcuda  # noqa: F401
+from . import c_oracle, core_pytorch, dwconv_ref, layernorm_ref, mmcv_msda_ref, refcuda  # noqa: F401

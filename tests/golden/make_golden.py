@@ -185,8 +185,32 @@ def dwconv_case(ref_adapter, name, C, H, W, B, seed):
     print(name)
 
 
+def layernorm_case(ref_adapter, name, C, shape, seed, heads=4):
+    """The `query_norm` LayerNorm that the reference's Injector constructs (adapter_modules.py:127-134: norm_layer =
+    partial(nn.LayerNorm, eps=1e-6)), with non-trivial affine parameters: output and autograd gradients (fp64)."""
+    torch.manual_seed(seed)
+    inj = ref_adapter.Injector(dim=C, num_heads=heads, n_points=4, n_levels=3).double()
+    norm = inj.query_norm
+    with torch.no_grad():
+        norm.weight.copy_(1.0 + 0.3 * torch.randn(C, dtype=torch.double))
+        norm.bias.copy_(0.2 * torch.randn(C, dtype=torch.double))
+    x = (2.0 * torch.randn(*shape, C, dtype=torch.double) + 0.7).requires_grad_()
+    gy = torch.randn(*shape, C, dtype=torch.double)
+    y = norm(x)
+    y.backward(gy)
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), x=x.detach().numpy(), weight=norm.weight.detach().numpy(),
+                        bias=norm.bias.detach().numpy(), y=y.detach().numpy(), grad_y=gy.numpy(), grad_x=x.grad.numpy(),
+                        grad_weight=norm.weight.grad.numpy(), grad_bias=norm.bias.grad.numpy(),
+                        eps=np.array([norm.eps], dtype=np.float64))
+    print(name)
+
+
 def main():
     ref_func, ref_mod, ref_adapter = load_reference()
+    if 'layernorm' in sys.argv[1:]:   # only the N2 fixtures (the others are unchanged)
+        layernorm_case(ref_adapter, 'layernorm_c96', C=96, shape=(2, 21), seed=51)
+        layernorm_case(ref_adapter, 'layernorm_c768', C=768, shape=(1, 5), seed=52, heads=12)
+        return
     # 1. the reference's own test fixture (detection/ops/test.py:16-37), seed 3 == SURVEY App. A.4 KAT
     op_case(ref_func, 'op_kat_seed3', N=1, M=2, D=2, Lq=2, shapes=[(6, 4), (3, 2)], P=2, seed=3, dist='ref_test')
     # 2. injector-like (L=3) and extractor-like (L=1) miniatures, with the edge distribution
@@ -208,6 +232,9 @@ def main():
     # 7. ConvFFN's depth-wise conv on the token layout (C = 12: vector path for fp32; C = 6: scalar path)
     dwconv_case(ref_adapter, 'dwconv_tokens', C=12, H=4, W=6, B=2, seed=41)
     dwconv_case(ref_adapter, 'dwconv_tokens_c6', C=6, H=2, W=2, B=1, seed=42)
+    # 8. the LayerNorm in front of the adapter's Linears
+    layernorm_case(ref_adapter, 'layernorm_c96', C=96, shape=(2, 21), seed=51)
+    layernorm_case(ref_adapter, 'layernorm_c768', C=768, shape=(1, 5), seed=52, heads=12)
 
 
 if __name__ == '__main__':

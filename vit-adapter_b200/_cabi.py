@@ -25,6 +25,7 @@ EXPORTS = (
     'msda_set_tuning', 'msda_forward_fused', 'msda_backward_fused',
     'adapter_dwconv_forward', 'adapter_dwconv_backward_input', 'adapter_dwconv_backward_weight',
     'adapter_dwconv_backward_weight_workspace_bytes',
+    'adapter_layernorm_forward', 'adapter_layernorm_backward', 'adapter_layernorm_backward_workspace_bytes',
 )
 
 
@@ -82,6 +83,14 @@ def load():
         lib.adapter_dwconv_backward_weight.argtypes = [ctypes.c_int, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, ctypes.c_size_t, vp]
         lib.adapter_dwconv_backward_weight_workspace_bytes.restype = ctypes.c_size_t
         lib.adapter_dwconv_backward_weight_workspace_bytes.argtypes = [ctypes.c_int, i32, i32, i32, i32, i32]
+        i64 = ctypes.c_int64
+        lib.adapter_layernorm_forward.restype = ctypes.c_int
+        lib.adapter_layernorm_forward.argtypes = [ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp, i64, i32, ctypes.c_float, vp]
+        lib.adapter_layernorm_backward_workspace_bytes.restype = ctypes.c_size_t
+        lib.adapter_layernorm_backward_workspace_bytes.argtypes = [i64, i32]
+        lib.adapter_layernorm_backward.restype = ctypes.c_int
+        lib.adapter_layernorm_backward.argtypes = [ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp,
+                                                   ctypes.c_size_t, vp]
         lib.msda_debug_point_index.restype = ctypes.c_int
         lib.msda_debug_point_index.argtypes = [dp, i64p, i64p, vp, vp, vp]
         lib.msda_launch_count.restype = ctypes.c_uint64
@@ -445,3 +454,50 @@ def set_tuning(**kv):
             _raise(-1, 'msda_set_tuning')
         if k == 'fwd_smem':
             _WANT_HOST_SHAPES = int(v) == 2
+
+
+# --- adapter LayerNorm prologues ---------------------------------------------------------------------
+_LN_COMBOS = {(torch.float32, torch.float32), (torch.float32, torch.bfloat16), (torch.bfloat16, torch.bfloat16)}
+
+
+def layernorm_supported(x, weight, bias, out_dtype):
+    """True when the row kernel applies; otherwise the module calls torch's LayerNorm (the reference's op)."""
+    C = x.shape[-1]
+    return (x.is_cuda and (x.dtype, out_dtype) in _LN_COMBOS and weight is not None and weight.dtype == torch.float32
+            and (bias is None or bias.dtype == torch.float32) and C % 4 == 0 and C <= 1024 and x.numel() > 0)
+
+
+def layernorm_forward(x, weight, bias, eps, out_dtype):
+    """(y in out_dtype, mean, rstd) for x [..., C] (contiguous)."""
+    lib = load()
+    dev = _check_cuda(x=x, weight=weight) if bias is None else _check_cuda(x=x, weight=weight, bias=bias)
+    C = x.shape[-1]
+    rows = x.numel() // C
+    with torch.cuda.device(dev):
+        y = torch.empty(x.shape, dtype=out_dtype, device=dev)
+        stats = torch.empty((2, rows), dtype=torch.float32, device=dev)
+        rc = lib.adapter_layernorm_forward(_DTYPES[x.dtype], _DTYPES[out_dtype], x.data_ptr(), weight.data_ptr(),
+                                           bias.data_ptr() if bias is not None else None, y.data_ptr(), stats[0].data_ptr(),
+                                           stats[1].data_ptr(), rows, C, float(eps), _stream())
+    if rc != 0:
+        _raise(rc, 'adapter_layernorm_forward')
+    return y, stats
+
+
+def layernorm_backward(grad_y, x, weight, stats):
+    """(grad_x in x.dtype, grad_weight fp32 [C], grad_bias fp32 [C])."""
+    lib = load()
+    dev = _check_cuda(grad_y=grad_y, x=x, weight=weight)
+    C = x.shape[-1]
+    rows = x.numel() // C
+    with torch.cuda.device(dev):
+        gx = torch.empty_like(x)
+        gwb = torch.empty((2, C), dtype=torch.float32, device=dev)
+        ws_bytes = lib.adapter_layernorm_backward_workspace_bytes(rows, C)
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        rc = lib.adapter_layernorm_backward(_DTYPES[x.dtype], _DTYPES[grad_y.dtype], grad_y.data_ptr(), x.data_ptr(), weight.data_ptr(),
+                                            stats[0].data_ptr(), stats[1].data_ptr(), gx.data_ptr(), gwb[0].data_ptr(), gwb[1].data_ptr(),
+                                            rows, C, ws.data_ptr(), ws_bytes, _stream())
+    if rc != 0:
+        _raise(rc, 'adapter_layernorm_backward')
+    return gx, gwb[0], gwb[1]

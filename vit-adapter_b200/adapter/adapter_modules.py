@@ -85,6 +85,39 @@ def deform_inputs(x):
     return out
 
 
+class _LayerNormRows(torch.autograd.Function):
+    """nn.LayerNorm over the last dimension as one row kernel (csrc/adapter_layernorm.cu): x is read once, y is written
+    in the consumer's dtype, mean / rstd are kept for a backward that also reads x once."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, out_dtype):
+        x = x.contiguous()
+        y, stats = _cabi.layernorm_forward(x, weight, bias, eps, out_dtype)
+        ctx.save_for_backward(x, weight, stats)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_y):
+        x, weight, stats = ctx.saved_tensors
+        gx, gw, gb = _cabi.layernorm_backward(grad_y.contiguous(), x, weight, stats)
+        return gx, gw, (gb if ctx.has_bias else None), None, None
+
+
+def apply_norm(norm, x, fused=True):
+    """`norm(x)` for the LayerNorms in front of the adapter's Linears (reference adapter_modules.py:110-116,142-145).
+    A plain affine nn.LayerNorm on CUDA goes through the row kernel and, under bf16 autocast, hands the Linear a bf16
+    tensor directly (torch would write fp32 and cast it again); anything else calls the module as the reference does."""
+    if fused and type(norm) is nn.LayerNorm and norm.elementwise_affine and len(norm.normalized_shape) == 1 and x.is_cuda:
+        out_dtype = x.dtype
+        if torch.is_autocast_enabled('cuda'):
+            out_dtype = torch.get_autocast_dtype('cuda')
+        if _cabi.layernorm_supported(x, norm.weight, norm.bias, out_dtype):
+            return _LayerNormRows.apply(x, norm.weight, norm.bias, norm.eps, out_dtype)
+    return norm(x)
+
+
 class _DWConvTokens(torch.autograd.Function):
     """Depth-wise 3x3 on the [B, 21n, C] token layout in one kernel (csrc/adapter_dwconv.cu) instead of the
     reference's slice / transpose / conv2d / transpose / cat sequence."""
@@ -160,6 +193,7 @@ class Extractor(nn.Module):
                                  ratio=deform_ratio)
         self.with_cffn = with_cffn
         self.with_cp = with_cp
+        self.fused_norm = True   # LayerNorms through the row kernel (apply_norm); False = torch's, as the reference
         if with_cffn:
             self.ffn = ConvFFN(in_features=dim, hidden_features=int(dim * cffn_ratio), drop=drop)
             self.ffn_norm = norm_layer(dim)
@@ -167,10 +201,11 @@ class Extractor(nn.Module):
 
     def forward(self, query, reference_points, feat, spatial_shapes, level_start_index, H, W):
         def inner(query, feat):
-            query = query + self.attn(self.query_norm(query), reference_points, self.feat_norm(feat),
+            fn = self.fused_norm
+            query = query + self.attn(apply_norm(self.query_norm, query, fn), reference_points, apply_norm(self.feat_norm, feat, fn),
                                       spatial_shapes, level_start_index, None)
             if self.with_cffn:
-                query = query + self.drop_path(self.ffn(self.ffn_norm(query), H, W))
+                query = query + self.drop_path(self.ffn(apply_norm(self.ffn_norm, query, fn), H, W))
             return query
 
         if self.with_cp and query.requires_grad:
@@ -190,11 +225,13 @@ class Injector(nn.Module):
         self.attn = MSDeformAttn(d_model=dim, n_levels=n_levels, n_heads=num_heads, n_points=n_points,
                                  ratio=deform_ratio)
         self.gamma = nn.Parameter(init_values * torch.ones((dim)), requires_grad=True)
+        self.fused_norm = True
 
     def forward(self, query, reference_points, feat, spatial_shapes, level_start_index):
         def inner(query, feat):
-            attn = self.attn(self.query_norm(query), reference_points, self.feat_norm(feat), spatial_shapes,
-                             level_start_index, None)
+            fn = self.fused_norm
+            attn = self.attn(apply_norm(self.query_norm, query, fn), reference_points, apply_norm(self.feat_norm, feat, fn),
+                             spatial_shapes, level_start_index, None)
             return query + self.gamma * attn
 
         if self.with_cp and query.requires_grad:

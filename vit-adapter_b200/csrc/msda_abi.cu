@@ -29,6 +29,24 @@ cudaError_t launch_dwconv(const DwParams& p, int dtype, bool flip, cudaStream_t 
 size_t dwconv_wgrad_workspace_bytes(const DwParams& p, int dtype);
 cudaError_t launch_dwconv_wgrad(const DwParams& p, int dtype, const void* grad_y, void* gw, void* gb, void* workspace,
                                 size_t workspace_bytes, int* launches, cudaStream_t s);
+struct LnParams {
+  const void* x;
+  const void* gamma;
+  const void* beta;
+  void* y;
+  float* mean;
+  float* rstd;
+  const void* grad_y;
+  void* grad_x;
+  float* partial;
+  long long rows;
+  int C;
+  float eps;
+};
+bool layernorm_supported(int C);
+size_t layernorm_backward_workspace_bytes(long long rows, int C);
+cudaError_t launch_layernorm_forward(const LnParams& p, int in_dtype, int out_dtype, cudaStream_t s);
+cudaError_t launch_layernorm_backward(const LnParams& p, int in_dtype, int out_dtype, float* dgamma, float* dbeta, cudaStream_t s);
 cudaError_t launch_forward_wide(const Params& p, int G, int minb, cudaStream_t s);
 cudaError_t launch_forward_smem(const Params& p, const SmemPlan& plan, int dtype, int G, int nt, cudaStream_t s);
 
@@ -500,6 +518,55 @@ int adapter_dwconv_backward_weight(int dtype, const void* x, const void* grad_y,
                                             (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "adapter_dwconv_backward_weight launch");
   g_launches.fetch_add(launches);
+  return 0;
+}
+
+static int ln_check(const char* who, int in_dtype, int out_dtype, int64_t rows, int32_t C) {
+  const bool combo = (in_dtype == MSDA_F32 && (out_dtype == MSDA_F32 || out_dtype == MSDA_BF16)) ||
+                     (in_dtype == MSDA_BF16 && out_dtype == MSDA_BF16);
+  if (!combo) return fail(MSDA_E_DTYPE, "%s: (x, y) dtypes must be (f32, f32), (f32, bf16) or (bf16, bf16), got (%d, %d)", who, in_dtype, out_dtype);
+  if (rows <= 0 || C <= 0 || rows * (int64_t)C >= (1ll << 40)) return fail(MSDA_E_DIMS, "%s: bad dims rows=%lld C=%d", who, (long long)rows, C);
+  if (!layernorm_supported(C)) return fail(MSDA_E_UNSUPPORTED, "%s: C=%d needs C %% 4 == 0 and C <= 1024", who, C);
+  return 0;
+}
+
+static bool ln_misaligned(const void* p, int dtype) { return (reinterpret_cast<uintptr_t>(p) & (4 * elem_size(dtype) - 1)) != 0; }
+
+int adapter_layernorm_forward(int in_dtype, int out_dtype, const void* x, const void* gamma, const void* beta, void* y,
+                              float* mean, float* rstd, int64_t rows, int32_t channels, float eps, void* stream) {
+  if (int e = ln_check("adapter_layernorm_forward", in_dtype, out_dtype, rows, channels)) return e;
+  if (!x || !gamma || !y || !mean || !rstd) return fail(MSDA_E_NULL, "adapter_layernorm_forward: NULL tensor pointer");
+  if (ln_misaligned(x, in_dtype) || ln_misaligned(y, out_dtype) || ln_misaligned(gamma, MSDA_F32) || (beta && ln_misaligned(beta, MSDA_F32)))
+    return fail(MSDA_E_ALIGN, "adapter_layernorm_forward: x, y, gamma, beta must be aligned to 4 elements");
+  LnParams p{x, gamma, beta, y, mean, rstd, nullptr, nullptr, nullptr, (long long)rows, channels, eps};
+  const cudaError_t e = launch_layernorm_forward(p, in_dtype, out_dtype, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "adapter_layernorm_forward launch");
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+size_t adapter_layernorm_backward_workspace_bytes(int64_t rows, int32_t channels) {
+  if (rows <= 0 || !layernorm_supported(channels)) return 0;
+  return layernorm_backward_workspace_bytes((long long)rows, channels);
+}
+
+int adapter_layernorm_backward(int in_dtype, int out_dtype, const void* grad_y, const void* x, const void* gamma,
+                               const float* mean, const float* rstd, void* grad_x, float* grad_gamma, float* grad_beta,
+                               int64_t rows, int32_t channels, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int e = ln_check("adapter_layernorm_backward", in_dtype, out_dtype, rows, channels)) return e;
+  if (!grad_y || !x || !gamma || !mean || !rstd || !grad_x || !grad_gamma || !grad_beta)
+    return fail(MSDA_E_NULL, "adapter_layernorm_backward: NULL tensor pointer");
+  if (ln_misaligned(x, in_dtype) || ln_misaligned(grad_x, in_dtype) || ln_misaligned(grad_y, out_dtype) || ln_misaligned(gamma, MSDA_F32))
+    return fail(MSDA_E_ALIGN, "adapter_layernorm_backward: x, grad_x, grad_y, gamma must be aligned to 4 elements");
+  const size_t need = layernorm_backward_workspace_bytes((long long)rows, channels);
+  if (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 15))
+    return fail(MSDA_E_WORKSPACE, "adapter_layernorm_backward: 16-byte aligned workspace of %zu bytes required, got %zu", need,
+                workspace ? workspace_bytes : (size_t)0);
+  LnParams p{x, gamma, nullptr, nullptr, const_cast<float*>(mean), const_cast<float*>(rstd), grad_y, grad_x,
+             reinterpret_cast<float*>(workspace), (long long)rows, channels, 0.f};
+  const cudaError_t e = launch_layernorm_backward(p, in_dtype, out_dtype, grad_gamma, grad_beta, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "adapter_layernorm_backward launch");
+  g_launches.fetch_add(2);
   return 0;
 }
 
