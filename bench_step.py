@@ -177,6 +177,11 @@ def main():
     ap.add_argument('--amp', action='store_true', help='torch.autocast(bfloat16) + bf16 sampling core')
     ap.add_argument('--with-cp', action='store_true', help='activation checkpointing in Injector/Extractor (L configs)')
     ap.add_argument('--op', default='ours', choices=['ours', 'ref_cuda'])
+    ap.add_argument('--reference-sequence', action='store_true',
+                    help="the adapter exactly as the reference runs it: reference CUDA core, torch LayerNorm, the DWConv "
+                         "slice/transpose/conv2d sequence, separate offset/weight linears + softmax (implies --op ref_cuda)")
+    ap.add_argument('--graph', action='store_true',
+                    help='capture the whole step (forward, backward, optimizer) in ONE CUDA graph and replay it (single GPU)')
     args = ap.parse_args()
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -190,6 +195,8 @@ def main():
 
     import vit_adapter_b200 as vab
     from vit_adapter_b200 import _cabi
+    if args.reference_sequence:
+        args.op = 'ref_cuda'
     if args.op == 'ref_cuda':
         use_reference_cuda_core()
     if args.amp:
@@ -197,12 +204,18 @@ def main():
 
     torch.manual_seed(1234 + rank)
     net = Net(args.variant, sync_bn=(world > 1), with_cp=args.with_cp).to(dev)
+    if args.reference_sequence:
+        for m in net.modules():
+            for flag in ('fused_norm', 'token_kernel', 'fused', 'merge_query_linears'):
+                if hasattr(m, flag):
+                    setattr(m, flag, False)
     n_params = sum(p.numel() for p in net.parameters())
     n_adapter = sum(p.numel() for n, p in net.named_parameters() if 'interactions' in n or 'spm' in n)
     model = net
     if world > 1 and args.mode == 'train':
         model = nn.parallel.DistributedDataParallel(net, device_ids=[local_rank], gradient_as_bucket_view=True)
-    opt = torch.optim.AdamW(net.parameters(), lr=6e-5, weight_decay=0.01, fused=True) if args.mode == 'train' else None
+    use_graph = args.graph and world == 1
+    opt = torch.optim.AdamW(net.parameters(), lr=6e-5, weight_decay=0.01, fused=True, capturable=use_graph) if args.mode == 'train' else None
     img = torch.randn(args.batch, 3, args.image, args.image, device=dev)
     lab = torch.randint(0, 150, (args.batch, args.image // 4, args.image // 4), device=dev)
 
@@ -229,6 +242,40 @@ def main():
     for _ in range(args.warmup):
         step()
     barrier()
+    launches_per_replay = 0
+    if use_graph:
+        # whole-step capture: at 2 images per GPU the step is ~1 900 kernels of a few microseconds each and the Python /
+        # launch path is as long as the GPU work; one graph launch replaces it. Everything on the path is capturable:
+        # no host sync (MSDeformAttn's shape check is memoised), no allocation outside torch's graph pool, the library
+        # launches on the capturing stream it is handed.
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                step()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        if opt is not None:
+            opt.zero_grad(set_to_none=True)
+        c0 = _cabi.launch_count()
+        with torch.cuda.graph(graph):
+            with torch.autocast('cuda', dtype=torch.bfloat16, enabled=args.amp):
+                if args.mode == 'train':
+                    static_out = F.cross_entropy(model(img).float(), lab)
+                else:
+                    with torch.no_grad():
+                        static_out = model(img)
+            if args.mode == 'train':
+                static_out.backward()
+                opt.step()
+        launches_per_replay = _cabi.launch_count() - c0
+
+        def step():  # noqa: F811
+            graph.replay()
+            return static_out
+        for _ in range(2):
+            step()
+        barrier()
     l0 = _cabi.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -237,7 +284,7 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = _cabi.launch_count() - l0
+    launches = _cabi.launch_count() - l0 + launches_per_replay * args.steps
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -247,7 +294,8 @@ def main():
             'metric': 'vit_adapter_%s_%s_img_per_s' % (args.variant, args.mode), 'value': world * args.batch * args.steps / (ms * 1e-3),
             'unit': 'img/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'dtype': 'bf16-autocast' if args.amp else 'f32', 'data': 'synthetic',
-            'op': args.op, 'msda_kernel_launches': launches,
+            'op': args.op, 'adapter': 'reference op sequence' if args.reference_sequence else 'this repo (fused norm / dwconv / softmax+locations)',
+            'msda_kernel_launches': launches, 'cuda_graph': bool(use_graph),
             'config': {'workload': 'ViT-Adapter-%s backbone (this repo\'s adapter modules + MSDeformAttn) + stand-in head, %dx%d, '
                                    '%d img/GPU, %s' % (args.variant, args.image, args.image, args.batch, args.mode),
                        'params_total': n_params, 'params_adapter': n_adapter, 'with_cp': args.with_cp,
