@@ -206,7 +206,7 @@ def main():
     net = Net(args.variant, sync_bn=(world > 1), with_cp=args.with_cp).to(dev)
     if args.reference_sequence:
         for m in net.modules():
-            for flag in ('fused_norm', 'token_kernel', 'fused', 'merge_query_linears'):
+            for flag in ('fused_norm', 'token_kernel', 'fused', 'merge_query_linears', 'colsum_bias_grad'):
                 if hasattr(m, flag):
                     setattr(m, flag, False)
     n_params = sum(p.numel() for p in net.parameters())

@@ -220,6 +220,18 @@ int adapter_layernorm_backward(int in_dtype, int out_dtype, const void* grad_y, 
                                const float* mean, const float* rstd, void* grad_x, float* grad_gamma, float* grad_beta,
                                int64_t rows, int32_t channels, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Bias gradient of the adapter's Linears: out[c] = sum over rows of x[row, c], fp32.
+ * Replaces the row reduction inside the backward of every nn.Linear with a bias in MSDeformAttn
+ * (ms_deform_attn.py:57-60) and ConvFFN (adapter_modules.py:56,60).
+ *   x [rows, C] f32 (C % 4 == 0, C <= 1024) or bf16 (C % 8 == 0, C <= 2048), 16-byte aligned; out [C] fp32
+ *   workspace: adapter_colsum_workspace_bytes(dtype, rows, C) bytes (per-CTA partial rows; deterministic sum)
+ *   anything else returns MSDA_E_UNSUPPORTED (the caller keeps torch's sum).
+ * ------------------------------------------------------------------------------------------------ */
+size_t adapter_colsum_workspace_bytes(int dtype, int64_t rows, int32_t channels);
+int adapter_colsum(int dtype, const void* x, int64_t rows, int32_t channels, float* out, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
 /* Test hook: for every sampling point (N*Lq*M*L*P of them, same order as attn_weight) write
  *   idx[4*i+0] = h_low, idx[4*i+1] = w_low,
  *   idx[4*i+2] = corner-validity mask (bit k = corner k+1 is read; 0 = sample skipped),

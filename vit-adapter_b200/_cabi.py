@@ -26,6 +26,7 @@ EXPORTS = (
     'adapter_dwconv_forward', 'adapter_dwconv_backward_input', 'adapter_dwconv_backward_weight',
     'adapter_dwconv_backward_weight_workspace_bytes',
     'adapter_layernorm_forward', 'adapter_layernorm_backward', 'adapter_layernorm_backward_workspace_bytes',
+    'adapter_colsum', 'adapter_colsum_workspace_bytes',
 )
 
 
@@ -88,6 +89,10 @@ def load():
         lib.adapter_layernorm_forward.argtypes = [ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp, i64, i32, ctypes.c_float, vp]
         lib.adapter_layernorm_backward_workspace_bytes.restype = ctypes.c_size_t
         lib.adapter_layernorm_backward_workspace_bytes.argtypes = [i64, i32]
+        lib.adapter_colsum_workspace_bytes.restype = ctypes.c_size_t
+        lib.adapter_colsum_workspace_bytes.argtypes = [ctypes.c_int, i64, i32]
+        lib.adapter_colsum.restype = ctypes.c_int
+        lib.adapter_colsum.argtypes = [ctypes.c_int, vp, i64, i32, vp, vp, ctypes.c_size_t, vp]
         lib.adapter_layernorm_backward.restype = ctypes.c_int
         lib.adapter_layernorm_backward.argtypes = [ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp,
                                                    ctypes.c_size_t, vp]
@@ -501,3 +506,33 @@ def layernorm_backward(grad_y, x, weight, stats):
     if rc != 0:
         _raise(rc, 'adapter_layernorm_backward')
     return gx, gwb[0], gwb[1]
+
+
+# --- bias gradient of the adapter's Linears ------------------------------------------------------------
+def colsum_supported(x):
+    """x: [..., C] contiguous CUDA f32 (C % 4 == 0, C <= 1024) or bf16 (C % 8 == 0, C <= 2048)."""
+    if not (x.is_cuda and x.dim() >= 2 and x.numel() > 0 and x.is_contiguous()):
+        return False
+    C = x.shape[-1]
+    if x.dtype == torch.float32:
+        return C % 4 == 0 and C <= 1024
+    if x.dtype == torch.bfloat16:
+        return C % 8 == 0 and C <= 2048
+    return False
+
+
+def colsum(x):
+    """fp32 [C] = sum of x over all leading dimensions (deterministic two-stage reduction)."""
+    lib = load()
+    dev = _check_cuda(x=x)
+    C = x.shape[-1]
+    rows = x.numel() // C
+    code = _DTYPES[x.dtype]
+    with torch.cuda.device(dev):
+        out = torch.empty((C,), dtype=torch.float32, device=dev)
+        ws_bytes = lib.adapter_colsum_workspace_bytes(code, rows, C)
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        rc = lib.adapter_colsum(code, x.data_ptr(), rows, C, out.data_ptr(), ws.data_ptr(), ws_bytes, _stream())
+    if rc != 0:
+        _raise(rc, 'adapter_colsum')
+    return out

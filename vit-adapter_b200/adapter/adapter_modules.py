@@ -20,6 +20,7 @@ import torch.nn as nn
 import torch.utils.checkpoint as cp
 
 from .. import _cabi
+from ..functions import linear
 from ..modules import MSDeformAttn
 
 
@@ -175,10 +176,12 @@ class ConvFFN(nn.Module):
         self.act = act_layer()
         self.fc2 = nn.Linear(hidden_features, out_features)
         self.drop = nn.Dropout(drop)
+        self.colsum_bias_grad = True   # bias gradients of fc1 / fc2 through the column-sum kernel (functions/linear.py)
 
     def forward(self, x, H, W):
-        x = self.drop(self.act(self.dwconv(self.fc1(x), H, W)))
-        return self.drop(self.fc2(x))
+        cs = self.colsum_bias_grad
+        x = self.drop(self.act(self.dwconv(linear(x, self.fc1.weight, self.fc1.bias, cs), H, W)))
+        return self.drop(linear(x, self.fc2.weight, self.fc2.bias, cs))
 
 
 class Extractor(nn.Module):

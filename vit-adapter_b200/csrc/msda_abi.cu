@@ -47,6 +47,9 @@ bool layernorm_supported(int C);
 size_t layernorm_backward_workspace_bytes(long long rows, int C);
 cudaError_t launch_layernorm_forward(const LnParams& p, int in_dtype, int out_dtype, cudaStream_t s);
 cudaError_t launch_layernorm_backward(const LnParams& p, int in_dtype, int out_dtype, float* dgamma, float* dbeta, cudaStream_t s);
+bool colsum_supported(int dtype, int C);
+size_t colsum_workspace_bytes(int dtype, long long rows, int C);
+cudaError_t launch_colsum(int dtype, const void* x, long long rows, int C, float* out, float* partial, cudaStream_t s);
 cudaError_t launch_forward_wide(const Params& p, int G, int minb, cudaStream_t s);
 cudaError_t launch_forward_smem(const Params& p, const SmemPlan& plan, int dtype, int G, int nt, cudaStream_t s);
 
@@ -566,6 +569,30 @@ int adapter_layernorm_backward(int in_dtype, int out_dtype, const void* grad_y, 
              reinterpret_cast<float*>(workspace), (long long)rows, channels, 0.f};
   const cudaError_t e = launch_layernorm_backward(p, in_dtype, out_dtype, grad_gamma, grad_beta, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "adapter_layernorm_backward launch");
+  g_launches.fetch_add(2);
+  return 0;
+}
+
+size_t adapter_colsum_workspace_bytes(int dtype, int64_t rows, int32_t channels) {
+  if (rows <= 0 || channels <= 0) return 0;
+  return colsum_workspace_bytes(dtype, (long long)rows, channels);
+}
+
+int adapter_colsum(int dtype, const void* x, int64_t rows, int32_t channels, float* out, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+  if (elem_size(dtype) == 0) return fail(MSDA_E_DTYPE, "adapter_colsum: unknown dtype %d", dtype);
+  if (rows <= 0 || channels <= 0 || rows * (int64_t)channels >= (1ll << 40))
+    return fail(MSDA_E_DIMS, "adapter_colsum: bad dims rows=%lld C=%d", (long long)rows, channels);
+  if (!colsum_supported(dtype, channels))
+    return fail(MSDA_E_UNSUPPORTED, "adapter_colsum: needs f32 (C %% 4 == 0, C <= 1024) or bf16 (C %% 8 == 0, C <= 2048), got dtype %d C=%d",
+                dtype, channels);
+  if (!x || !out) return fail(MSDA_E_NULL, "adapter_colsum: NULL tensor pointer");
+  if (reinterpret_cast<uintptr_t>(x) & 15) return fail(MSDA_E_ALIGN, "adapter_colsum: x must be 16-byte aligned");
+  const size_t need = colsum_workspace_bytes(dtype, (long long)rows, channels);
+  if (!workspace || workspace_bytes < need)
+    return fail(MSDA_E_WORKSPACE, "adapter_colsum: workspace of %zu bytes required, got %zu", need, workspace ? workspace_bytes : (size_t)0);
+  const cudaError_t e = launch_colsum(dtype, x, (long long)rows, channels, out, reinterpret_cast<float*>(workspace), (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "adapter_colsum launch");
   g_launches.fetch_add(2);
   return 0;
 }

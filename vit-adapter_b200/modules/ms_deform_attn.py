@@ -19,7 +19,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .. import _cabi
-from ..functions import MSDeformAttnFunction, MSDeformAttnFusedFunction, MSDeformAttnMergedFunction
+from ..functions import MSDeformAttnFunction, MSDeformAttnFusedFunction, MSDeformAttnMergedFunction, linear
 
 
 def _is_power_of_2(n):
@@ -55,6 +55,9 @@ class MSDeformAttn(nn.Module):
         # rounding of the softmax normalisation. Set to False to force the reference's op sequence.
         self.fused = True
         self.merge_query_linears = True
+        # bias gradients of value_proj / output_proj / the merged query linear through the column-sum kernel
+        # (functions/linear.py); False = nn.Linear's own backward
+        self.colsum_bias_grad = True
         self._reset_parameters()
 
     def _reset_parameters(self):
@@ -94,7 +97,8 @@ class MSDeformAttn(nn.Module):
         self._check_len_in(input_spatial_shapes, len_in)
         M, L, P = self.n_heads, self.n_levels, self.n_points
 
-        value = self.value_proj(input_flatten)
+        cs = self.colsum_bias_grad
+        value = linear(input_flatten, self.value_proj.weight, self.value_proj.bias, cs)
         if input_padding_mask is not None:
             value = value.masked_fill(input_padding_mask[..., None], float(0))
         value = value.view(N, len_in, M, int(self.ratio * self.d_model) // M)
@@ -105,7 +109,7 @@ class MSDeformAttn(nn.Module):
                 # (state-dict keys untouched); the kernels consume its output in place
                 w = torch.cat([self.sampling_offsets.weight, self.attention_weights.weight], 0)
                 b = torch.cat([self.sampling_offsets.bias, self.attention_weights.bias], 0)
-                merged = F.linear(query, w, b)
+                merged = linear(query, w, b, cs)
                 output = MSDeformAttnMergedFunction.apply(value, input_spatial_shapes, input_level_start_index,
                                                           reference_points, merged, L, P)
             else:
@@ -113,7 +117,7 @@ class MSDeformAttn(nn.Module):
                 logits = self.attention_weights(query).view(N, Lq, M, L * P)
                 output = MSDeformAttnFusedFunction.apply(value, input_spatial_shapes, input_level_start_index,
                                                          reference_points, offsets, logits)
-            return self.output_proj(output)
+            return linear(output, self.output_proj.weight, self.output_proj.bias, cs)
 
         offsets = self.sampling_offsets(query).view(N, Lq, M, L, P, 2)
         weights = F.softmax(self.attention_weights(query).view(N, Lq, M, L * P), -1).view(N, Lq, M, L, P)
@@ -130,4 +134,4 @@ class MSDeformAttn(nn.Module):
                 reference_points.shape[-1]))
         output = MSDeformAttnFunction.apply(value, input_spatial_shapes, input_level_start_index,
                                             locations, weights, self.im2col_step)
-        return self.output_proj(output)
+        return linear(output, self.output_proj.weight, self.output_proj.bias, cs)
