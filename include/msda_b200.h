@@ -216,9 +216,19 @@ int adapter_dwconv_backward_weight(int dtype, const void* x, const void* grad_y,
 int adapter_layernorm_forward(int in_dtype, int out_dtype, const void* x, const void* gamma, const void* beta, void* y,
                               float* mean, float* rstd, int64_t rows, int32_t channels, float eps, void* stream);
 size_t adapter_layernorm_backward_workspace_bytes(int64_t rows, int32_t channels);
+/* grad_residual (optional, [rows, C] in_dtype, may be NULL): when x also feeds a residual connection
+ * (query + f(LN(query)), adapter_modules.py:113-116), the gradient arriving over that connection; it is added into
+ * grad_x here, which removes autograd's separate full-tensor add. */
 int adapter_layernorm_backward(int in_dtype, int out_dtype, const void* grad_y, const void* x, const void* gamma,
-                               const float* mean, const float* rstd, void* grad_x, float* grad_gamma, float* grad_beta,
-                               int64_t rows, int32_t channels, void* workspace, size_t workspace_bytes, void* stream);
+                               const float* mean, const float* rstd, const void* grad_residual, void* grad_x,
+                               float* grad_gamma, float* grad_beta, int64_t rows, int32_t channels, void* workspace,
+                               size_t workspace_bytes, void* stream);
+
+/* Residual epilogue of the Extractor (adapter_modules.py:113-116 `query = query + attn`,
+ * `query = query + drop_path(ffn(...))`): out[i] = residual[i] + (float)branch[i] with an fp32 stream and an f32 | bf16
+ * branch (the mixed-dtype case torch's add does not vectorise). n % 8 == 0, 16-byte aligned pointers; out may alias
+ * residual. Anything else: MSDA_E_UNSUPPORTED / MSDA_E_ALIGN and the caller keeps torch's add. */
+int adapter_residual_add(int branch_dtype, const float* residual, const void* branch, float* out, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Bias gradient of the adapter's Linears: out[c] = sum over rows of x[row, c], fp32.

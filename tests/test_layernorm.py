@@ -141,3 +141,79 @@ def test_injector_extractor_with_and_without_row_kernel_agree():
         torch.testing.assert_close(outs[0], outs[1], rtol=1e-4, atol=1e-5)
         for a, b in zip(*grads):
             torch.testing.assert_close(a, b, rtol=2e-4, atol=2e-4 * float(b.abs().max()) + 1e-7)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('amp', [False, True], ids=['f32', 'bf16-autocast'])
+def test_residual_gradient_is_folded_into_layernorm_backward(amp):
+    """x + f(LN(x)): the gradient over the residual connection enters the LayerNorm backward kernel (no separate add)."""
+    from vit_adapter_b200 import _cabi
+    from vit_adapter_b200.adapter.adapter_modules import apply_norm_residual
+    g = load_golden('layernorm_c96')
+    m = _module(g)
+    x = g['x'].float().cuda().requires_grad_()
+    a = torch.randn(g['x'].shape, generator=torch.Generator().manual_seed(9))
+    n0 = _cabi.launch_count()
+    with torch.autocast('cuda', dtype=torch.bfloat16, enabled=amp):
+        y, xr = apply_norm_residual(m, x)
+    assert torch.equal(xr, x) and xr.requires_grad
+    gy = g['grad_y'].to(y.dtype)
+    ((y.float() * gy.float().cuda()).sum() + (xr * a.cuda()).sum()).backward()
+    assert _cabi.launch_count() - n0 == 3
+    wgx, _, _ = layernorm_ref.layernorm_backward(g['x'].float().double(), g['weight'].float().double(), float(g['eps'][0]), gy.double())
+    want = wgx + a.double()
+    torch.testing.assert_close(x.grad.cpu().double(), want, rtol=1e-5, atol=1e-5 * float(want.abs().max()))
+    # only the residual output used -> gradient passes straight through
+    x2 = g['x'].float().cuda().requires_grad_()
+    _, xr2 = apply_norm_residual(m, x2)
+    (xr2 * a.cuda()).sum().backward()
+    torch.testing.assert_close(x2.grad.cpu(), a, rtol=0, atol=0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('bdt', [torch.bfloat16, torch.float32], ids=['bf16-branch', 'f32-branch'])
+def test_residual_add_kernel_is_bit_identical_to_torch(bdt):
+    from vit_adapter_b200 import _cabi
+    gen = torch.Generator().manual_seed(4)
+    res = torch.randn(3, 1001, 8 * 13, generator=gen).cuda()
+    br = torch.randn(3, 1001, 8 * 13, generator=gen).to(bdt).cuda()
+    assert _cabi.residual_add_supported(res, br)
+    n0 = _cabi.launch_count()
+    out = _cabi.residual_add(res, br)
+    assert _cabi.launch_count() - n0 == 1
+    assert torch.equal(out, res + br) and out.dtype == torch.float32
+    assert not _cabi.residual_add_supported(res[..., :7].contiguous(), br[..., :7].contiguous())   # 3*1001*7 not a multiple of 8
+    from vit_adapter_b200.adapter.adapter_modules import residual_add
+    r = res.clone().requires_grad_()
+    b = br.clone().requires_grad_()
+    residual_add(r, b).square().sum().backward()
+    r2 = res.clone().requires_grad_()
+    b2 = br.clone().requires_grad_()
+    (r2 + b2).square().sum().backward()
+    assert torch.equal(r.grad, r2.grad) and torch.equal(b.grad, b2.grad) and b.grad.dtype == bdt
+
+
+@pytest.mark.gpu
+def test_extractor_bf16_autocast_with_and_without_adapter_kernels():
+    """bf16 autocast: row-kernel LayerNorm + folded residual gradient + residual-add kernel vs torch's op sequence."""
+    from vit_adapter_b200.adapter import Extractor, deform_inputs
+    torch.manual_seed(1)
+    dev = torch.device('cuda')
+    dim, heads, side = 64, 4, 64
+    _, di2 = deform_inputs(torch.zeros(2, 3, side, side, device=dev))
+    h = side // 16
+    x = torch.randn(2, h * h, dim, device=dev)
+    c = torch.randn(2, 21 * (h // 2) ** 2, dim, device=dev)
+    mod = Extractor(dim, heads, 4, 1, 1.0).to(dev)
+    res = []
+    for fused in (True, False):
+        mod.fused_norm = fused
+        mod.zero_grad(set_to_none=True)
+        q = c.clone().requires_grad_()
+        with torch.autocast('cuda', dtype=torch.bfloat16):
+            out = mod(q, di2[0], x, di2[1], di2[2], h, h)
+        assert out.dtype == torch.float32
+        out.square().sum().backward()
+        res.append((out.detach(), q.grad, mod.query_norm.weight.grad.clone(), mod.ffn.fc2.bias.grad.clone()))
+    for a, b in zip(*res):
+        torch.testing.assert_close(a, b, rtol=3e-2, atol=3e-2 * float(b.abs().max()))

@@ -27,8 +27,15 @@ def main():
     ap.add_argument('--amp', type=int, default=1)
     ap.add_argument('--out', default='')
     ap.add_argument('--top', type=int, default=25)
+    ap.add_argument('--no-fold', action='store_true', help='autograd adds the residual gradient (no folding into the LayerNorm backward)')
+    ap.add_argument('--no-residual-kernel', action='store_true', help="torch's mixed-dtype add for the residual epilogues")
     args = ap.parse_args()
     dev = torch.device('cuda', 0)
+    from vit_adapter_b200.adapter import adapter_modules as am
+    if args.no_fold:
+        am.apply_norm_residual = lambda norm, x, fused=True: (am.apply_norm(norm, x, fused), x)
+    if args.no_residual_kernel:
+        am.residual_add = lambda res, branch, fused=True: res + branch
     d, heads, ratio = CFG[args.variant]
     blk = InteractionBlock(d, heads, 4, deform_ratio=ratio, cffn_ratio=0.25, init_values=0.0, extra_extractor=False).to(dev)
     with torch.no_grad():
@@ -45,7 +52,7 @@ def main():
     def step():
         with torch.autocast('cuda', dtype=torch.bfloat16, enabled=bool(args.amp)):
             xo, co = blk(x, c, [], di1, di2, h, h)
-        (xo.float().sum() + co.float().sum()).backward()
+        (xo.float().square().sum() + co.float().square().sum()).backward()   # a loss whose gradient is a real tensor, not an expanded scalar
     for _ in range(3):
         step()
     torch.cuda.synchronize()

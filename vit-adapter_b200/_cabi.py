@@ -26,7 +26,7 @@ EXPORTS = (
     'adapter_dwconv_forward', 'adapter_dwconv_backward_input', 'adapter_dwconv_backward_weight',
     'adapter_dwconv_backward_weight_workspace_bytes',
     'adapter_layernorm_forward', 'adapter_layernorm_backward', 'adapter_layernorm_backward_workspace_bytes',
-    'adapter_colsum', 'adapter_colsum_workspace_bytes',
+    'adapter_colsum', 'adapter_colsum_workspace_bytes', 'adapter_residual_add',
 )
 
 
@@ -94,8 +94,10 @@ def load():
         lib.adapter_colsum.restype = ctypes.c_int
         lib.adapter_colsum.argtypes = [ctypes.c_int, vp, i64, i32, vp, vp, ctypes.c_size_t, vp]
         lib.adapter_layernorm_backward.restype = ctypes.c_int
-        lib.adapter_layernorm_backward.argtypes = [ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp,
+        lib.adapter_layernorm_backward.argtypes = [ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp,
                                                    ctypes.c_size_t, vp]
+        lib.adapter_residual_add.restype = ctypes.c_int
+        lib.adapter_residual_add.argtypes = [ctypes.c_int, vp, vp, vp, i64, vp]
         lib.msda_debug_point_index.restype = ctypes.c_int
         lib.msda_debug_point_index.argtypes = [dp, i64p, i64p, vp, vp, vp]
         lib.msda_launch_count.restype = ctypes.c_uint64
@@ -489,10 +491,15 @@ def layernorm_forward(x, weight, bias, eps, out_dtype):
     return y, stats
 
 
-def layernorm_backward(grad_y, x, weight, stats):
-    """(grad_x in x.dtype, grad_weight fp32 [C], grad_bias fp32 [C])."""
+def layernorm_backward(grad_y, x, weight, stats, grad_residual=None):
+    """(grad_x in x.dtype, grad_weight fp32 [C], grad_bias fp32 [C]); grad_residual (x's shape and dtype, contiguous) is
+    added into grad_x."""
     lib = load()
     dev = _check_cuda(grad_y=grad_y, x=x, weight=weight)
+    if grad_residual is not None:
+        _check_cuda(grad_residual=grad_residual)
+        if grad_residual.dtype != x.dtype or grad_residual.shape != x.shape:
+            raise RuntimeError('layernorm_backward: grad_residual must have the shape and dtype of x')
     C = x.shape[-1]
     rows = x.numel() // C
     with torch.cuda.device(dev):
@@ -501,7 +508,9 @@ def layernorm_backward(grad_y, x, weight, stats):
         ws_bytes = lib.adapter_layernorm_backward_workspace_bytes(rows, C)
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
         rc = lib.adapter_layernorm_backward(_DTYPES[x.dtype], _DTYPES[grad_y.dtype], grad_y.data_ptr(), x.data_ptr(), weight.data_ptr(),
-                                            stats[0].data_ptr(), stats[1].data_ptr(), gx.data_ptr(), gwb[0].data_ptr(), gwb[1].data_ptr(),
+                                            stats[0].data_ptr(), stats[1].data_ptr(),
+                                            grad_residual.data_ptr() if grad_residual is not None else None,
+                                            gx.data_ptr(), gwb[0].data_ptr(), gwb[1].data_ptr(),
                                             rows, C, ws.data_ptr(), ws_bytes, _stream())
     if rc != 0:
         _raise(rc, 'adapter_layernorm_backward')
@@ -535,4 +544,23 @@ def colsum(x):
         rc = lib.adapter_colsum(code, x.data_ptr(), rows, C, out.data_ptr(), ws.data_ptr(), ws_bytes, _stream())
     if rc != 0:
         _raise(rc, 'adapter_colsum')
+    return out
+
+
+# --- residual epilogue ----------------------------------------------------------------------------------
+def residual_add_supported(res, branch):
+    return (res.is_cuda and branch.is_cuda and res.dtype == torch.float32 and branch.dtype in (torch.float32, torch.bfloat16)
+            and res.shape == branch.shape and res.is_contiguous() and branch.is_contiguous() and res.numel() > 0
+            and res.numel() % 8 == 0 and res.data_ptr() % 16 == 0 and branch.data_ptr() % 16 == 0)
+
+
+def residual_add(res, branch):
+    """fp32 res + (f32 | bf16) branch -> fp32, one pass with 16-byte accesses on every operand."""
+    lib = load()
+    dev = _check_cuda(res=res, branch=branch)
+    with torch.cuda.device(dev):
+        out = torch.empty_like(res)
+        rc = lib.adapter_residual_add(_DTYPES[branch.dtype], res.data_ptr(), branch.data_ptr(), out.data_ptr(), res.numel(), _stream())
+    if rc != 0:
+        _raise(rc, 'adapter_residual_add')
     return out

@@ -91,32 +91,78 @@ class _LayerNormRows(torch.autograd.Function):
     in the consumer's dtype, mean / rstd are kept for a backward that also reads x once."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, eps, out_dtype):
+    def forward(ctx, x, weight, bias, eps, out_dtype, with_residual):
         x = x.contiguous()
         y, stats = _cabi.layernorm_forward(x, weight, bias, eps, out_dtype)
         ctx.save_for_backward(x, weight, stats)
         ctx.has_bias = bias is not None
+        ctx.set_materialize_grads(False)
+        if with_residual:
+            # second output: x itself, for the residual connection around the normalised branch. Its gradient comes
+            # back into THIS node, where the backward kernel adds it to dx (one pass instead of LN backward + add).
+            return y, x.view_as(x)
         return y
 
     @staticmethod
     @torch.autograd.function.once_differentiable
-    def backward(ctx, grad_y):
+    def backward(ctx, grad_y, grad_res=None):
         x, weight, stats = ctx.saved_tensors
-        gx, gw, gb = _cabi.layernorm_backward(grad_y.contiguous(), x, weight, stats)
-        return gx, gw, (gb if ctx.has_bias else None), None, None
+        if grad_y is None:   # only the residual output was used
+            return grad_res, None, None, None, None, None
+        if grad_res is not None and (grad_res.dtype != x.dtype or not grad_res.is_contiguous()):
+            grad_res = grad_res.to(x.dtype).contiguous()
+        gx, gw, gb = _cabi.layernorm_backward(grad_y.contiguous(), x, weight, stats, grad_res)
+        return gx, gw, (gb if ctx.has_bias else None), None, None, None
+
+
+def _norm_kernel_dtype(norm, x, fused):
+    """Output dtype when the row kernel takes this LayerNorm call, else None."""
+    if fused and type(norm) is nn.LayerNorm and norm.elementwise_affine and len(norm.normalized_shape) == 1 and x.is_cuda:
+        out_dtype = torch.get_autocast_dtype('cuda') if torch.is_autocast_enabled('cuda') else x.dtype
+        if _cabi.layernorm_supported(x, norm.weight, norm.bias, out_dtype):
+            return out_dtype
+    return None
 
 
 def apply_norm(norm, x, fused=True):
     """`norm(x)` for the LayerNorms in front of the adapter's Linears (reference adapter_modules.py:110-116,142-145).
     A plain affine nn.LayerNorm on CUDA goes through the row kernel and, under bf16 autocast, hands the Linear a bf16
     tensor directly (torch would write fp32 and cast it again); anything else calls the module as the reference does."""
-    if fused and type(norm) is nn.LayerNorm and norm.elementwise_affine and len(norm.normalized_shape) == 1 and x.is_cuda:
-        out_dtype = x.dtype
-        if torch.is_autocast_enabled('cuda'):
-            out_dtype = torch.get_autocast_dtype('cuda')
-        if _cabi.layernorm_supported(x, norm.weight, norm.bias, out_dtype):
-            return _LayerNormRows.apply(x, norm.weight, norm.bias, norm.eps, out_dtype)
+    out_dtype = _norm_kernel_dtype(norm, x, fused)
+    if out_dtype is not None:
+        return _LayerNormRows.apply(x, norm.weight, norm.bias, norm.eps, out_dtype, False)
     return norm(x)
+
+
+def apply_norm_residual(norm, x, fused=True):
+    """(norm(x), x') for the pre-norm residual pattern `x + f(norm(x))` (reference adapter_modules.py:113-116, :145):
+    use x' (same values as x) for the residual connection. With the row kernel, the gradient of x' is folded into the
+    LayerNorm backward kernel instead of a separate full-tensor add by autograd."""
+    out_dtype = _norm_kernel_dtype(norm, x, fused)
+    if out_dtype is not None and torch.is_grad_enabled() and x.requires_grad:
+        return _LayerNormRows.apply(x, norm.weight, norm.bias, norm.eps, out_dtype, True)
+    return apply_norm(norm, x, fused), x
+
+
+class _ResidualAdd(torch.autograd.Function):
+    """fp32 stream + bf16 branch in one vectorised pass (csrc/adapter_residual.cu)."""
+
+    @staticmethod
+    def forward(ctx, res, branch):
+        ctx.branch_dtype = branch.dtype
+        return _cabi.residual_add(res, branch)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad):
+        return grad, (grad.to(ctx.branch_dtype) if ctx.needs_input_grad[1] else None)
+
+
+def residual_add(res, branch, fused=True):
+    """`res + branch` (reference adapter_modules.py:113-116); the mixed fp32 + bf16 case goes through the kernel."""
+    if fused and res.dtype != branch.dtype and _cabi.residual_add_supported(res, branch):
+        return _ResidualAdd.apply(res, branch)
+    return res + branch
 
 
 class _DWConvTokens(torch.autograd.Function):
@@ -205,10 +251,12 @@ class Extractor(nn.Module):
     def forward(self, query, reference_points, feat, spatial_shapes, level_start_index, H, W):
         def inner(query, feat):
             fn = self.fused_norm
-            query = query + self.attn(apply_norm(self.query_norm, query, fn), reference_points, apply_norm(self.feat_norm, feat, fn),
-                                      spatial_shapes, level_start_index, None)
+            normed, query = apply_norm_residual(self.query_norm, query, fn)
+            query = residual_add(query, self.attn(normed, reference_points, apply_norm(self.feat_norm, feat, fn),
+                                                  spatial_shapes, level_start_index, None), fn)
             if self.with_cffn:
-                query = query + self.drop_path(self.ffn(apply_norm(self.ffn_norm, query, fn), H, W))
+                normed, query = apply_norm_residual(self.ffn_norm, query, fn)
+                query = residual_add(query, self.drop_path(self.ffn(normed, H, W)), fn)
             return query
 
         if self.with_cp and query.requires_grad:
@@ -233,8 +281,9 @@ class Injector(nn.Module):
     def forward(self, query, reference_points, feat, spatial_shapes, level_start_index):
         def inner(query, feat):
             fn = self.fused_norm
-            attn = self.attn(apply_norm(self.query_norm, query, fn), reference_points, apply_norm(self.feat_norm, feat, fn),
-                             spatial_shapes, level_start_index, None)
+            normed, query = apply_norm_residual(self.query_norm, query, fn)
+            attn = self.attn(normed, reference_points, apply_norm(self.feat_norm, feat, fn), spatial_shapes,
+                             level_start_index, None)
             return query + self.gamma * attn
 
         if self.with_cp and query.requires_grad:

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'lib')
 LIBNAME = 'libmsda_b200.so'
-SOURCES = ['msda_fwd.cu', 'msda_fwd_smem.cu', 'msda_bwd.cu', 'adapter_dwconv.cu', 'adapter_layernorm.cu', 'adapter_colsum.cu', 'msda_abi.cu']
+SOURCES = ['msda_fwd.cu', 'msda_fwd_smem.cu', 'msda_bwd.cu', 'adapter_dwconv.cu', 'adapter_layernorm.cu', 'adapter_colsum.cu', 'adapter_residual.cu', 'msda_abi.cu']
 HEADERS = ['msda_common.cuh', os.path.join('..', '..', 'include', 'msda_b200.h')]
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',

@@ -13,7 +13,8 @@
 //   backward: xhat recomputed from the saved statistics, the two row sums (gamma*dy, gamma*dy*xhat) by warp shuffles,
 //             dx written in x's dtype; dgamma / dbeta accumulate per lane across the rows the warp walks, are reduced over
 //             the CTA's warps through shared memory, written as one partial row per CTA and summed in a fixed order by a
-//             second kernel (deterministic, no atomics).
+//             second kernel (deterministic, no atomics). When x also feeds a residual connection (query + f(LN(query))), the
+//             gradient arriving over that connection is added into dx here, which removes autograd's separate add pass.
 // Compulsory traffic: forward rows*C*(e_in + e_out); backward rows*C*(e_in + e_out + e_in).
 #include "msda_common.cuh"
 
@@ -32,6 +33,7 @@ struct LnParams {
   long long rows;
   int C;
   float eps;
+  const void* grad_res; // backward, optional: [rows, C] TI gradient of the residual branch that shares x, added into grad_x
 };
 
 constexpr int kLnWarps = 8;
@@ -42,6 +44,10 @@ template <> struct LnQuad<float> {
     const float4 q = __ldg(reinterpret_cast<const float4*>(p));
     v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
   }
+  static __device__ __forceinline__ void ld_shared(const float* p, float (&v)[4]) {
+    const float4 q = *reinterpret_cast<const float4*>(p);
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+  }
   static __device__ __forceinline__ void st(float* p, const float (&v)[4]) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   }
@@ -49,6 +55,11 @@ template <> struct LnQuad<float> {
 template <> struct LnQuad<__nv_bfloat16> {
   static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float (&v)[4]) {
     const uint2 q = __ldg(reinterpret_cast<const uint2*>(p));
+    v[0] = __uint_as_float(q.x << 16); v[1] = __uint_as_float(q.x & 0xffff0000u);
+    v[2] = __uint_as_float(q.y << 16); v[3] = __uint_as_float(q.y & 0xffff0000u);
+  }
+  static __device__ __forceinline__ void ld_shared(const __nv_bfloat16* p, float (&v)[4]) {
+    const uint2 q = *reinterpret_cast<const uint2*>(p);
     v[0] = __uint_as_float(q.x << 16); v[1] = __uint_as_float(q.x & 0xffff0000u);
     v[2] = __uint_as_float(q.y << 16); v[3] = __uint_as_float(q.y & 0xffff0000u);
   }
@@ -124,11 +135,17 @@ __global__ void __launch_bounds__(kLnWarps * 32, 2) adapter_ln_fwd_kernel(const 
 
 template <typename TI, typename TO, int VPL>
 __global__ void __launch_bounds__(kLnWarps * 32, (VPL <= 6 ? 2 : 1)) adapter_ln_bwd_kernel(const LnParams p) {
-  __shared__ float red[kLnWarps / 2][2 * VPL * 128];  // tree reduction over the warps: at most 4 rows of (dgamma | dbeta)
+  // one buffer, two lives: while rows are walked, warp w stages the residual-gradient row it will need at the store
+  // (cp.async: bytes in flight that cost no registers) in its VPL*512-byte slice; afterwards the same memory is the
+  // tree reduction over the warps (at most 4 rows of dgamma | dbeta)
+  __shared__ __align__(16) float ln_smem[kLnWarps / 2 * 2 * VPL * 128];
+  float (*red)[2 * VPL * 128] = reinterpret_cast<float (*)[2 * VPL * 128]>(ln_smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  TI* stage = reinterpret_cast<TI*>(ln_smem + warp * VPL * 128);
   const TI* __restrict__ x = reinterpret_cast<const TI*>(p.x);
   const TO* __restrict__ dy = reinterpret_cast<const TO*>(p.grad_y);
   TI* __restrict__ dx = reinterpret_cast<TI*>(p.grad_x);
+  const TI* __restrict__ gres = reinterpret_cast<const TI*>(p.grad_res);
   const float* __restrict__ gamma = reinterpret_cast<const float*>(p.gamma);
   bool ok[VPL];
   float dg[VPL][4], db[VPL][4];  // gamma is re-read per row (L1-resident): 4*VPL registers matter more here
@@ -152,6 +169,17 @@ __global__ void __launch_bounds__(kLnWarps * 32, (VPL <= 6 ? 2 : 1)) adapter_ln_
         LnQuad<TO>::ld(dyr + (i * 32 + lane) * 4, gy[i]);
       }
     }
+    if (gres) {  // the residual gradient is only needed at the store: start it towards shared memory now
+#pragma unroll
+      for (int i = 0; i < VPL; ++i)
+        if (ok[i]) {
+          const unsigned dst = (unsigned)__cvta_generic_to_shared(stage + (i * 32 + lane) * 4);
+          const TI* src = gres + row * p.C + (i * 32 + lane) * 4;
+          if constexpr (sizeof(TI) == 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+          else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+        }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     const float mean = p.mean[row], rstd = p.rstd[row];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -174,15 +202,23 @@ __global__ void __launch_bounds__(kLnWarps * 32, (VPL <= 6 ? 2 : 1)) adapter_ln_
     s1 = warp_sum(s1) * inv_c;
     s2 = warp_sum(s2) * inv_c;
     TI* dxr = dx + row * p.C;
+    if (gres) asm volatile("cp.async.wait_group 0;" ::: "memory");  // each lane reads back only what it copied itself
 #pragma unroll
     for (int i = 0; i < VPL; ++i)
       if (ok[i]) {
         float o[4];
 #pragma unroll
         for (int v = 0; v < 4; ++v) o[v] = (gy[i][v] - fmaf(xh[i][v], s2, s1)) * rstd;
+        if (gres) {  // x also feeds a residual connection: fold that branch's gradient in here instead of a separate add pass
+          float r[4];
+          LnQuad<TI>::ld_shared(stage + (i * 32 + lane) * 4, r);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) o[v] += r[v];
+        }
         LnQuad<TI>::st(dxr + (i * 32 + lane) * 4, o);
       }
   }
+  __syncthreads();  // every warp is done with its staging slice before the buffer becomes the reduction tree
   // tree over the 8 warps: upper half writes, lower half adds, in a fixed order
 #pragma unroll
   for (int half = kLnWarps / 2; half > 0; half >>= 1) {

@@ -42,7 +42,9 @@ struct LnParams {
   long long rows;
   int C;
   float eps;
+  const void* grad_res;
 };
+cudaError_t launch_residual_add(int branch_dtype, const float* res, const void* branch, float* out, long long n, cudaStream_t s);
 bool layernorm_supported(int C);
 size_t layernorm_backward_workspace_bytes(long long rows, int C);
 cudaError_t launch_layernorm_forward(const LnParams& p, int in_dtype, int out_dtype, cudaStream_t s);
@@ -554,22 +556,38 @@ size_t adapter_layernorm_backward_workspace_bytes(int64_t rows, int32_t channels
 }
 
 int adapter_layernorm_backward(int in_dtype, int out_dtype, const void* grad_y, const void* x, const void* gamma,
-                               const float* mean, const float* rstd, void* grad_x, float* grad_gamma, float* grad_beta,
-                               int64_t rows, int32_t channels, void* workspace, size_t workspace_bytes, void* stream) {
+                               const float* mean, const float* rstd, const void* grad_residual, void* grad_x,
+                               float* grad_gamma, float* grad_beta, int64_t rows, int32_t channels, void* workspace,
+                               size_t workspace_bytes, void* stream) {
   if (int e = ln_check("adapter_layernorm_backward", in_dtype, out_dtype, rows, channels)) return e;
   if (!grad_y || !x || !gamma || !mean || !rstd || !grad_x || !grad_gamma || !grad_beta)
     return fail(MSDA_E_NULL, "adapter_layernorm_backward: NULL tensor pointer");
-  if (ln_misaligned(x, in_dtype) || ln_misaligned(grad_x, in_dtype) || ln_misaligned(grad_y, out_dtype) || ln_misaligned(gamma, MSDA_F32))
-    return fail(MSDA_E_ALIGN, "adapter_layernorm_backward: x, grad_x, grad_y, gamma must be aligned to 4 elements");
+  if (ln_misaligned(x, in_dtype) || ln_misaligned(grad_x, in_dtype) || ln_misaligned(grad_y, out_dtype) || ln_misaligned(gamma, MSDA_F32) ||
+      (grad_residual && ln_misaligned(grad_residual, in_dtype)))
+    return fail(MSDA_E_ALIGN, "adapter_layernorm_backward: x, grad_x, grad_y, grad_residual, gamma must be aligned to 4 elements");
   const size_t need = layernorm_backward_workspace_bytes((long long)rows, channels);
   if (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 15))
     return fail(MSDA_E_WORKSPACE, "adapter_layernorm_backward: 16-byte aligned workspace of %zu bytes required, got %zu", need,
                 workspace ? workspace_bytes : (size_t)0);
   LnParams p{x, gamma, nullptr, nullptr, const_cast<float*>(mean), const_cast<float*>(rstd), grad_y, grad_x,
-             reinterpret_cast<float*>(workspace), (long long)rows, channels, 0.f};
+             reinterpret_cast<float*>(workspace), (long long)rows, channels, 0.f, grad_residual};
   const cudaError_t e = launch_layernorm_backward(p, in_dtype, out_dtype, grad_gamma, grad_beta, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "adapter_layernorm_backward launch");
   g_launches.fetch_add(2);
+  return 0;
+}
+
+int adapter_residual_add(int branch_dtype, const float* residual, const void* branch, float* out, int64_t n, void* stream) {
+  if (branch_dtype != MSDA_F32 && branch_dtype != MSDA_BF16)
+    return fail(MSDA_E_DTYPE, "adapter_residual_add: branch must be f32 or bf16, got %d", branch_dtype);
+  if (n <= 0 || n >= (1ll << 40)) return fail(MSDA_E_DIMS, "adapter_residual_add: bad element count %lld", (long long)n);
+  if (n % 8) return fail(MSDA_E_UNSUPPORTED, "adapter_residual_add: element count %lld is not a multiple of 8", (long long)n);
+  if (!residual || !branch || !out) return fail(MSDA_E_NULL, "adapter_residual_add: NULL tensor pointer");
+  if ((reinterpret_cast<uintptr_t>(residual) | reinterpret_cast<uintptr_t>(branch) | reinterpret_cast<uintptr_t>(out)) & 15)
+    return fail(MSDA_E_ALIGN, "adapter_residual_add: pointers must be 16-byte aligned");
+  const cudaError_t e = launch_residual_add(branch_dtype, residual, branch, out, (long long)n, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "adapter_residual_add launch");
+  g_launches.fetch_add(1);
   return 0;
 }
 
