@@ -12,3 +12,11 @@ ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpuru
 python tools/profile_step.py > gpurun_out/plain.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:msda_ -s 8 -c 4 -o gpurun_out/prof python tools/profile_step.py > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out
+python tools/profile_adapter_kernels.py > gpurun_out/plain_adapter.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:adapter_ -s 20 -c 10 -o gpurun_out/prof_adapter python tools/profile_adapter_kernels.py > gpurun_out/ncu_adapter.log 2>&1
+python tools/profile_block.py --batch 16 --amp 1 --top 30 --out gpurun_out/block_profile_b16_bf16.json > gpurun_out/block_profile_b16_bf16.txt 2>&1
+python tools/profile_block.py --batch 2 --amp 1 --top 30 --out gpurun_out/block_profile_b2_bf16.json > gpurun_out/block_profile_b2_bf16.txt 2>&1
+python tools/bench_layernorm.py > gpurun_out/layernorm_kernels.jsonl 2> gpurun_out/adapter_bench.err
+python tools/bench_dwconv.py --kernels > gpurun_out/dwconv_kernels.jsonl 2>> gpurun_out/adapter_bench.err
+python tools/bench_dwconv.py > gpurun_out/dwconv_bench.jsonl 2>> gpurun_out/adapter_bench.err
+ls -la gpurun_out
