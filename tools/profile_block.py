@@ -27,6 +27,7 @@ def main():
     ap.add_argument('--amp', type=int, default=1)
     ap.add_argument('--out', default='')
     ap.add_argument('--top', type=int, default=25)
+    ap.add_argument('--reference-sequence', action='store_true', help="every adapter-side kernel off: torch LayerNorm, DWConv op sequence, separate linears + softmax, nn.Linear backward, torch adds (the sampling core stays this repo's)")
     ap.add_argument('--no-fold', action='store_true', help='autograd adds the residual gradient (no folding into the LayerNorm backward)')
     ap.add_argument('--no-residual-kernel', action='store_true', help="torch's mixed-dtype add for the residual epilogues")
     args = ap.parse_args()
@@ -41,6 +42,11 @@ def main():
     with torch.no_grad():
         for p in blk.parameters():
             p.add_(torch.randn_like(p) * 0.02)
+    if args.reference_sequence:
+        for m in blk.modules():
+            for flag in ('fused_norm', 'token_kernel', 'fused', 'merge_query_linears', 'colsum_bias_grad'):
+                if hasattr(m, flag):
+                    setattr(m, flag, False)
     if args.amp:
         vab.set_amp_value_dtype(torch.bfloat16)
     img = torch.zeros(args.batch, 3, args.image, args.image, device=dev)

@@ -155,8 +155,26 @@ def _check_meta(spatial_shapes, level_start_index):
         raise RuntimeError('spatial_shapes / level_start_index must be int64 (as in the reference)')
 
 
+class _NoSwitch:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_SWITCH = _NoSwitch()
+
+
+def _on(dev):
+    """Device guard for allocation + launch; free when `dev` is already current (torch.cuda.device() costs ~10 us a call)."""
+    return _NO_SWITCH if dev.index == torch.cuda.current_device() else torch.cuda.device(dev)
+
+
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # the raw handle of torch's current stream on the current device; torch.cuda.current_stream() builds a Stream
+    # object and costs ~18 us a call, which at 2 images per GPU was 15% of an adapter interaction's host time
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
 
 
 class TensorMemo:
@@ -212,7 +230,7 @@ def forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
     rc = lib.msda_check_im2col_step(dims.batch, int(im2col_step))
     if rc != 0:
         _raise(rc, 'ms_deform_attn_forward')
-    with torch.cuda.device(dev):
+    with _on(dev):
         out = torch.empty((dims.batch, dims.num_query, dims.num_heads * dims.channels),
                           dtype=value.dtype, device=dev)
         hs = host_shapes(spatial_shapes) if _WANT_HOST_SHAPES else None
@@ -238,7 +256,7 @@ def backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight
     rc = lib.msda_check_im2col_step(dims.batch, int(im2col_step))
     if rc != 0:
         _raise(rc, 'ms_deform_attn_backward')
-    with torch.cuda.device(dev):
+    with _on(dev):
         grad_value = torch.empty_like(value)
         grad_loc = torch.empty_like(sampling_loc)
         grad_aw = torch.empty_like(attn_weight)
@@ -288,7 +306,7 @@ def forward_fused(value, spatial_shapes, level_start_index, reference_points, sa
     _check_meta(spatial_shapes, level_start_index)
     dims, rb, rl = _fused_dims(value, reference_points, sampling_offsets, attn_logits)
     code = _DTYPES.get(value.dtype)
-    with torch.cuda.device(dev):
+    with _on(dev):
         out = torch.empty((dims.batch, dims.num_query, dims.num_heads * dims.channels), dtype=value.dtype, device=dev)
         rc = lib.msda_forward_fused(ctypes.byref(dims), code, value.data_ptr(), spatial_shapes.data_ptr(),
                                     level_start_index.data_ptr(), reference_points.data_ptr(), rb, rl,
@@ -317,7 +335,7 @@ def forward_fused_merged(value, spatial_shapes, level_start_index, reference_poi
     _check_meta(spatial_shapes, level_start_index)
     dims, rb, rl, width = _merged_dims(value, reference_points, merged, n_levels, n_points)
     code = _DTYPES.get(value.dtype)
-    with torch.cuda.device(dev):
+    with _on(dev):
         out = torch.empty((dims.batch, dims.num_query, dims.num_heads * dims.channels), dtype=value.dtype, device=dev)
         rc = lib.msda_forward_fused(ctypes.byref(dims), code, value.data_ptr(), spatial_shapes.data_ptr(),
                                     level_start_index.data_ptr(), reference_points.data_ptr(), rb, rl,
@@ -337,7 +355,7 @@ def backward_fused_merged(value, spatial_shapes, level_start_index, reference_po
     code = _DTYPES.get(value.dtype)
     if grad_output.dtype != value.dtype:
         raise RuntimeError('grad_output dtype %s != value dtype %s' % (grad_output.dtype, value.dtype))
-    with torch.cuda.device(dev):
+    with _on(dev):
         grad_value = torch.empty_like(value)
         grad_merged = torch.empty_like(merged)
         ws_bytes = lib.msda_backward_workspace_bytes(ctypes.byref(dims), code)
@@ -364,7 +382,7 @@ def backward_fused(value, spatial_shapes, level_start_index, reference_points, s
     code = _DTYPES.get(value.dtype)
     if grad_output.dtype != value.dtype:
         raise RuntimeError('grad_output dtype %s != value dtype %s' % (grad_output.dtype, value.dtype))
-    with torch.cuda.device(dev):
+    with _on(dev):
         grad_value = torch.empty_like(value)
         grad_off = torch.empty_like(sampling_offsets)
         grad_logits = torch.empty_like(attn_logits)
@@ -390,7 +408,7 @@ def dwconv_forward(x, weight, bias, H, W):
     lib = load()
     dev = _check_cuda(x=x, weight=weight) if bias is None else _check_cuda(x=x, weight=weight, bias=bias)
     B, n, C = x.shape
-    with torch.cuda.device(dev):
+    with _on(dev):
         y = torch.empty_like(x)
         rc = lib.adapter_dwconv_forward(_DTYPES[x.dtype], x.data_ptr(), weight.data_ptr(),
                                         bias.data_ptr() if bias is not None else None, y.data_ptr(), B, n, C, H, W, _stream())
@@ -406,7 +424,7 @@ def dwconv_backward(x, weight, grad_y, H, W, need_input=True, need_weight=True):
     B, n, C = x.shape
     code = _DTYPES[x.dtype]
     gx = gw = gb = None
-    with torch.cuda.device(dev):
+    with _on(dev):
         if need_input:
             gx = torch.empty_like(x)
             rc = lib.adapter_dwconv_backward_input(code, grad_y.data_ptr(), weight.data_ptr(), gx.data_ptr(), B, n, C, H, W, _stream())
@@ -437,7 +455,7 @@ def debug_point_index(spatial_shapes, level_start_index, sampling_loc, num_heads
         raise RuntimeError('debug_point_index: float32 sampling_loc [N,Lq,M,L,P,2] expected')
     S = int((spatial_shapes[:, 0] * spatial_shapes[:, 1]).sum().item())
     dims = MsdaDims(N, S, M, channels, L, Lq, P)
-    with torch.cuda.device(dev):
+    with _on(dev):
         idx = torch.empty((N * Lq * M * L * P, 4), dtype=torch.int32, device=dev)
         rc = lib.msda_debug_point_index(ctypes.byref(dims), spatial_shapes.data_ptr(),
                                         level_start_index.data_ptr(), sampling_loc.data_ptr(),
@@ -480,7 +498,7 @@ def layernorm_forward(x, weight, bias, eps, out_dtype):
     dev = _check_cuda(x=x, weight=weight) if bias is None else _check_cuda(x=x, weight=weight, bias=bias)
     C = x.shape[-1]
     rows = x.numel() // C
-    with torch.cuda.device(dev):
+    with _on(dev):
         y = torch.empty(x.shape, dtype=out_dtype, device=dev)
         stats = torch.empty((2, rows), dtype=torch.float32, device=dev)
         rc = lib.adapter_layernorm_forward(_DTYPES[x.dtype], _DTYPES[out_dtype], x.data_ptr(), weight.data_ptr(),
@@ -502,7 +520,7 @@ def layernorm_backward(grad_y, x, weight, stats, grad_residual=None):
             raise RuntimeError('layernorm_backward: grad_residual must have the shape and dtype of x')
     C = x.shape[-1]
     rows = x.numel() // C
-    with torch.cuda.device(dev):
+    with _on(dev):
         gx = torch.empty_like(x)
         gwb = torch.empty((2, C), dtype=torch.float32, device=dev)
         ws_bytes = lib.adapter_layernorm_backward_workspace_bytes(rows, C)
@@ -537,7 +555,7 @@ def colsum(x):
     C = x.shape[-1]
     rows = x.numel() // C
     code = _DTYPES[x.dtype]
-    with torch.cuda.device(dev):
+    with _on(dev):
         out = torch.empty((C,), dtype=torch.float32, device=dev)
         ws_bytes = lib.adapter_colsum_workspace_bytes(code, rows, C)
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
@@ -558,7 +576,7 @@ def residual_add(res, branch):
     """fp32 res + (f32 | bf16) branch -> fp32, one pass with 16-byte accesses on every operand."""
     lib = load()
     dev = _check_cuda(res=res, branch=branch)
-    with torch.cuda.device(dev):
+    with _on(dev):
         out = torch.empty_like(res)
         rc = lib.adapter_residual_add(_DTYPES[branch.dtype], res.data_ptr(), branch.data_ptr(), out.data_ptr(), res.numel(), _stream())
     if rc != 0:

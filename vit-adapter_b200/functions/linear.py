@@ -20,8 +20,7 @@ class _LinearColsumBias(torch.autograd.Function):
         xc = x if x.dtype == dt else x.to(dt)
         wc = weight if weight.dtype == dt else weight.to(dt)
         bc = bias if bias.dtype == dt else bias.to(dt)
-        with torch.autocast('cuda', enabled=False):
-            y = F.linear(xc, wc, bc)
+        y = F.linear(xc, wc, bc)   # operands already share the compute dtype: autocast, if on, has nothing left to cast
         ctx.save_for_backward(xc, wc)
         return y
 
@@ -33,11 +32,12 @@ class _LinearColsumBias(torch.autograd.Function):
         if not gy2.is_contiguous():
             gy2 = gy2.contiguous()
         gx = gw = gb = None
-        with torch.autocast('cuda', enabled=False):
-            if ctx.needs_input_grad[0]:
-                gx = (gy2 @ wc).view(xc.shape)
-            if ctx.needs_input_grad[1]:
-                gw = gy2.t() @ xc.reshape(-1, xc.shape[-1])
+        if gy2.dtype != wc.dtype:
+            gy2 = gy2.to(wc.dtype)
+        if ctx.needs_input_grad[0]:
+            gx = (gy2 @ wc).view(xc.shape)
+        if ctx.needs_input_grad[1]:
+            gw = gy2.t() @ xc.reshape(-1, xc.shape[-1])
         if ctx.needs_input_grad[2]:
             gb = _cabi.colsum(gy2) if _cabi.colsum_supported(gy2) else gy2.sum(0)
         return gx, gw, gb
