@@ -278,13 +278,20 @@ class Injector(nn.Module):
         self.gamma = nn.Parameter(init_values * torch.ones((dim)), requires_grad=True)
         self.fused_norm = True
 
-    def forward(self, query, reference_points, feat, spatial_shapes, level_start_index):
+    def forward(self, query, reference_points, feat, spatial_shapes, level_start_index, return_feat=False):
+        """Same as the reference; with return_feat=True also returns `feat` as handed out by its LayerNorm node
+        (same values): a caller that goes on using feat (InteractionBlock feeds c to the Extractor next) should use
+        that one, so the gradient of the later use is added inside the LayerNorm backward kernel."""
         def inner(query, feat):
             fn = self.fused_norm
             normed, query = apply_norm_residual(self.query_norm, query, fn)
-            attn = self.attn(normed, reference_points, apply_norm(self.feat_norm, feat, fn), spatial_shapes,
-                             level_start_index, None)
-            return query + self.gamma * attn
+            if return_feat:
+                normed_feat, feat = apply_norm_residual(self.feat_norm, feat, fn)
+            else:
+                normed_feat = apply_norm(self.feat_norm, feat, fn)
+            attn = self.attn(normed, reference_points, normed_feat, spatial_shapes, level_start_index, None)
+            out = query + self.gamma * attn
+            return (out, feat) if return_feat else out
 
         if self.with_cp and query.requires_grad:
             return cp.checkpoint(inner, query, feat, use_reentrant=True)
@@ -304,8 +311,9 @@ class _InteractionBase(nn.Module):
         self.extra_extractors = nn.Sequential(*[Extractor(**ext) for _ in range(2)]) if extra_extractor else None
 
     def _inject(self, x, c, deform_inputs1):
+        """(x after injection, c to keep using): c comes back through the injector's feat_norm node (see Injector.forward)."""
         return self.injector(query=x, reference_points=deform_inputs1[0], feat=c, spatial_shapes=deform_inputs1[1],
-                             level_start_index=deform_inputs1[2])
+                             level_start_index=deform_inputs1[2], return_feat=True)
 
     def _extract(self, x, c, deform_inputs2, H, W):
         extractors = [self.extractor] + (list(self.extra_extractors) if self.extra_extractors is not None else [])
@@ -320,7 +328,7 @@ class InteractionBlock(_InteractionBase):
     reference adapter_modules.py:155-191."""
 
     def forward(self, x, c, blocks, deform_inputs1, deform_inputs2, H, W):
-        x = self._inject(x, c, deform_inputs1)
+        x, c = self._inject(x, c, deform_inputs1)
         for blk in blocks:
             x = blk(x, H, W)
         return x, self._extract(x, c, deform_inputs2, H, W)
@@ -330,7 +338,7 @@ class InteractionBlockWithCls(_InteractionBase):
     """Same, with BEiT's class token re-attached around the ViT blocks (segmentation copy :194-234)."""
 
     def forward(self, x, c, cls, blocks, deform_inputs1, deform_inputs2, H, W):
-        x = self._inject(x, c, deform_inputs1)
+        x, c = self._inject(x, c, deform_inputs1)
         x = torch.cat((cls, x), dim=1)
         for blk in blocks:
             x = blk(x, H, W)

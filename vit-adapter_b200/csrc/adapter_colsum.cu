@@ -63,18 +63,28 @@ __global__ void __launch_bounds__(256) adapter_colsum_kernel(const T* __restrict
   }
 }
 
-__global__ void __launch_bounds__(256) adapter_colsum_final_kernel(const float* __restrict__ partial, int prow, int C,
-                                                                   float* __restrict__ out) {
-  __shared__ float red[8][32];
+// second stage: 32 columns x 32 row slices per CTA, four independent partial sums per thread (latency, not bytes, is the cost)
+__global__ void __launch_bounds__(1024) adapter_colsum_final_kernel(const float* __restrict__ partial, int prow, int C,
+                                                                    float* __restrict__ out) {
+  __shared__ float red[32][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
-  float t = 0.f;
-  if (c < C)
-    for (int r = threadIdx.y; r < prow; r += 8) t += partial[(size_t)r * C + c];
-  red[threadIdx.y][threadIdx.x] = t;
+  float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+  if (c < C) {
+    int r = threadIdx.y;
+    for (; r + 96 < prow; r += 128) {
+      t0 += partial[(size_t)r * C + c];
+      t1 += partial[(size_t)(r + 32) * C + c];
+      t2 += partial[(size_t)(r + 64) * C + c];
+      t3 += partial[(size_t)(r + 96) * C + c];
+    }
+    for (; r < prow; r += 32) t0 += partial[(size_t)r * C + c];
+  }
+  red[threadIdx.y][threadIdx.x] = (t0 + t1) + (t2 + t3);
   __syncthreads();
   if (threadIdx.y == 0 && c < C) {
+    float t = 0.f;
 #pragma unroll
-    for (int yy = 1; yy < 8; ++yy) t += red[yy][threadIdx.x];
+    for (int yy = 0; yy < 32; ++yy) t += red[yy][threadIdx.x];
     out[c] = t;
   }
 }
@@ -107,7 +117,7 @@ cudaError_t launch_colsum(int dtype, const void* x, long long rows, int C, float
     adapter_colsum_kernel<__nv_bfloat16><<<grid, cg * rs, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), rows, C, cg, rs, partial);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  adapter_colsum_final_kernel<<<(C + 31) / 32, dim3(32, 8), 0, s>>>(partial, (int)grid, C, out);
+  adapter_colsum_final_kernel<<<(C + 31) / 32, dim3(32, 32), 0, s>>>(partial, (int)grid, C, out);
   return cudaGetLastError();
 }
 

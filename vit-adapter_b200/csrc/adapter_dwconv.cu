@@ -387,20 +387,30 @@ __global__ void __launch_bounds__(256, 2) adapter_dwconv_wgrad_run_kernel(const 
   }
 }
 
-// second stage: sum the per-CTA partial rows; i = (tap * 4 + v) * cvec + cv -> grad_weight[(cv*4+v)*9 + tap] / grad_bias
-__global__ void __launch_bounds__(256) adapter_dwconv_wgrad_sum_kernel(const float* __restrict__ partial, int rows, int cvec,
-                                                                       float* __restrict__ gw, float* __restrict__ gb) {
-  __shared__ float red[8][32];
+// second stage: sum the per-CTA partial rows; i = (tap * 4 + v) * cvec + cv -> grad_weight[(cv*4+v)*9 + tap] / grad_bias.
+// block = (32 columns, 32 row slices), four independent partial sums per thread
+__global__ void __launch_bounds__(1024) adapter_dwconv_wgrad_sum_kernel(const float* __restrict__ partial, int rows, int cvec,
+                                                                        float* __restrict__ gw, float* __restrict__ gb) {
+  __shared__ float red[32][33];
   const int i = blockIdx.x * 32 + threadIdx.x;
   const int n = 40 * cvec;
-  float tot = 0.f;
-  if (i < n)
-    for (int r = threadIdx.y; r < rows; r += 8) tot += partial[(size_t)r * n + i];
-  red[threadIdx.y][threadIdx.x] = tot;
+  float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+  if (i < n) {
+    int r = threadIdx.y;
+    for (; r + 96 < rows; r += 128) {
+      t0 += partial[(size_t)r * n + i];
+      t1 += partial[(size_t)(r + 32) * n + i];
+      t2 += partial[(size_t)(r + 64) * n + i];
+      t3 += partial[(size_t)(r + 96) * n + i];
+    }
+    for (; r < rows; r += 32) t0 += partial[(size_t)r * n + i];
+  }
+  red[threadIdx.y][threadIdx.x] = (t0 + t1) + (t2 + t3);
   __syncthreads();
   if (threadIdx.y == 0 && i < n) {
+    float tot = 0.f;
 #pragma unroll
-    for (int yy = 1; yy < 8; ++yy) tot += red[yy][threadIdx.x];
+    for (int yy = 0; yy < 32; ++yy) tot += red[yy][threadIdx.x];
     const int kv = i / cvec, cvi = i - kv * cvec;
     const int k = kv >> 2, ch = cvi * 4 + (kv & 3);
     if (k < 9) gw[ch * 9 + k] = tot; else gb[ch] = tot;
@@ -487,7 +497,7 @@ cudaError_t launch_dwconv_wgrad(const DwParams& p, int dtype, const void* grad_y
         adapter_dwconv_wgrad_run_kernel<__nv_bfloat16><<<grid, cvec * ty_count, smem, s>>>(p, g, grad_y, partial, cvec, ty_count);
       cudaError_t e2 = cudaGetLastError();
       if (e2 != cudaSuccess) return e2;
-      adapter_dwconv_wgrad_sum_kernel<<<(40 * cvec + 31) / 32, dim3(32, 8), 0, s>>>(partial, (int)grid, cvec, (float*)gw, (float*)gb);
+      adapter_dwconv_wgrad_sum_kernel<<<(40 * cvec + 31) / 32, dim3(32, 32), 0, s>>>(partial, (int)grid, cvec, (float*)gw, (float*)gb);
       *launches = 2;
       return cudaGetLastError();
     }

@@ -254,20 +254,31 @@ __global__ void __launch_bounds__(kLnWarps * 32, (VPL <= 6 ? 2 : 1)) adapter_ln_
   }
 }
 
-// dgamma[c] = sum_r partial[r][0][c], dbeta[c] = sum_r partial[r][1][c]; block = (32 columns, 8 row slices)
-__global__ void __launch_bounds__(256) adapter_ln_param_grad_kernel(const float* __restrict__ partial, int rows, int C,
-                                                                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  __shared__ float red[8][32];
+// dgamma[c] = sum_r partial[r][0][c], dbeta[c] = sum_r partial[r][1][c]; block = (32 columns, 32 row slices), four
+// independent partial sums per thread
+__global__ void __launch_bounds__(1024) adapter_ln_param_grad_kernel(const float* __restrict__ partial, int rows, int C,
+                                                                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float red[32][33];
   const int i = blockIdx.x * 32 + threadIdx.x;  // column of the [2*C] partial row
-  float tot = 0.f;
-  if (i < 2 * C)
-    for (int r = threadIdx.y; r < rows; r += 8) tot += partial[(size_t)r * 2 * C + i];
-  red[threadIdx.y][threadIdx.x] = tot;
+  const int n = 2 * C;
+  float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+  if (i < n) {
+    int r = threadIdx.y;
+    for (; r + 96 < rows; r += 128) {
+      t0 += partial[(size_t)r * n + i];
+      t1 += partial[(size_t)(r + 32) * n + i];
+      t2 += partial[(size_t)(r + 64) * n + i];
+      t3 += partial[(size_t)(r + 96) * n + i];
+    }
+    for (; r < rows; r += 32) t0 += partial[(size_t)r * n + i];
+  }
+  red[threadIdx.y][threadIdx.x] = (t0 + t1) + (t2 + t3);
   __syncthreads();
-  if (threadIdx.y == 0 && i < 2 * C) {
+  if (threadIdx.y == 0 && i < n) {
+    float t = 0.f;
 #pragma unroll
-    for (int yy = 1; yy < 8; ++yy) tot += red[yy][threadIdx.x];
-    if (i < C) dgamma[i] = tot; else dbeta[i - C] = tot;
+    for (int yy = 0; yy < 32; ++yy) t += red[yy][threadIdx.x];
+    if (i < C) dgamma[i] = t; else dbeta[i - C] = t;
   }
 }
 
@@ -314,7 +325,7 @@ cudaError_t launch_layernorm_forward(const LnParams& p, int in_dtype, int out_dt
 cudaError_t launch_layernorm_backward(const LnParams& p, int in_dtype, int out_dtype, float* dgamma, float* dbeta, cudaStream_t s) {
   cudaError_t e = ln_dispatch<true>(p, in_dtype, out_dtype, s);
   if (e != cudaSuccess) return e;
-  adapter_ln_param_grad_kernel<<<(2 * p.C + 31) / 32, dim3(32, 8), 0, s>>>(p.partial, (int)ln_grid(p.rows), p.C, dgamma, dbeta);
+  adapter_ln_param_grad_kernel<<<(2 * p.C + 31) / 32, dim3(32, 32), 0, s>>>(p.partial, (int)ln_grid(p.rows), p.C, dgamma, dbeta);
   return cudaGetLastError();
 }
 
