@@ -180,10 +180,16 @@ def main():
     ap.add_argument('--reference-sequence', action='store_true',
                     help="the adapter exactly as the reference runs it: reference CUDA core, torch LayerNorm, the DWConv "
                          "slice/transpose/conv2d sequence, separate offset/weight linears + softmax (implies --op ref_cuda)")
+    ap.add_argument('--tf32', action='store_true',
+                    help='fp32 GEMMs / convolutions on TF32 tensor cores - the default of the torch 1.9.0 the reference pins '
+                         '(segmentation/README.md:24); off by default in the torch of this image')
     ap.add_argument('--graph', action='store_true',
                     help='capture the whole step (forward, backward, optimizer) in ONE CUDA graph and replay it (single GPU)')
     args = ap.parse_args()
 
+    if args.tf32:
+        torch.backends.cuda.matmul.allow_tf32 = True
+        torch.backends.cudnn.allow_tf32 = True
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -295,7 +301,7 @@ def main():
             'unit': 'img/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'dtype': 'bf16-autocast' if args.amp else 'f32', 'data': 'synthetic',
             'op': args.op, 'adapter': 'reference op sequence' if args.reference_sequence else 'this repo (fused norm / dwconv / softmax+locations)',
-            'msda_kernel_launches': launches, 'cuda_graph': bool(use_graph),
+            'msda_kernel_launches': launches, 'cuda_graph': bool(use_graph), 'tf32_gemm': bool(args.tf32),
             'config': {'workload': 'ViT-Adapter-%s backbone (this repo\'s adapter modules + MSDeformAttn) + stand-in head, %dx%d, '
                                    '%d img/GPU, %s' % (args.variant, args.image, args.image, args.batch, args.mode),
                        'params_total': n_params, 'params_adapter': n_adapter, 'with_cp': args.with_cp,

@@ -8,6 +8,9 @@ for amp in "" "--amp"; do
   run $amp
   run $amp --graph
 done
+run --tf32 --reference-sequence
+run --tf32
+run --tf32 --graph
 run --variant L --image 896 --batch 1 --amp --with-cp --reference-sequence
 run --variant L --image 896 --batch 1 --amp --with-cp
 run --variant L --image 1024 --batch 1 --mode infer --reference-sequence
@@ -19,6 +22,6 @@ python - <<'PY'
 import json
 for l in open('gpurun_out/step_matrix.jsonl'):
     d = json.loads(l)
-    print(d['metric'], d['dtype'], d['op'], d['adapter'][:9], 'graph' if d['cuda_graph'] else 'eager', round(d['value'], 2), 'img/s', round(d['ms_per_step'], 2), 'ms')
+    print(d['metric'], d['dtype'], d['op'], d['adapter'][:9], 'graph' if d['cuda_graph'] else 'eager', 'tf32' if d.get('tf32_gemm') else '', round(d['value'], 2), 'img/s', round(d['ms_per_step'], 2), 'ms')
 PY
 tail -3 gpurun_out/step_matrix.err
