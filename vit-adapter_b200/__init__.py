@@ -18,5 +18,6 @@ from . import _cabi  # noqa: F401
 from .functions import (MSDeformAttnFunction, MSDeformAttnFusedFunction, MSDeformAttnMergedFunction,  # noqa: F401
                         set_amp_value_dtype)
 from .modules import MSDeformAttn  # noqa: F401
+from .graphs import GraphedStep  # noqa: F401
 
-__all__ = ['MSDeformAttnFunction', 'MSDeformAttnFusedFunction', 'MSDeformAttnMergedFunction', 'MSDeformAttn', 'set_amp_value_dtype']
+__all__ = ['MSDeformAttnFunction', 'MSDeformAttnFusedFunction', 'MSDeformAttnMergedFunction', 'MSDeformAttn', 'set_amp_value_dtype', 'GraphedStep']
