@@ -47,7 +47,9 @@ extern "C" {
 enum msda_dtype {
   MSDA_F32 = 0,  /* loc/aw f32; the reference's production dtype (custom_fwd casts to fp32)   */
   MSDA_BF16 = 1, /* loc/aw f32, fp32 accumulation; new capability (reference has no bf16 path) */
-  MSDA_F64 = 2   /* loc/aw f64; exists so the reference's fp64 gradcheck (ops/test.py:78-101) runs */
+  MSDA_F64 = 2,  /* loc/aw f64; exists so the reference's fp64 gradcheck (ops/test.py:78-101) runs */
+  MSDA_F16 = 3   /* adapter_* entry points only (fp16 autocast, the reference's `fp16 = dict(loss_scale=...)` configs);
+                    the msda_* entry points reject it: like the reference, the sampling core runs fp16 AMP in fp32 */
 };
 
 /* negative error codes */
@@ -184,9 +186,9 @@ int msda_backward_fused(const msda_dims* dims, int dtype,
  * Replaces DWConv.forward of the reference (adapter_modules.py:73-87: slice the [B, 21n, C] sequence into the
  * three maps 2Hx2W / HxW / (H/2)x(W/2), transpose each to NCHW, nn.Conv2d(C, C, 3, 1, 1, groups=C), transpose
  * back, concatenate) with one kernel that reads and writes the tokens in place (channels-last).
- *   x, y, grad_y, grad_x   [B, n_tokens, C]  dtype T (f32 | bf16 | f64), n_tokens = 21 * H * W / 4, H and W even
+ *   x, y, grad_y, grad_x   [B, n_tokens, C]  dtype T (f32 | bf16 | f16 | f64), n_tokens = 21 * H * W / 4, H and W even
  *   weight                 [C, 1, 3, 3]      dtype T ;  bias [C] dtype T or NULL
- *   grad_weight [C*9], grad_bias [C]: fp32 accumulators for T in {f32, bf16}, fp64 for T = f64 (fully written here)
+ *   grad_weight [C*9], grad_bias [C]: fp32 accumulators for T in {f32, bf16, f16}, fp64 for T = f64 (fully written here)
  *   workspace: adapter_dwconv_backward_weight_workspace_bytes(...) bytes of device scratch (per-CTA partial sums of the
  *   deterministic two-stage reduction); 0 = none needed (generic path: f64 or C % 4 != 0, reduced with atomics).
  * ------------------------------------------------------------------------------------------------ */
@@ -207,7 +209,7 @@ int adapter_dwconv_backward_weight(int dtype, const void* x, const void* grad_y,
  *   y = (x - mean(x)) / sqrt(var(x) + eps) * gamma + beta   per row of C channels, biased variance,
  * with y written directly in the consumer's dtype (bf16 under AMP: torch writes fp32 and the Linear casts it
  * with another full pass) and mean / rstd saved for the backward.
- *   x, grad_x [rows, C] in_dtype ; y, grad_y [rows, C] out_dtype ; (in, out) in {(f32,f32), (f32,bf16), (bf16,bf16)}
+ *   x, grad_x [rows, C] in_dtype ; y, grad_y [rows, C] out_dtype ; (in, out) in {(f32,f32), (f32,bf16), (bf16,bf16), (f32,f16), (f16,f16)}
  *   gamma, beta [C] fp32 (beta may be NULL) ; mean, rstd [rows] fp32 ; grad_gamma, grad_beta [C] fp32 (fully written)
  *   C % 4 == 0 and C <= 1024, else MSDA_E_UNSUPPORTED (the caller keeps torch's LayerNorm)
  *   workspace: adapter_layernorm_backward_workspace_bytes(rows, C) bytes, 16-byte aligned (per-CTA partial sums of the
@@ -225,7 +227,7 @@ int adapter_layernorm_backward(int in_dtype, int out_dtype, const void* grad_y, 
                                size_t workspace_bytes, void* stream);
 
 /* Residual epilogue of the Extractor (adapter_modules.py:113-116 `query = query + attn`,
- * `query = query + drop_path(ffn(...))`): out[i] = residual[i] + (float)branch[i] with an fp32 stream and an f32 | bf16
+ * `query = query + drop_path(ffn(...))`): out[i] = residual[i] + (float)branch[i] with an fp32 stream and an f32 | bf16 | f16
  * branch (the mixed-dtype case torch's add does not vectorise). n % 8 == 0, 16-byte aligned pointers; out may alias
  * residual. Anything else: MSDA_E_UNSUPPORTED / MSDA_E_ALIGN and the caller keeps torch's add. */
 int adapter_residual_add(int branch_dtype, const float* residual, const void* branch, float* out, int64_t n, void* stream);
@@ -234,7 +236,7 @@ int adapter_residual_add(int branch_dtype, const float* residual, const void* br
  * Bias gradient of the adapter's Linears: out[c] = sum over rows of x[row, c], fp32.
  * Replaces the row reduction inside the backward of every nn.Linear with a bias in MSDeformAttn
  * (ms_deform_attn.py:57-60) and ConvFFN (adapter_modules.py:56,60).
- *   x [rows, C] f32 (C % 4 == 0, C <= 1024) or bf16 (C % 8 == 0, C <= 2048), 16-byte aligned; out [C] fp32
+ *   x [rows, C] f32 (C % 4 == 0, C <= 1024) or bf16 / f16 (C % 8 == 0, C <= 2048), 16-byte aligned; out [C] fp32
  *   workspace: adapter_colsum_workspace_bytes(dtype, rows, C) bytes (per-CTA partial rows; deterministic sum)
  *   anything else returns MSDA_E_UNSUPPORTED (the caller keeps torch's sum).
  * ------------------------------------------------------------------------------------------------ */

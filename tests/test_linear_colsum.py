@@ -19,7 +19,7 @@ def test_linear_on_cpu_is_f_linear():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize('rows,C', [(86016, 768), (16384, 432), (5000, 144), (777, 8), (3, 2048), (100000, 192), (1, 64)])
-@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['f32', 'bf16'])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16, torch.float16], ids=['f32', 'bf16', 'f16'])
 def test_colsum_kernel(rows, C, dtype):
     from vit_adapter_b200 import _cabi
     if dtype == torch.float32 and C > 1024:
@@ -45,7 +45,7 @@ def test_colsum_unsupported_shapes():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('amp', [False, True], ids=['f32', 'bf16-autocast'])
+@pytest.mark.parametrize('amp', [False, torch.bfloat16, torch.float16], ids=['f32', 'bf16-autocast', 'f16-autocast'])
 def test_linear_matches_nn_linear(amp):
     from vit_adapter_b200 import _cabi
     torch.manual_seed(0)
@@ -57,7 +57,7 @@ def test_linear_matches_nn_linear(amp):
         lin.zero_grad(set_to_none=True)
         xi = x.clone().requires_grad_()
         n0 = _cabi.launch_count()
-        with torch.autocast('cuda', dtype=torch.bfloat16, enabled=amp):
+        with torch.autocast('cuda', dtype=amp or torch.bfloat16, enabled=bool(amp)):
             y = linear(xi, lin.weight, lin.bias) if ours else lin(xi)
         y.backward(gy.to(y.dtype))
         assert (_cabi.launch_count() - n0 == 2) == ours
@@ -68,7 +68,7 @@ def test_linear_matches_nn_linear(amp):
     for a, b in ((y0, y1), (gx0, gx1), (gw0, gw1)):   # the same GEMMs (cuBLAS may pick another algorithm for a transposed view)
         torch.testing.assert_close(a, b, rtol=tol, atol=tol * float(b.abs().max()))
     torch.testing.assert_close(gb0, gb1, rtol=tol, atol=tol * float(gb1.abs().max()))
-    want = gy.to(y0.dtype if not amp else torch.bfloat16).double().sum((0, 1))
+    want = gy.to(amp or torch.float32).double().sum((0, 1))
     torch.testing.assert_close(gb0.double(), want, rtol=1e-5, atol=1e-5 * float(want.abs().max()))
 
 

@@ -17,6 +17,9 @@ LIB_PATH = os.path.join(_HERE, 'lib', 'libmsda_b200.so')
 
 MSDA_F32, MSDA_BF16, MSDA_F64 = 0, 1, 2
 _DTYPES = {torch.float32: MSDA_F32, torch.bfloat16: MSDA_BF16, torch.float64: MSDA_F64}
+MSDA_F16 = 3   # adapter_* entry points only
+_ADAPTER_DTYPES = dict(_DTYPES)
+_ADAPTER_DTYPES[torch.float16] = MSDA_F16
 
 # every symbol include/msda_b200.h declares
 EXPORTS = (
@@ -400,7 +403,7 @@ def backward_fused(value, spatial_shapes, level_start_index, reference_points, s
 
 def dwconv_supported(x, weight, H, W):
     """True when the token-layout depth-wise 3x3 kernel applies (else the module runs the reference's op sequence)."""
-    return (x.is_cuda and x.dtype in _DTYPES and weight.dtype == x.dtype and x.dim() == 3 and H % 2 == 0 and W % 2 == 0
+    return (x.is_cuda and x.dtype in _ADAPTER_DTYPES and weight.dtype == x.dtype and x.dim() == 3 and H % 2 == 0 and W % 2 == 0
             and x.shape[1] == 21 * (H // 2) * (W // 2) and x.shape[2] <= 1024 and tuple(weight.shape) == (x.shape[2], 1, 3, 3))
 
 
@@ -410,7 +413,7 @@ def dwconv_forward(x, weight, bias, H, W):
     B, n, C = x.shape
     with _on(dev):
         y = torch.empty_like(x)
-        rc = lib.adapter_dwconv_forward(_DTYPES[x.dtype], x.data_ptr(), weight.data_ptr(),
+        rc = lib.adapter_dwconv_forward(_ADAPTER_DTYPES[x.dtype], x.data_ptr(), weight.data_ptr(),
                                         bias.data_ptr() if bias is not None else None, y.data_ptr(), B, n, C, H, W, _stream())
     if rc != 0:
         _raise(rc, 'adapter_dwconv_forward')
@@ -422,7 +425,7 @@ def dwconv_backward(x, weight, grad_y, H, W, need_input=True, need_weight=True):
     lib = load()
     dev = _check_cuda(x=x, weight=weight, grad_y=grad_y)
     B, n, C = x.shape
-    code = _DTYPES[x.dtype]
+    code = _ADAPTER_DTYPES[x.dtype]
     gx = gw = gb = None
     with _on(dev):
         if need_input:
@@ -482,7 +485,8 @@ def set_tuning(**kv):
 
 
 # --- adapter LayerNorm prologues ---------------------------------------------------------------------
-_LN_COMBOS = {(torch.float32, torch.float32), (torch.float32, torch.bfloat16), (torch.bfloat16, torch.bfloat16)}
+_LN_COMBOS = {(torch.float32, torch.float32), (torch.float32, torch.bfloat16), (torch.bfloat16, torch.bfloat16),
+              (torch.float32, torch.float16), (torch.float16, torch.float16)}
 
 
 def layernorm_supported(x, weight, bias, out_dtype):
@@ -501,7 +505,7 @@ def layernorm_forward(x, weight, bias, eps, out_dtype):
     with _on(dev):
         y = torch.empty(x.shape, dtype=out_dtype, device=dev)
         stats = torch.empty((2, rows), dtype=torch.float32, device=dev)
-        rc = lib.adapter_layernorm_forward(_DTYPES[x.dtype], _DTYPES[out_dtype], x.data_ptr(), weight.data_ptr(),
+        rc = lib.adapter_layernorm_forward(_ADAPTER_DTYPES[x.dtype], _ADAPTER_DTYPES[out_dtype], x.data_ptr(), weight.data_ptr(),
                                            bias.data_ptr() if bias is not None else None, y.data_ptr(), stats[0].data_ptr(),
                                            stats[1].data_ptr(), rows, C, float(eps), _stream())
     if rc != 0:
@@ -525,7 +529,7 @@ def layernorm_backward(grad_y, x, weight, stats, grad_residual=None):
         gwb = torch.empty((2, C), dtype=torch.float32, device=dev)
         ws_bytes = lib.adapter_layernorm_backward_workspace_bytes(rows, C)
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
-        rc = lib.adapter_layernorm_backward(_DTYPES[x.dtype], _DTYPES[grad_y.dtype], grad_y.data_ptr(), x.data_ptr(), weight.data_ptr(),
+        rc = lib.adapter_layernorm_backward(_ADAPTER_DTYPES[x.dtype], _ADAPTER_DTYPES[grad_y.dtype], grad_y.data_ptr(), x.data_ptr(), weight.data_ptr(),
                                             stats[0].data_ptr(), stats[1].data_ptr(),
                                             grad_residual.data_ptr() if grad_residual is not None else None,
                                             gx.data_ptr(), gwb[0].data_ptr(), gwb[1].data_ptr(),
@@ -537,13 +541,13 @@ def layernorm_backward(grad_y, x, weight, stats, grad_residual=None):
 
 # --- bias gradient of the adapter's Linears ------------------------------------------------------------
 def colsum_supported(x):
-    """x: [..., C] contiguous CUDA f32 (C % 4 == 0, C <= 1024) or bf16 (C % 8 == 0, C <= 2048)."""
+    """x: [..., C] contiguous CUDA f32 (C % 4 == 0, C <= 1024) or bf16 / f16 (C % 8 == 0, C <= 2048)."""
     if not (x.is_cuda and x.dim() >= 2 and x.numel() > 0 and x.is_contiguous()):
         return False
     C = x.shape[-1]
     if x.dtype == torch.float32:
         return C % 4 == 0 and C <= 1024
-    if x.dtype == torch.bfloat16:
+    if x.dtype in (torch.bfloat16, torch.float16):
         return C % 8 == 0 and C <= 2048
     return False
 
@@ -554,7 +558,7 @@ def colsum(x):
     dev = _check_cuda(x=x)
     C = x.shape[-1]
     rows = x.numel() // C
-    code = _DTYPES[x.dtype]
+    code = _ADAPTER_DTYPES[x.dtype]
     with _on(dev):
         out = torch.empty((C,), dtype=torch.float32, device=dev)
         ws_bytes = lib.adapter_colsum_workspace_bytes(code, rows, C)
@@ -567,7 +571,7 @@ def colsum(x):
 
 # --- residual epilogue ----------------------------------------------------------------------------------
 def residual_add_supported(res, branch):
-    return (res.is_cuda and branch.is_cuda and res.dtype == torch.float32 and branch.dtype in (torch.float32, torch.bfloat16)
+    return (res.is_cuda and branch.is_cuda and res.dtype == torch.float32 and branch.dtype in (torch.float32, torch.bfloat16, torch.float16)
             and res.shape == branch.shape and res.is_contiguous() and branch.is_contiguous() and res.numel() > 0
             and res.numel() % 8 == 0 and res.data_ptr() % 16 == 0 and branch.data_ptr() % 16 == 0)
 
@@ -578,7 +582,7 @@ def residual_add(res, branch):
     dev = _check_cuda(res=res, branch=branch)
     with _on(dev):
         out = torch.empty_like(res)
-        rc = lib.adapter_residual_add(_DTYPES[branch.dtype], res.data_ptr(), branch.data_ptr(), out.data_ptr(), res.numel(), _stream())
+        rc = lib.adapter_residual_add(_ADAPTER_DTYPES[branch.dtype], res.data_ptr(), branch.data_ptr(), out.data_ptr(), res.numel(), _stream())
     if rc != 0:
         _raise(rc, 'adapter_residual_add')
     return out

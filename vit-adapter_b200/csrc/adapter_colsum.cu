@@ -8,6 +8,8 @@
 // independent loads in flight, fp32 accumulation; the CTA's row slots are reduced in shared memory into one partial row
 // per CTA, and a second kernel sums the <= 592 partial rows in a fixed order (deterministic, no atomics).
 // Compulsory traffic: rows * C * e.
+#include <cuda_fp16.h>
+
 #include "msda_common.cuh"
 
 namespace msda {
@@ -29,6 +31,20 @@ template <> struct CsVec<__nv_bfloat16> {
     for (int i = 0; i < 4; ++i) {
       a[2 * i] += __uint_as_float(u[i] << 16);
       a[2 * i + 1] += __uint_as_float(u[i] & 0xffff0000u);
+    }
+  }
+};
+
+template <> struct CsVec<__half> {
+  static constexpr int kN = 8;
+  static __device__ __forceinline__ void add(const __half* p, float (&a)[8]) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+    const unsigned u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u[i]));
+      a[2 * i] += f.x;
+      a[2 * i + 1] += f.y;
     }
   }
 };
@@ -89,10 +105,10 @@ __global__ void __launch_bounds__(1024) adapter_colsum_final_kernel(const float*
   }
 }
 
-static int cs_vec(int dtype) { return dtype == MSDA_BF16 ? 8 : 4; }
+static int cs_vec(int dtype) { return dtype == MSDA_F32 ? 4 : 8; }
 
 bool colsum_supported(int dtype, int C) {
-  if (dtype != MSDA_F32 && dtype != MSDA_BF16) return false;
+  if (dtype != MSDA_F32 && dtype != MSDA_BF16 && dtype != MSDA_F16) return false;
   const int v = cs_vec(dtype);
   return C > 0 && C % v == 0 && C / v <= 256 && (size_t)C * sizeof(float) * (256 / (C / v)) <= 48 * 1024;
 }
@@ -113,8 +129,10 @@ cudaError_t launch_colsum(int dtype, const void* x, long long rows, int C, float
   const size_t smem = (size_t)rs * C * sizeof(float);
   if (dtype == MSDA_F32)
     adapter_colsum_kernel<float><<<grid, cg * rs, smem, s>>>(reinterpret_cast<const float*>(x), rows, C, cg, rs, partial);
-  else
+  else if (dtype == MSDA_BF16)
     adapter_colsum_kernel<__nv_bfloat16><<<grid, cg * rs, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), rows, C, cg, rs, partial);
+  else
+    adapter_colsum_kernel<__half><<<grid, cg * rs, smem, s>>>(reinterpret_cast<const __half*>(x), rows, C, cg, rs, partial);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   adapter_colsum_final_kernel<<<(C + 31) / 32, dim3(32, 32), 0, s>>>(partial, (int)grid, C, out);

@@ -9,6 +9,10 @@
 // writes the output tokens once. Compulsory traffic = read x + write y; the 9-tap reuse is served by L1/L2.
 // The backward reuses the same gather with flipped taps for grad_x and reduces grad_weight / grad_bias in
 // registers -> shared memory -> one fp32 atomicAdd per (CTA, channel, tap).
+#include <cuda_fp16.h>
+
+#include <type_traits>
+
 #include "msda_common.cuh"
 
 namespace msda {
@@ -26,8 +30,10 @@ template <> struct DwAcc<double> { using type = double; };
 
 template <typename T> __device__ __forceinline__ typename DwAcc<T>::type dw_ld(const T* p) { return (typename DwAcc<T>::type)(*p); }
 template <> __device__ __forceinline__ float dw_ld<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <> __device__ __forceinline__ float dw_ld<__half>(const __half* p) { return __half2float(*p); }
 template <typename T, typename A> __device__ __forceinline__ void dw_st(T* p, A v) { *p = (T)v; }
 template <> __device__ __forceinline__ void dw_st<__nv_bfloat16, float>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ void dw_st<__half, float>(__half* p, float v) { *p = __float2half_rn(v); }
 
 // token index inside the sequence -> (map origin token, map height, map width, h, w)
 __device__ __forceinline__ void dw_locate(int t, int H, int W, int& t0, int& mh, int& mw, int& h, int& w) {
@@ -79,7 +85,7 @@ __global__ void __launch_bounds__(256) adapter_dwconv_kernel(const DwParams p) {
           const float4 q = __ldg(reinterpret_cast<const float4*>(src));
           acc[0] = fmaf(q.x, tap[0], acc[0]); acc[1] = fmaf(q.y, tap[1], acc[1]);
           acc[2] = fmaf(q.z, tap[2], acc[2]); acc[3] = fmaf(q.w, tap[3], acc[3]);
-        } else if constexpr (sizeof(T) * VEC == 16 && sizeof(T) == 2) {
+        } else if constexpr (sizeof(T) * VEC == 16 && std::is_same<T, __nv_bfloat16>::value) {
           const uint4 q = __ldg(reinterpret_cast<const uint4*>(src));
           const unsigned u[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
@@ -96,7 +102,7 @@ __global__ void __launch_bounds__(256) adapter_dwconv_kernel(const DwParams p) {
     T* dst = y + ((b * p.Ntok + t) * p.C + cv * VEC);
     if constexpr (sizeof(T) * VEC == 16 && sizeof(T) == 4) {
       *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    } else if constexpr (sizeof(T) * VEC == 16 && sizeof(T) == 2) {
+    } else if constexpr (sizeof(T) * VEC == 16 && std::is_same<T, __nv_bfloat16>::value) {
       uint4 o;
       o.x = Vec<__nv_bfloat16>::pack2(acc[0], acc[1]); o.y = Vec<__nv_bfloat16>::pack2(acc[2], acc[3]);
       o.z = Vec<__nv_bfloat16>::pack2(acc[4], acc[5]); o.w = Vec<__nv_bfloat16>::pack2(acc[6], acc[7]);
@@ -241,6 +247,26 @@ template <> struct Quad<__nv_bfloat16> {
   static __device__ __forceinline__ void st(__nv_bfloat16* p, const float (&v)[4]) {
     uint2 o;
     o.x = Vec<__nv_bfloat16>::pack2(v[0], v[1]); o.y = Vec<__nv_bfloat16>::pack2(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = o;
+  }
+};
+
+template <> struct Quad<__half> {
+  using Raw = uint2;
+  static __device__ __forceinline__ Raw ld(const __half* p, bool ok) {
+    Raw q = make_uint2(0u, 0u);
+    if (ok) q = __ldg(reinterpret_cast<const uint2*>(p));
+    return q;
+  }
+  static __device__ __forceinline__ void unpack(const Raw& q, float (&v)[4]) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&q.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  }
+  static __device__ __forceinline__ void st(__half* p, const float (&v)[4]) {
+    uint2 o;
+    const __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+    o.x = *reinterpret_cast<const unsigned*>(&a); o.y = *reinterpret_cast<const unsigned*>(&b);
     *reinterpret_cast<uint2*>(p) = o;
   }
 };
@@ -467,6 +493,7 @@ cudaError_t launch_dwconv(const DwParams& p, int dtype, bool flip, cudaStream_t 
   switch (dtype) {
     case MSDA_F32: return flip ? launch_dw<float, true>(p, s) : launch_dw<float, false>(p, s);
     case MSDA_BF16: return flip ? launch_dw<__nv_bfloat16, true>(p, s) : launch_dw<__nv_bfloat16, false>(p, s);
+    case MSDA_F16: return flip ? launch_dw<__half, true>(p, s) : launch_dw<__half, false>(p, s);
     case MSDA_F64: return flip ? launch_dw<double, true>(p, s) : launch_dw<double, false>(p, s);
     default: return cudaErrorInvalidValue;
   }
@@ -474,7 +501,7 @@ cudaError_t launch_dwconv(const DwParams& p, int dtype, bool flip, cudaStream_t 
 
 // bytes of the per-CTA partial rows the deterministic two-stage reduction needs (0: the generic atomic path is used)
 size_t dwconv_wgrad_workspace_bytes(const DwParams& p, int dtype) {
-  if ((dtype != MSDA_F32 && dtype != MSDA_BF16) || p.C % 4 != 0 || p.C / 4 > 256) return 0;
+  if ((dtype != MSDA_F32 && dtype != MSDA_BF16 && dtype != MSDA_F16) || p.C % 4 != 0 || p.C / 4 > 256) return 0;
   const int cvec = p.C / 4;
   return (size_t)dw_run_grid(dw_run_geom(p), 256 / cvec) * 40 * cvec * sizeof(float);
 }
@@ -483,7 +510,7 @@ size_t dwconv_wgrad_workspace_bytes(const DwParams& p, int dtype) {
 cudaError_t launch_dwconv_wgrad(const DwParams& p, int dtype, const void* grad_y, void* gw, void* gb, void* workspace,
                                 size_t workspace_bytes, int* launches, cudaStream_t s) {
   const size_t asz = dtype == MSDA_F64 ? 8 : 4;
-  if (dtype == MSDA_F32 || dtype == MSDA_BF16) {
+  if (dtype == MSDA_F32 || dtype == MSDA_BF16 || dtype == MSDA_F16) {
     int cvec, ty_count;
     const bool ok = dtype == MSDA_F32 ? dw_run_shape<float>(p, grad_y, cvec, ty_count) : dw_run_shape<__nv_bfloat16>(p, grad_y, cvec, ty_count);
     if (ok && workspace && workspace_bytes >= dwconv_wgrad_workspace_bytes(p, dtype)) {
@@ -493,8 +520,10 @@ cudaError_t launch_dwconv_wgrad(const DwParams& p, int dtype, const void* grad_y
       float* partial = reinterpret_cast<float*>(workspace);
       if (dtype == MSDA_F32)
         adapter_dwconv_wgrad_run_kernel<float><<<grid, cvec * ty_count, smem, s>>>(p, g, grad_y, partial, cvec, ty_count);
-      else
+      else if (dtype == MSDA_BF16)
         adapter_dwconv_wgrad_run_kernel<__nv_bfloat16><<<grid, cvec * ty_count, smem, s>>>(p, g, grad_y, partial, cvec, ty_count);
+      else
+        adapter_dwconv_wgrad_run_kernel<__half><<<grid, cvec * ty_count, smem, s>>>(p, g, grad_y, partial, cvec, ty_count);
       cudaError_t e2 = cudaGetLastError();
       if (e2 != cudaSuccess) return e2;
       adapter_dwconv_wgrad_sum_kernel<<<(40 * cvec + 31) / 32, dim3(32, 32), 0, s>>>(partial, (int)grid, cvec, (float*)gw, (float*)gb);
@@ -522,6 +551,9 @@ cudaError_t launch_dwconv_wgrad(const DwParams& p, int dtype, const void* grad_y
       break;
     case MSDA_BF16:
       adapter_dwconv_wgrad_kernel<__nv_bfloat16><<<grid, block, smem, s>>>(p, grad_y, nullptr, (float*)gw, nullptr, (float*)gb, tokens_per_cta);
+      break;
+    case MSDA_F16:
+      adapter_dwconv_wgrad_kernel<__half><<<grid, block, smem, s>>>(p, grad_y, nullptr, (float*)gw, nullptr, (float*)gb, tokens_per_cta);
       break;
     case MSDA_F64:
       adapter_dwconv_wgrad_kernel<double><<<grid, block, smem, s>>>(p, grad_y, (double*)gw, nullptr, (double*)gb, nullptr, tokens_per_cta);

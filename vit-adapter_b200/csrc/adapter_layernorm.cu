@@ -16,6 +16,8 @@
 //             second kernel (deterministic, no atomics). When x also feeds a residual connection (query + f(LN(query))), the
 //             gradient arriving over that connection is added into dx here, which removes autograd's separate add pass.
 // Compulsory traffic: forward rows*C*(e_in + e_out); backward rows*C*(e_in + e_out + e_in).
+#include <cuda_fp16.h>
+
 #include "msda_common.cuh"
 
 namespace msda {
@@ -66,6 +68,22 @@ template <> struct LnQuad<__nv_bfloat16> {
   static __device__ __forceinline__ void st(__nv_bfloat16* p, const float (&v)[4]) {
     uint2 o;
     o.x = Vec<__nv_bfloat16>::pack2(v[0], v[1]); o.y = Vec<__nv_bfloat16>::pack2(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = o;
+  }
+};
+
+template <> struct LnQuad<__half> {
+  static __device__ __forceinline__ void cvt(const uint2& q, float (&v)[4]) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&q.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  }
+  static __device__ __forceinline__ void ld(const __half* p, float (&v)[4]) { cvt(__ldg(reinterpret_cast<const uint2*>(p)), v); }
+  static __device__ __forceinline__ void ld_shared(const __half* p, float (&v)[4]) { cvt(*reinterpret_cast<const uint2*>(p), v); }
+  static __device__ __forceinline__ void st(__half* p, const float (&v)[4]) {
+    uint2 o;
+    const __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+    o.x = *reinterpret_cast<const unsigned*>(&a); o.y = *reinterpret_cast<const unsigned*>(&b);
     *reinterpret_cast<uint2*>(p) = o;
   }
 };
@@ -314,6 +332,8 @@ static cudaError_t ln_dispatch(const LnParams& p, int in_dtype, int out_dtype, c
   if (in_dtype == MSDA_F32 && out_dtype == MSDA_F32) return ln_launch<float, float, BWD>(p, s);
   if (in_dtype == MSDA_F32 && out_dtype == MSDA_BF16) return ln_launch<float, __nv_bfloat16, BWD>(p, s);
   if (in_dtype == MSDA_BF16 && out_dtype == MSDA_BF16) return ln_launch<__nv_bfloat16, __nv_bfloat16, BWD>(p, s);
+  if (in_dtype == MSDA_F32 && out_dtype == MSDA_F16) return ln_launch<float, __half, BWD>(p, s);
+  if (in_dtype == MSDA_F16 && out_dtype == MSDA_F16) return ln_launch<__half, __half, BWD>(p, s);
   return cudaErrorInvalidValue;
 }
 

@@ -1,10 +1,14 @@
 // adapter_residual.cu — the residual epilogues of the adapter's Extractor.
 //
 // Reference: `query = query + attn` and `query = query + self.drop_path(self.ffn(...))` (adapter_modules.py:113-116). Under
-// AMP the stream `query` is fp32 and the branch (a Linear's output) is bf16; torch's mixed-dtype add falls off its
+// AMP the stream `query` is fp32 and the branch (a Linear's output) is bf16 (or fp16); torch's mixed-dtype add falls off its
 // vectorised path (measured: 216 us for 86 016 x 768 on B200, 0.47 of the HBM roofline). This is the same add with
 // 16-byte loads on both operands: out[i] = res[i] + (float)branch[i].
 // Compulsory traffic: n * (4 + e_branch + 4).
+#include <cuda_fp16.h>
+
+#include <type_traits>
+
 #include "msda_common.cuh"
 
 namespace msda {
@@ -22,7 +26,14 @@ __global__ void __launch_bounds__(256) adapter_residual_add_kernel(const float* 
       const uint4 q = __ldg(reinterpret_cast<const uint4*>(branch) + i);
       const unsigned u[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { b[2 * k] = __uint_as_float(u[k] << 16); b[2 * k + 1] = __uint_as_float(u[k] & 0xffff0000u); }
+      for (int k = 0; k < 4; ++k) {
+        if constexpr (std::is_same<TB, __half>::value) {
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u[k]));
+          b[2 * k] = f.x; b[2 * k + 1] = f.y;
+        } else {
+          b[2 * k] = __uint_as_float(u[k] << 16); b[2 * k + 1] = __uint_as_float(u[k] & 0xffff0000u);
+        }
+      }
     } else {
       const float4 q0 = __ldg(reinterpret_cast<const float4*>(branch) + 2 * i);
       const float4 q1 = __ldg(reinterpret_cast<const float4*>(branch) + 2 * i + 1);
@@ -40,6 +51,8 @@ cudaError_t launch_residual_add(int branch_dtype, const float* res, const void* 
   if (blocks < 1) blocks = 1;
   if (branch_dtype == MSDA_BF16)
     adapter_residual_add_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, s>>>(res, reinterpret_cast<const __nv_bfloat16*>(branch), out, n8);
+  else if (branch_dtype == MSDA_F16)
+    adapter_residual_add_kernel<__half><<<(unsigned)blocks, 256, 0, s>>>(res, reinterpret_cast<const __half*>(branch), out, n8);
   else if (branch_dtype == MSDA_F32)
     adapter_residual_add_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(res, reinterpret_cast<const float*>(branch), out, n8);
   else

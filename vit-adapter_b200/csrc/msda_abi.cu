@@ -470,8 +470,11 @@ int msda_backward_fused(const msda_dims* dims, int dtype, const void* value, con
   return 0;
 }
 
+// element size for the adapter_* entry points (they also take fp16)
+static size_t adapter_elem_size(int dtype) { return dtype == MSDA_F16 ? 2 : elem_size(dtype); }
+
 static int dw_check(int dtype, int32_t B, int32_t n_tokens, int32_t C, int32_t H, int32_t W) {
-  if (elem_size(dtype) == 0) return fail(MSDA_E_DTYPE, "adapter_dwconv: unknown dtype %d", dtype);
+  if (adapter_elem_size(dtype) == 0) return fail(MSDA_E_DTYPE, "adapter_dwconv: unknown dtype %d", dtype);
   if (B <= 0 || n_tokens <= 0 || C <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1) ||
       (int64_t)n_tokens != 21ll * (H / 2) * (W / 2) || C > 1024 || (int64_t)B * n_tokens * C >= (1ll << 40))
     return fail(MSDA_E_DIMS, "adapter_dwconv: need n_tokens == 21*H*W/4 with even H, W and C <= 1024 (B=%d n=%d C=%d H=%d W=%d)",
@@ -527,15 +530,17 @@ int adapter_dwconv_backward_weight(int dtype, const void* x, const void* grad_y,
 }
 
 static int ln_check(const char* who, int in_dtype, int out_dtype, int64_t rows, int32_t C) {
-  const bool combo = (in_dtype == MSDA_F32 && (out_dtype == MSDA_F32 || out_dtype == MSDA_BF16)) ||
-                     (in_dtype == MSDA_BF16 && out_dtype == MSDA_BF16);
-  if (!combo) return fail(MSDA_E_DTYPE, "%s: (x, y) dtypes must be (f32, f32), (f32, bf16) or (bf16, bf16), got (%d, %d)", who, in_dtype, out_dtype);
+  const bool combo = (in_dtype == MSDA_F32 && (out_dtype == MSDA_F32 || out_dtype == MSDA_BF16 || out_dtype == MSDA_F16)) ||
+                     (in_dtype == MSDA_BF16 && out_dtype == MSDA_BF16) || (in_dtype == MSDA_F16 && out_dtype == MSDA_F16);
+  if (!combo)
+    return fail(MSDA_E_DTYPE, "%s: (x, y) dtypes must be (f32, f32), (f32, bf16), (bf16, bf16), (f32, f16) or (f16, f16), got (%d, %d)", who,
+                in_dtype, out_dtype);
   if (rows <= 0 || C <= 0 || rows * (int64_t)C >= (1ll << 40)) return fail(MSDA_E_DIMS, "%s: bad dims rows=%lld C=%d", who, (long long)rows, C);
   if (!layernorm_supported(C)) return fail(MSDA_E_UNSUPPORTED, "%s: C=%d needs C %% 4 == 0 and C <= 1024", who, C);
   return 0;
 }
 
-static bool ln_misaligned(const void* p, int dtype) { return (reinterpret_cast<uintptr_t>(p) & (4 * elem_size(dtype) - 1)) != 0; }
+static bool ln_misaligned(const void* p, int dtype) { return (reinterpret_cast<uintptr_t>(p) & (4 * adapter_elem_size(dtype) - 1)) != 0; }
 
 int adapter_layernorm_forward(int in_dtype, int out_dtype, const void* x, const void* gamma, const void* beta, void* y,
                               float* mean, float* rstd, int64_t rows, int32_t channels, float eps, void* stream) {
@@ -578,8 +583,8 @@ int adapter_layernorm_backward(int in_dtype, int out_dtype, const void* grad_y, 
 }
 
 int adapter_residual_add(int branch_dtype, const float* residual, const void* branch, float* out, int64_t n, void* stream) {
-  if (branch_dtype != MSDA_F32 && branch_dtype != MSDA_BF16)
-    return fail(MSDA_E_DTYPE, "adapter_residual_add: branch must be f32 or bf16, got %d", branch_dtype);
+  if (branch_dtype != MSDA_F32 && branch_dtype != MSDA_BF16 && branch_dtype != MSDA_F16)
+    return fail(MSDA_E_DTYPE, "adapter_residual_add: branch must be f32, bf16 or f16, got %d", branch_dtype);
   if (n <= 0 || n >= (1ll << 40)) return fail(MSDA_E_DIMS, "adapter_residual_add: bad element count %lld", (long long)n);
   if (n % 8) return fail(MSDA_E_UNSUPPORTED, "adapter_residual_add: element count %lld is not a multiple of 8", (long long)n);
   if (!residual || !branch || !out) return fail(MSDA_E_NULL, "adapter_residual_add: NULL tensor pointer");
@@ -598,11 +603,11 @@ size_t adapter_colsum_workspace_bytes(int dtype, int64_t rows, int32_t channels)
 
 int adapter_colsum(int dtype, const void* x, int64_t rows, int32_t channels, float* out, void* workspace,
                    size_t workspace_bytes, void* stream) {
-  if (elem_size(dtype) == 0) return fail(MSDA_E_DTYPE, "adapter_colsum: unknown dtype %d", dtype);
+  if (adapter_elem_size(dtype) == 0) return fail(MSDA_E_DTYPE, "adapter_colsum: unknown dtype %d", dtype);
   if (rows <= 0 || channels <= 0 || rows * (int64_t)channels >= (1ll << 40))
     return fail(MSDA_E_DIMS, "adapter_colsum: bad dims rows=%lld C=%d", (long long)rows, channels);
   if (!colsum_supported(dtype, channels))
-    return fail(MSDA_E_UNSUPPORTED, "adapter_colsum: needs f32 (C %% 4 == 0, C <= 1024) or bf16 (C %% 8 == 0, C <= 2048), got dtype %d C=%d",
+    return fail(MSDA_E_UNSUPPORTED, "adapter_colsum: needs f32 (C %% 4 == 0, C <= 1024) or bf16 / f16 (C %% 8 == 0, C <= 2048), got dtype %d C=%d",
                 dtype, channels);
   if (!x || !out) return fail(MSDA_E_NULL, "adapter_colsum: NULL tensor pointer");
   if (reinterpret_cast<uintptr_t>(x) & 15) return fail(MSDA_E_ALIGN, "adapter_colsum: x must be 16-byte aligned");

@@ -43,14 +43,14 @@ class _LinearColsumBias(torch.autograd.Function):
         return gx, gw, gb
 
 
-_OK = (torch.float32, torch.bfloat16)
+_OK = (torch.float32, torch.bfloat16, torch.float16)
 
 
 def linear(x, weight, bias, enabled=True):
     """F.linear(x, weight, bias); on CUDA with a trainable bias the backward's bias gradient uses the column-sum kernel."""
     if enabled and bias is not None and x.is_cuda and torch.is_grad_enabled() and bias.requires_grad:
         if torch.is_autocast_enabled('cuda'):
-            ok = torch.get_autocast_dtype('cuda') == torch.bfloat16 and x.dtype in _OK and weight.dtype in _OK and bias.dtype in _OK
+            ok = torch.get_autocast_dtype('cuda') in (torch.bfloat16, torch.float16) and x.dtype in _OK and weight.dtype in _OK and bias.dtype in _OK
         else:
             ok = x.dtype in _OK and weight.dtype == x.dtype and bias.dtype == x.dtype
         if ok:
