@@ -4,7 +4,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from conftest import load_golden, make_inputs
+from conftest import load_golden
 
 import vit_adapter_b200 as vab
 from vit_adapter_b200 import _cabi

@@ -1,4 +1,4 @@
-import cProfile, pstats, sys, os, io
+import cProfile, pstats, sys, io
 sys.path.insert(0, '/root/repo')
 import torch
 import vit_adapter_b200 as vab

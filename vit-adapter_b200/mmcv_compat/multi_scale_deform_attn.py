@@ -22,7 +22,6 @@ compare it with a CPU restatement of the published forward built on the referenc
 """
 import warnings
 
-import torch
 from torch import nn
 
 from ..functions import MSDeformAttnFunction
