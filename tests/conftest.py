@@ -13,6 +13,15 @@ GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
+    # a fresh checkout has no lib/libmsda_b200.so (build artefacts are git-ignored): build it once, here, exactly as
+    # __graft_entry__.build() does, so the ABI tests exercise the real library. If nvcc is missing the product's own
+    # loud failure ("... is not built ...") is what the tests then report.
+    try:
+        from vit_adapter_b200 import build as _build
+        if _build.is_stale():
+            _build.build()
+    except Exception as exc:  # pragma: no cover
+        sys.stderr.write('conftest: could not build the CUDA library: %r\n' % (exc,))
 
 
 def pytest_collection_modifyitems(config, items):
