@@ -183,7 +183,7 @@ def main():
                     help='fp32 GEMMs / convolutions on TF32 tensor cores - the default of the torch 1.9.0 the reference pins '
                          '(segmentation/README.md:24); off by default in the torch of this image')
     ap.add_argument('--graph', action='store_true',
-                    help='capture the whole step (forward, backward, optimizer) in ONE CUDA graph and replay it (single GPU)')
+                    help='capture the whole step (forward, backward, optimizer, and under torchrun the DDP all-reduce) in ONE CUDA graph and replay it')
     args = ap.parse_args()
 
     if args.tf32:
@@ -196,6 +196,8 @@ def main():
     dev = torch.device('cuda', local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        if args.graph:
+            os.environ.setdefault('TORCH_NCCL_ASYNC_ERROR_HANDLING', '0')   # NCCL work captured in a graph has no watchdog-visible events
         dist.init_process_group('nccl', device_id=dev)
 
     import vit_adapter_b200 as vab
@@ -217,9 +219,18 @@ def main():
     n_params = sum(p.numel() for p in net.parameters())
     n_adapter = sum(p.numel() for n, p in net.named_parameters() if 'interactions' in n or 'spm' in n)
     model = net
+    use_graph = args.graph
     if world > 1 and args.mode == 'train':
-        model = nn.parallel.DistributedDataParallel(net, device_ids=[local_rank], gradient_as_bucket_view=True)
-    use_graph = args.graph and world == 1
+        if use_graph:
+            # DDP under whole-step capture (torch docs, "Usage with DistributedDataParallel"): construct DDP on a side
+            # stream, and warm up >= 11 eager iterations so that bucket rebuilding is over before the capture
+            side0 = torch.cuda.Stream()
+            with torch.cuda.stream(side0):
+                model = nn.parallel.DistributedDataParallel(net, device_ids=[local_rank], gradient_as_bucket_view=True)
+            torch.cuda.current_stream().wait_stream(side0)
+            args.warmup = max(args.warmup, 11)
+        else:
+            model = nn.parallel.DistributedDataParallel(net, device_ids=[local_rank], gradient_as_bucket_view=True)
     opt = torch.optim.AdamW(net.parameters(), lr=6e-5, weight_decay=0.01, fused=True, capturable=use_graph) if args.mode == 'train' else None
     img = torch.randn(args.batch, 3, args.image, args.image, device=dev)
     lab = torch.randint(0, 150, (args.batch, args.image // 4, args.image // 4), device=dev)
@@ -256,7 +267,7 @@ def main():
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(3):
+            for _ in range(11 if world > 1 else 3):
                 step()
         torch.cuda.current_stream().wait_stream(side)
         graph = torch.cuda.CUDAGraph()
@@ -309,6 +320,13 @@ def main():
             'final': float(out.detach().float().mean()) if torch.is_tensor(out) else None,
         }) + '\n').encode())
     if world > 1:
+        if use_graph:
+            # tearing the NCCL communicator down after its collectives were captured in a graph hung on the test box:
+            # the result is out, every rank is synchronised - leave without the destructor
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 
