@@ -275,6 +275,8 @@ def run_ours(args):
                            '(use --impl reference for the CPU arm)')
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_host_thread_to_gpu(dev)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=dev)
@@ -413,7 +415,7 @@ def run_ours(args):
     h2d = sum(sum(c['host'][k].numel() * c['host'][k].element_size() for k in in_keys) for c in calls)
     d2h = sum(sum(t.numel() * t.element_size() for t in bufs) for bufs in host_out[0])
     e2e_steps = max(4, min(K, 50))   # the timed region includes the pipeline's fill and drain: all K steps, like the device arm
-    run_e2e(2)
+    run_e2e(max(4, W))
     # the host link is noisy from one pass to the next (8.6 - 12 ms per step seen on one box): three passes of K steps
     # each, every pass timed on the device as the max over ranks; the best pass is reported and all three are listed
     e2e_runs = []
@@ -538,6 +540,7 @@ def run_ours(args):
     # ---- CPU baseline (rank 0, N=1 only; bounded sample) ----------------------------------------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)   # the CPU arm gets every host core again (the GPU arm was pinned to its NUMA node)
         threads = os.cpu_count() or 1
         sb = min(batch, 2)
         cv, csec, cpts = cpu_reference_pass(variant, sb, threads, steps=3, warmup=1)
@@ -556,12 +559,48 @@ def run_ours(args):
                     'ms_per_step': e2e_ms / e2e_steps, 'steps': e2e_steps, 'passes_ms_per_step': [r / e2e_steps for r in e2e_runs], 'api': 'MSDeformAttnFunction.apply + autograd backward; pinned host buffers; copy-in / compute / copy-out on 3 streams, double-buffered'},
             'gpu_launches': launches, 'clocks': clocks, 'kernels': kernels, 'ref_cuda': ref_cuda,
             'points_per_step_per_gpu': pts_step, 'other_shapes': other, 'adapter_kernels': adapter_kernels,
+            'host_affinity': numa,
         }
         emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def bind_host_thread_to_gpu(dev):
+    """Pin this process to the CPUs NVML reports as local to its GPU, BEFORE any pinned host buffer is allocated, so the
+    e2e arm's staging buffers are first-touched on the GPU's own NUMA node (with one rank per GPU and no binding, half
+    of the ranks copy across the socket interconnect). Returns a short description for the JSON line, or None."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        h = None
+        try:
+            uuid = str(torch.cuda.get_device_properties(dev).uuid)
+            for cand in ('GPU-' + uuid, uuid):
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(cand.encode() if hasattr(cand, 'encode') else cand)
+                    break
+                except Exception:
+                    h = None
+        except Exception:
+            h = None
+        if h is None:
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            idx = int(vis.split(',')[dev.index]) if vis and vis.split(',')[dev.index].isdigit() else dev.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [w * 64 + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return {'cpus': '%d-%d' % (allowed[0], allowed[-1]), 'n': len(allowed)}
+    except Exception:
+        return None
 
 
 def time_adapter_kernels(dev):
