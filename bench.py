@@ -415,7 +415,7 @@ def run_ours(args):
     h2d = sum(sum(c['host'][k].numel() * c['host'][k].element_size() for k in in_keys) for c in calls)
     d2h = sum(sum(t.numel() * t.element_size() for t in bufs) for bufs in host_out[0])
     e2e_steps = max(4, min(K, 50))   # the timed region includes the pipeline's fill and drain: all K steps, like the device arm
-    run_e2e(max(4, W))
+    run_e2e(max(4, args.warmup))
     # the host link is noisy from one pass to the next (8.6 - 12 ms per step seen on one box): three passes of K steps
     # each, every pass timed on the device as the max over ranks; the best pass is reported and all three are listed
     e2e_runs = []
