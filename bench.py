@@ -544,7 +544,8 @@ def run_ours(args):
         threads = os.cpu_count() or 1
         sb = min(batch, 2)
         cv, csec, cpts = cpu_reference_pass(variant, sb, threads, steps=3, warmup=1)
-        cpu_baseline = {'value': cv, 'unit': 'Gsamples/s', 'cores': threads, 'kind': 'port',
+        cv1, _, _ = cpu_reference_pass(variant, sb, 1, steps=1, warmup=1)   # "... and also 1 thread"
+        cpu_baseline = {'value': cv, 'unit': 'Gsamples/s', 'cores': threads, 'kind': 'port', 'value_1_thread': cv1,
                         'sample': '%d of %d images, Injector+Extractor fwd+bwd, oracle/core_pytorch.py (restatement of the '
                                   "reference's ms_deform_attn_core_pytorch), %.0f ms per pass" % (sb, batch, csec * 1e3)}
 
