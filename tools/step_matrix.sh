@@ -13,6 +13,7 @@ run --tf32
 run --tf32 --graph
 run --variant L --image 896 --batch 1 --amp --with-cp --reference-sequence
 run --variant L --image 896 --batch 1 --amp --with-cp
+run --variant L --image 896 --batch 1 --amp --with-cp --graph
 run --variant L --image 1024 --batch 1 --mode infer --reference-sequence
 run --variant L --image 1024 --batch 1 --mode infer
 run --variant L --image 1024 --batch 1 --mode infer --graph
