@@ -21,6 +21,19 @@ __global__ void red_v4_kernel(float* table, int nrows_mask, const int* __restric
   }
 }
 
+// packed bf16x2 atomics: 16 bytes per lane carry 8 channels; LANES lanes cover one (b, token, head) row of 8*LANES channels
+template <int LANES>
+__global__ void red_bf16x2_kernel(unsigned* table, int nrows_mask, const int* __restrict__ rowidx, int iters) {
+  const int lane = threadIdx.x & 31, grp = lane / LANES, j = lane % LANES;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned one2 = 0x3f803f80u;  // (1.0bf16, 1.0bf16)
+  for (int i = 0; i < iters; ++i) {
+    const int row = __ldg(&rowidx[((gw * (32 / LANES) + grp) * 64 + (i & 63)) & 0xfffff]) & nrows_mask;
+    unsigned* p = table + (size_t)row * (LANES * 4) + j * 4;
+    asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(one2), "r"(one2), "r"(one2), "r"(one2) : "memory");
+  }
+}
+
 // rows_per_req: 1 -> every group reduces its own 128-byte row; 2 / 4 -> lane 0 of group 0 (and 2) reduces 256 / 512 contiguous bytes
 template <int ROWS_PER_REQ>
 __global__ void bulk_red_kernel(float* table, int nrows_mask, const int* __restrict__ rowidx, int iters) {
@@ -86,6 +99,21 @@ int main() {
     const double rows = (double)ctas * 32 * iters * 4;
     printf(" \"red_v4_one_cta_of_1024_per_sm_on_%d_sms\": {\"rows_per_ns\": %.2f, \"sm_cycles_per_row\": %.2f},\n", ctas, rows / (ms * 1e6),
            ms * 1e6 * 1.965 * ctas / rows);
+  }
+  {
+    const int ctas = nsm * 8;
+    // 4 lanes x 16 B = 64-byte rows = 32 bf16 channels (D = 32): 8 rows per warp instruction
+    red_bf16x2_kernel<4><<<ctas, 256>>>((unsigned*)table, (1 << 19) - 1, rowidx, iters);
+    cudaEventRecord(e0);
+    red_bf16x2_kernel<4><<<ctas, 256>>>((unsigned*)table, (1 << 19) - 1, rowidx, iters);
+    cudaEventRecord(e1); CHECK(cudaDeviceSynchronize()); cudaEventElapsedTime(&ms, e0, e1);
+    printf(" \"red_v4_bf16x2_64B_rows_32ch\": {\"rows_per_ns\": %.2f},\n", (double)ctas * 8 * iters * 8 / (ms * 1e6));
+    // 8 lanes x 16 B = 128-byte rows = 64 bf16 channels (D = 64)
+    red_bf16x2_kernel<8><<<ctas, 256>>>((unsigned*)table, mask, rowidx, iters);
+    cudaEventRecord(e0);
+    red_bf16x2_kernel<8><<<ctas, 256>>>((unsigned*)table, mask, rowidx, iters);
+    cudaEventRecord(e1); CHECK(cudaDeviceSynchronize()); cudaEventElapsedTime(&ms, e0, e1);
+    printf(" \"red_v4_bf16x2_128B_rows_64ch\": {\"rows_per_ns\": %.2f},\n", (double)ctas * 8 * iters * 4 / (ms * 1e6));
   }
   const size_t smem = 8 * 4 * 4 * 32 * 4;
 #define BULK(R)                                                                                                      \
