@@ -21,7 +21,7 @@
  *   - Thread-safe and re-entrant; no global mutable state.
  *
  * Tensor layouts (identical to the reference, ms_deform_attn_func.py:20-33):
- *   value              [N, S, M, D]        dtype T   (T = f32 | bf16 | f64)
+ *   value              [N, S, M, D]        dtype T   (T = f32 | bf16 | f16 | f64)
  *   spatial_shapes     [L, 2]  int64       (H_l, W_l)      -- on device, as in the reference
  *   level_start_index  [L]     int64                         -- on device
  *   sampling_loc       [N, Lq, M, L, P, 2] dtype F   (x, y) normalised to [0,1]
@@ -29,7 +29,7 @@
  *   out / grad_out     [N, Lq, M*D]        dtype T
  *   grad_value         [N, S, M, D]        dtype T
  *   grad_sampling_loc  like sampling_loc, grad_attn_weight like attn_weight (dtype F)
- * where F = f32 for T in {f32, bf16} and F = f64 for T = f64.
+ * where F = f32 for T in {f32, bf16, f16} and F = f64 for T = f64.
  */
 #ifndef MSDA_B200_H_
 #define MSDA_B200_H_
@@ -48,8 +48,9 @@ enum msda_dtype {
   MSDA_F32 = 0,  /* loc/aw f32; the reference's production dtype (custom_fwd casts to fp32)   */
   MSDA_BF16 = 1, /* loc/aw f32, fp32 accumulation; new capability (reference has no bf16 path) */
   MSDA_F64 = 2,  /* loc/aw f64; exists so the reference's fp64 gradcheck (ops/test.py:78-101) runs */
-  MSDA_F16 = 3   /* adapter_* entry points only (fp16 autocast, the reference's `fp16 = dict(loss_scale=...)` configs);
-                    the msda_* entry points reject it: like the reference, the sampling core runs fp16 AMP in fp32 */
+  MSDA_F16 = 3   /* fp16 I/O, loc/aw f32, fp32 accumulation (like MSDA_BF16; for the reference's `fp16 = dict(loss_scale=...)` AMP
+                    configs). The Python layer keeps the reference's behaviour - fp32 up-cast under fp16 AMP - unless asked
+                    (set_amp_value_dtype(torch.float16)); not available in the shared-memory forward */
 };
 
 /* negative error codes */
@@ -117,7 +118,7 @@ int msda_forward_ex(const msda_dims* dims, int dtype,
                     void* stream);
 
 /* Bytes of scratch the backward needs for (dims, dtype); 0 when none is needed.
- * (bf16 accumulates grad_value in an fp32 scratch of N*S*M*D floats.) */
+ * (bf16 / f16 accumulate grad_value in an fp32 scratch of N*S*M*D floats.) */
 size_t msda_backward_workspace_bytes(const msda_dims* dims, int dtype);
 
 /* Backward: replaces ms_deform_attn_cuda_backward (ms_deform_attn_cuda.cu:83-153) and the col2im

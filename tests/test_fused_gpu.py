@@ -50,19 +50,25 @@ CASES = [
 
 
 @pytest.mark.parametrize('cfg', CASES, ids=[c[0] for c in CASES])
-@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['f32', 'bf16'])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16, torch.float16], ids=['f32', 'bf16', 'f16'])
 def test_fused_matches_unfused(cfg, dtype):
     _, N, M, D, Lq, shapes, rb, rl = cfg
     value, shapes_t, lsi, ref, offsets, logits, go = _raw_inputs(N, M, D, Lq, shapes, 4, 31, rb, rl, dtype)
     assert _cabi.fused_supported(value, len(shapes), 4)
-    v1, o1, l1 = value.clone().requires_grad_(), offsets.clone().requires_grad_(), logits.clone().requires_grad_()
-    out1 = vab.MSDeformAttnFusedFunction.apply(v1, shapes_t, lsi, ref, o1, l1)
-    out1.backward(go)
-    v2, o2, l2 = value.clone().requires_grad_(), offsets.clone().requires_grad_(), logits.clone().requires_grad_()
-    out2 = _unfused(v2, shapes_t, lsi, ref, o2, l2)
-    out2.backward(go)
-    torch.cuda.synchronize()
-    ft, gt = (1e-5, 1e-4) if dtype == torch.float32 else (1e-2, 1e-2)
+    if dtype == torch.float16:
+        vab.set_amp_value_dtype(torch.float16)   # fp16 tensors run natively only when asked (default: fp32 up-cast, as the reference)
+    try:
+        v1, o1, l1 = value.clone().requires_grad_(), offsets.clone().requires_grad_(), logits.clone().requires_grad_()
+        out1 = vab.MSDeformAttnFusedFunction.apply(v1, shapes_t, lsi, ref, o1, l1)
+        out1.backward(go)
+        v2, o2, l2 = value.clone().requires_grad_(), offsets.clone().requires_grad_(), logits.clone().requires_grad_()
+        out2 = _unfused(v2, shapes_t, lsi, ref, o2, l2)
+        out2.backward(go)
+        torch.cuda.synchronize()
+    finally:
+        vab.set_amp_value_dtype(torch.float32)
+    assert out1.dtype == dtype and v1.grad.dtype == dtype
+    ft, gt = {torch.float32: (1e-5, 1e-4), torch.bfloat16: (1e-2, 1e-2), torch.float16: (2e-3, 2e-3)}[dtype]
     torch.testing.assert_close(out1.float(), out2.float(), rtol=ft, atol=ft * max(1.0, _scale(out2.float())))
     torch.testing.assert_close(v1.grad.float(), v2.grad.float(), rtol=gt, atol=gt * _scale(v2.grad.float()))
     torch.testing.assert_close(o1.grad, o2.grad, rtol=gt, atol=gt * _scale(o2.grad))
@@ -116,7 +122,7 @@ def test_fused_unsupported_configurations_fall_back():
                             torch.zeros(1, 3, 2, 1, 4, 2, device=DEV), torch.zeros(1, 3, 2, 4, device=DEV))
 
 
-@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['f32', 'bf16-autocast'])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16, torch.float16], ids=['f32', 'bf16-autocast', 'f16-autocast'])
 def test_module_fused_vs_reference_sequence(dtype):
     """MSDeformAttn(fused=True) vs the same module running the reference's op sequence (fused=False):
     outputs and every parameter / input gradient."""
@@ -130,9 +136,9 @@ def test_module_fused_vs_reference_sequence(dtype):
     query = torch.randn(2, 64, 384, device=DEV)
     feat = torch.randn(2, 336, 384, device=DEV)
     ref = torch.rand(1, 64, 1, 2, device=DEV)
-    amp = dtype == torch.bfloat16
+    amp = dtype != torch.float32
     if amp:
-        vab.set_amp_value_dtype(torch.bfloat16)
+        vab.set_amp_value_dtype(dtype)
     try:
         res = []
         for fused, merge in ((True, True), (False, False), (True, False)):
@@ -141,7 +147,7 @@ def test_module_fused_vs_reference_sequence(dtype):
             m.zero_grad(set_to_none=True)
             q, f = query.clone().requires_grad_(), feat.clone().requires_grad_()
             n0 = _cabi.launch_count()
-            with torch.autocast('cuda', dtype=torch.bfloat16, enabled=amp):
+            with torch.autocast('cuda', dtype=dtype if amp else torch.bfloat16, enabled=amp):
                 out = m(q, ref, f, shapes, lsi)
             out.float().square().mean().backward()
             res.append((out.detach().float(), q.grad, f.grad, {k: p.grad.clone() for k, p in m.named_parameters()},

@@ -31,9 +31,14 @@ def _run(inp, dtype):
     cdt = torch.float64 if dtype == torch.float64 else torch.float32
     loc = g['loc'].to(cdt).requires_grad_()
     aw = g['aw'].to(cdt).requires_grad_()
-    out = vab.MSDeformAttnFunction.apply(value, g['shapes'], g['lsi'], loc, aw, 64)
-    out.backward(g['grad_out'].to(dtype))
-    torch.cuda.synchronize()
+    if dtype == torch.float16:
+        vab.set_amp_value_dtype(torch.float16)   # native fp16 I/O is opt-in (default: fp32 up-cast, as the reference)
+    try:
+        out = vab.MSDeformAttnFunction.apply(value, g['shapes'], g['lsi'], loc, aw, 64)
+        out.backward(g['grad_out'].to(dtype))
+        torch.cuda.synchronize()
+    finally:
+        vab.set_amp_value_dtype(torch.float32)
     return out.detach().cpu(), value.grad.cpu(), loc.grad.cpu(), aw.grad.cpu()
 
 
@@ -70,21 +75,24 @@ def test_golden_f64(case):
     torch.testing.assert_close(ga, g['grad_aw_f64'], rtol=1e-9, atol=1e-11)
 
 
+@pytest.mark.parametrize('low', [torch.bfloat16, torch.float16], ids=['bf16', 'f16'])
 @pytest.mark.parametrize('case', ['op_inj_edges', 'op_ext_edges', 'op_d32_edges', 'op_d64_edges', 'op_odd_d5'])
-def test_golden_bf16(case):
+def test_golden_bf16(case, low):
+    """16-bit I/O (bf16; fp16 = the same kernels on __half), fp32 locations / weights / accumulation."""
     g = load_golden(case)
-    # oracle on the bf16-rounded value / grad_out, in fp32: isolates kernel error from input rounding
-    vq = g['value'].bfloat16().float()
-    goq = g['grad_out'].bfloat16().float()
+    # oracle on the rounded value / grad_out, in fp32: isolates kernel error from input rounding
+    vq = g['value'].to(low).float()
+    goq = g['grad_out'].to(low).float()
+    tol = 1e-2 if low == torch.bfloat16 else 2e-3
     want = c_oracle.forward(vq, g['shapes'], g['lsi'], g['loc'], g['aw'])
     wgv, wgl, wga = c_oracle.backward(vq, g['shapes'], g['lsi'], g['loc'], g['aw'], goq)
     g2 = dict(g)
-    out, gv, gl, ga = _run(g2, torch.bfloat16)
-    assert out.dtype == torch.bfloat16 and gv.dtype == torch.bfloat16
-    torch.testing.assert_close(out.float(), want, rtol=1e-2, atol=1e-2 * _scale(want))
-    torch.testing.assert_close(gv.float(), wgv, rtol=1e-2, atol=1e-2 * _scale(wgv))
-    torch.testing.assert_close(gl, wgl, rtol=1e-2, atol=1e-2 * _scale(wgl))
-    torch.testing.assert_close(ga, wga, rtol=1e-2, atol=1e-2 * _scale(wga))
+    out, gv, gl, ga = _run(g2, low)
+    assert out.dtype == low and gv.dtype == low
+    torch.testing.assert_close(out.float(), want, rtol=tol, atol=tol * _scale(want))
+    torch.testing.assert_close(gv.float(), wgv, rtol=tol, atol=tol * _scale(wgv))
+    torch.testing.assert_close(gl, wgl, rtol=tol, atol=tol * _scale(wgl))
+    torch.testing.assert_close(ga, wga, rtol=tol, atol=tol * _scale(wga))
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -273,12 +281,15 @@ FULL = [
 
 
 @pytest.mark.parametrize('cfg', FULL, ids=[s[0] for s in FULL])
-@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['f32', 'bf16'])
-def test_full_size_properties(cfg, dtype):
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16, torch.float16], ids=['f32', 'bf16', 'f16'])
+def test_full_size_properties(cfg, dtype, request):
     _, N, M, D, Lq, shapes, P = cfg
     inp = make_inputs(N, M, D, Lq, shapes, P, seed=1, dist='adapter')
     g = _cuda(inp)
-    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    tol = {torch.float32: 1e-5, torch.bfloat16: 2e-2, torch.float16: 3e-3}[dtype]
+    if dtype == torch.float16:
+        vab.set_amp_value_dtype(torch.float16)
+        request.addfinalizer(lambda: vab.set_amp_value_dtype(torch.float32))
     value = g['value'].to(dtype)
     f = lambda v, a: vab.MSDeformAttnFunction.apply(v, g['shapes'], g['lsi'], g['loc'], a, 64).float()
     out = f(value, g['aw'])
@@ -362,6 +373,23 @@ def test_autocast_matches_reference_policy():
     finally:
         vab.set_amp_value_dtype(torch.float32)
     torch.testing.assert_close(got16.float(), want, rtol=2e-2, atol=2e-2 * _scale(want))
+    # fp16 autocast (the reference's `fp16 = dict(loss_scale=...)` configs): fp32 core by default, fp16 I/O when asked
+    with torch.autocast('cuda', dtype=torch.float16):
+        g32 = vab.MSDeformAttnFunction.apply(inp['value'].half(), inp['shapes'], inp['lsi'], inp['loc'], inp['aw'], 64)
+        assert g32.dtype == torch.float32
+    vab.set_amp_value_dtype(torch.float16)
+    try:
+        with torch.autocast('cuda', dtype=torch.float16):
+            v = inp['value'].clone().requires_grad_()
+            gh = vab.MSDeformAttnFunction.apply(v, inp['shapes'], inp['lsi'], inp['loc'], inp['aw'], 64)
+            assert gh.dtype == torch.float16
+            gh.float().sum().backward()
+            assert v.grad.dtype == torch.float32 and bool(torch.isfinite(v.grad).all())
+    finally:
+        vab.set_amp_value_dtype(torch.float32)
+    torch.testing.assert_close(gh.float(), want, rtol=3e-3, atol=3e-3 * _scale(want))
+    with pytest.raises(ValueError):
+        vab.set_amp_value_dtype(torch.float64)
 
 
 def test_launch_counter_and_stream():

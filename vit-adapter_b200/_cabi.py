@@ -16,10 +16,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libmsda_b200.so')
 
 MSDA_F32, MSDA_BF16, MSDA_F64 = 0, 1, 2
-_DTYPES = {torch.float32: MSDA_F32, torch.bfloat16: MSDA_BF16, torch.float64: MSDA_F64}
-MSDA_F16 = 3   # adapter_* entry points only
-_ADAPTER_DTYPES = dict(_DTYPES)
-_ADAPTER_DTYPES[torch.float16] = MSDA_F16
+MSDA_F16 = 3
+_DTYPES = {torch.float32: MSDA_F32, torch.bfloat16: MSDA_BF16, torch.float64: MSDA_F64, torch.float16: MSDA_F16}
+_ADAPTER_DTYPES = _DTYPES
 
 # every symbol include/msda_b200.h declares
 EXPORTS = (
@@ -146,7 +145,7 @@ def _dims(value, spatial_shapes, sampling_loc):
 def _dtype_code(value, sampling_loc, attn_weight):
     code = _DTYPES.get(value.dtype)
     if code is None:
-        raise RuntimeError('unsupported value dtype %s (float32, bfloat16, float64)' % value.dtype)
+        raise RuntimeError('unsupported value dtype %s (float32, bfloat16, float16, float64)' % value.dtype)
     want = torch.float64 if code == MSDA_F64 else torch.float32
     if sampling_loc.dtype != want or attn_weight.dtype != want:
         raise RuntimeError('sampling_loc / attn_weight must be %s for value dtype %s' % (want, value.dtype))
@@ -280,7 +279,7 @@ MSDA_E_UNSUPPORTED = -8
 
 def fused_supported(value, n_levels, n_points):
     """True when the fused entry points have a kernel for this configuration (else use forward/backward)."""
-    if not value.is_cuda or value.dtype not in (torch.float32, torch.bfloat16):
+    if not value.is_cuda or value.dtype not in (torch.float32, torch.bfloat16, torch.float16):
         return False
     D = value.shape[-1]
     if not ((n_levels, n_points) in ((3, 4), (1, 4))) or D % 4 != 0 or (D // 4) not in (8, 16):

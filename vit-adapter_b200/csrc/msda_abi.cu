@@ -15,7 +15,7 @@ namespace msda {
 bool vec_supported(int dtype, int D, int* G_out);
 cudaError_t launch_forward(const Params& p, int dtype, bool vec_ok, int G, int minb, cudaStream_t s);
 cudaError_t launch_backward(const Params& p, int dtype, bool vec_ok, int G, int minb, cudaStream_t s);
-cudaError_t launch_cvt_f32_bf16(const float* src, void* dst, size_t n, cudaStream_t s);
+cudaError_t launch_cvt_f32_bf16(const float* src, void* dst, size_t n, int dtype, cudaStream_t s);
 cudaError_t launch_forward_fused(const Params& p, int dtype, int G, cudaStream_t s);
 cudaError_t launch_backward_fused(const Params& p, int dtype, int G, cudaStream_t s);
 struct DwParams {
@@ -74,7 +74,7 @@ static int cuda_fail(cudaError_t e, const char* what) {
 }
 
 static size_t elem_size(int dtype) {
-  return dtype == MSDA_F32 ? 4 : dtype == MSDA_BF16 ? 2 : dtype == MSDA_F64 ? 8 : 0;
+  return dtype == MSDA_F32 ? 4 : (dtype == MSDA_BF16 || dtype == MSDA_F16) ? 2 : dtype == MSDA_F64 ? 8 : 0;
 }
 
 static int check_dims(const msda_dims* d, int dtype) {
@@ -125,7 +125,7 @@ static int pick_chunk(const msda_dims* d, int per_iter, int override_qc) {
 // the same LSU data pipe. So it is OPT-IN (tuning key "fwd_smem" = 2).
 static bool plan_forward_smem(const msda_dims* d, int dtype, int G, const int64_t* hs, int nt, SmemPlan* plan,
                               int* qc_out, int* nchunk_out) {
-  if (!hs) return false;
+  if (!hs || dtype == MSDA_F16) return false;   // the staged forward is instantiated for f32 / bf16
   const int L = d->num_levels;
   if (!((L == 3 || L == 1) && d->num_point == 4)) return false;
   const int mode = g_smem_mode.load();
@@ -319,7 +319,7 @@ int msda_forward_ex(const msda_dims* dims, int dtype, const void* value, const i
 }
 
 size_t msda_backward_workspace_bytes(const msda_dims* dims, int dtype) {
-  if (!dims || dtype != MSDA_BF16) return 0;
+  if (!dims || (dtype != MSDA_BF16 && dtype != MSDA_F16)) return 0;
   return (size_t)dims->batch * dims->spatial_size * dims->num_heads * dims->channels * sizeof(float);
 }
 
@@ -349,13 +349,14 @@ int msda_backward(const msda_dims* dims, int dtype, const void* value, const int
   p.grad_loc = grad_sampling_loc; p.grad_aw = grad_attn_weight;
 
   const size_t nvalue = (size_t)p.N * p.S * p.M * p.D;
-  void* accum = (dtype == MSDA_BF16) ? workspace : grad_value;
-  const size_t accum_bytes = (dtype == MSDA_BF16) ? nvalue * sizeof(float) : nvalue * es;
+  const bool lowp = dtype == MSDA_BF16 || dtype == MSDA_F16;   // 16-bit I/O: fp32 accumulator in the workspace, converted once
+  void* accum = lowp ? workspace : grad_value;
+  const size_t accum_bytes = lowp ? nvalue * sizeof(float) : nvalue * es;
   p.grad_value = accum;
 
   // backward lane layout: 4 channels per lane for both dtypes (see VecB in msda_bwd.cu)
   int G = p.D / 4;
-  bool vec = (dtype == MSDA_F32 || dtype == MSDA_BF16) && p.D % 4 == 0 && G >= 2 && G <= 32 && (G & (G - 1)) == 0 &&
+  bool vec = (dtype == MSDA_F32 || lowp) && p.D % 4 == 0 && G >= 2 && G <= 32 && (G & (G - 1)) == 0 &&
              aligned(value, 16) && aligned(grad_out, 16) &&
              aligned(accum, 16) && aligned(sampling_loc, 8) && aligned(grad_sampling_loc, 8);
   const int per_iter = vec ? kWarps * (32 / G) : kWarps;
@@ -367,8 +368,8 @@ int msda_backward(const msda_dims* dims, int dtype, const void* value, const int
   e = launch_backward(p, dtype, vec, G, g_minb_bwd.load(), s);
   if (e != cudaSuccess) return cuda_fail(e, "msda_backward launch");
   g_launches.fetch_add(1);
-  if (dtype == MSDA_BF16) {
-    e = launch_cvt_f32_bf16(reinterpret_cast<const float*>(accum), grad_value, nvalue, s);
+  if (lowp) {
+    e = launch_cvt_f32_bf16(reinterpret_cast<const float*>(accum), grad_value, nvalue, dtype, s);
     if (e != cudaSuccess) return cuda_fail(e, "msda_backward bf16 convert launch");
     g_launches.fetch_add(1);
   }
@@ -434,7 +435,7 @@ int msda_backward_fused(const msda_dims* dims, int dtype, const void* value, con
       !grad_sampling_offsets || !grad_attn_logits)
     return fail(MSDA_E_NULL, "msda_backward_fused: NULL tensor pointer");
   const int G = dims->channels / 4;
-  if (!(dtype == MSDA_F32 || dtype == MSDA_BF16) || dims->channels % 4 != 0 || !(G == 8 || G == 16) ||
+  if (!(dtype == MSDA_F32 || dtype == MSDA_BF16 || dtype == MSDA_F16) || dims->channels % 4 != 0 || !(G == 8 || G == 16) ||
       !((dims->num_levels == 3 || dims->num_levels == 1) && dims->num_point == 4))
     return fail(MSDA_E_UNSUPPORTED, "msda_backward_fused: no fused kernel for dtype=%d D=%d L=%d P=%d", dtype, dims->channels,
                 dims->num_levels, dims->num_point);
@@ -449,7 +450,8 @@ int msda_backward_fused(const msda_dims* dims, int dtype, const void* value, con
   p.grad_loc = grad_sampling_offsets; p.grad_aw = grad_attn_logits;
   if (int e = fused_ref_params(p, dims, reference_points, ref_batch, ref_levels, offsets_row_stride, logits_row_stride)) return e;
   const size_t nvalue = (size_t)p.N * p.S * p.M * p.D;
-  void* accum = (dtype == MSDA_BF16) ? workspace : grad_value;
+  const bool lowp = dtype == MSDA_BF16 || dtype == MSDA_F16;   // 16-bit I/O: fp32 accumulator in the workspace, converted once
+  void* accum = lowp ? workspace : grad_value;
   p.grad_value = accum;
   if (!aligned(value, 16) || !aligned(grad_out, 16) || !aligned(accum, 16) || !aligned(sampling_offsets, 8) ||
       !aligned(grad_sampling_offsets, 8))
@@ -462,16 +464,15 @@ int msda_backward_fused(const msda_dims* dims, int dtype, const void* value, con
   if (e == cudaErrorNotSupported) return fail(MSDA_E_UNSUPPORTED, "msda_backward_fused: no fused kernel for G=%d", G);
   if (e != cudaSuccess) return cuda_fail(e, "msda_backward_fused launch");
   g_launches.fetch_add(1);
-  if (dtype == MSDA_BF16) {
-    e = launch_cvt_f32_bf16(reinterpret_cast<const float*>(accum), grad_value, nvalue, s);
+  if (lowp) {
+    e = launch_cvt_f32_bf16(reinterpret_cast<const float*>(accum), grad_value, nvalue, dtype, s);
     if (e != cudaSuccess) return cuda_fail(e, "msda_backward_fused bf16 convert launch");
     g_launches.fetch_add(1);
   }
   return 0;
 }
 
-// element size for the adapter_* entry points (they also take fp16)
-static size_t adapter_elem_size(int dtype) { return dtype == MSDA_F16 ? 2 : elem_size(dtype); }
+static size_t adapter_elem_size(int dtype) { return elem_size(dtype); }
 
 static int dw_check(int dtype, int32_t B, int32_t n_tokens, int32_t C, int32_t H, int32_t W) {
   if (adapter_elem_size(dtype) == 0) return fail(MSDA_E_DTYPE, "adapter_dwconv: unknown dtype %d", dtype);

@@ -53,6 +53,26 @@ struct VecB<__nv_bfloat16> {
   }
 };
 
+template <>
+struct VecB<__half> {
+  static constexpr int kCpl = 4;
+  static constexpr int kLaneBytes = 8;
+  float v[4];
+  __device__ __forceinline__ static VecB load(const __half* p) {
+    const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&t.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
+    VecB r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y;
+    return r;
+  }
+  __device__ __forceinline__ static VecB zero() {
+    VecB r;
+    r.v[0] = r.v[1] = r.v[2] = r.v[3] = 0.f;
+    return r;
+  }
+};
+
 template <int G>
 __device__ __forceinline__ float group_sum(float v) {
 #pragma unroll
@@ -369,24 +389,23 @@ __global__ void __launch_bounds__(kThreads) msda_bwd_generic_kernel(const Params
   }
 }
 
-// fp32 scratch -> bf16 grad_value (n is a multiple of 8 on the vector path; tail handled scalar).
-__global__ void __launch_bounds__(kThreads) msda_cvt_f32_bf16_kernel(const float* __restrict__ src,
-                                                                     __nv_bfloat16* __restrict__ dst,
-                                                                     size_t n) {
+// fp32 scratch -> bf16 / fp16 grad_value (n is a multiple of 8 on the vector path; tail handled scalar).
+template <typename TO>
+__global__ void __launch_bounds__(kThreads) msda_cvt_f32_bf16_kernel(const float* __restrict__ src, TO* __restrict__ dst, size_t n) {
   const size_t nvec = n / 8;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
     const float4 a = __ldcs(reinterpret_cast<const float4*>(src) + 2 * i);
     const float4 b = __ldcs(reinterpret_cast<const float4*>(src) + 2 * i + 1);
     uint4 o;
-    o.x = Vec<__nv_bfloat16>::pack2(a.x, a.y);
-    o.y = Vec<__nv_bfloat16>::pack2(a.z, a.w);
-    o.z = Vec<__nv_bfloat16>::pack2(b.x, b.y);
-    o.w = Vec<__nv_bfloat16>::pack2(b.z, b.w);
+    o.x = Vec<TO>::pack2(a.x, a.y);
+    o.y = Vec<TO>::pack2(a.z, a.w);
+    o.z = Vec<TO>::pack2(b.x, b.y);
+    o.w = Vec<TO>::pack2(b.z, b.w);
     reinterpret_cast<uint4*>(dst)[i] = o;
   }
   for (size_t i = nvec * 8 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    dst[i] = __float2bfloat16_rn(src[i]);
+    st_scalar(dst + i, src[i]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -430,6 +449,9 @@ cudaError_t launch_backward_fused(const Params& p, int dtype, int G, cudaStream_
   } else if (dtype == MSDA_BF16) {
     if (G == 8) return launch_fused_g<__nv_bfloat16, 8>(p, grid, s);
     if (G == 16) return launch_fused_g<__nv_bfloat16, 16>(p, grid, s);
+  } else if (dtype == MSDA_F16) {
+    if (G == 8) return launch_fused_g<__half, 8>(p, grid, s);
+    if (G == 16) return launch_fused_g<__half, 16>(p, grid, s);
   }
   return cudaErrorNotSupported;
 }
@@ -452,22 +474,27 @@ cudaError_t launch_backward(const Params& p, int dtype, bool vec_ok, int G, int 
   const dim3 grid((unsigned)((size_t)p.N * p.nchunk * p.M));
   if (vec_ok) {
     if (dtype == MSDA_F32) return launch_vec<float>(p, G, minb, grid, s);
+    if (dtype == MSDA_F16) return launch_vec<__half>(p, G, minb, grid, s);
     return launch_vec<__nv_bfloat16>(p, G, minb, grid, s);
   }
   switch (dtype) {
     case MSDA_F32: msda_bwd_generic_kernel<float, float, float><<<grid, kThreads, 0, s>>>(p); break;
     case MSDA_BF16: msda_bwd_generic_kernel<__nv_bfloat16, float, float><<<grid, kThreads, 0, s>>>(p); break;
+    case MSDA_F16: msda_bwd_generic_kernel<__half, float, float><<<grid, kThreads, 0, s>>>(p); break;
     case MSDA_F64: msda_bwd_generic_kernel<double, double, double><<<grid, kThreads, 0, s>>>(p); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
 }
 
-cudaError_t launch_cvt_f32_bf16(const float* src, void* dst, size_t n, cudaStream_t s) {
+cudaError_t launch_cvt_f32_bf16(const float* src, void* dst, size_t n, int dtype, cudaStream_t s) {
   size_t blocks = (n / 8 + kThreads - 1) / kThreads;
   if (blocks < 1) blocks = 1;
   if (blocks > 148u * 16u) blocks = 148u * 16u;
-  msda_cvt_f32_bf16_kernel<<<(unsigned)blocks, kThreads, 0, s>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  if (dtype == MSDA_F16)
+    msda_cvt_f32_bf16_kernel<__half><<<(unsigned)blocks, kThreads, 0, s>>>(src, reinterpret_cast<__half*>(dst), n);
+  else
+    msda_cvt_f32_bf16_kernel<__nv_bfloat16><<<(unsigned)blocks, kThreads, 0, s>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
   return cudaGetLastError();
 }
 

@@ -9,6 +9,7 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -137,6 +138,7 @@ __device__ __forceinline__ PointTap point_tap(float x, float y, float a, int H, 
 // 16-byte channel vectors. One lane owns kCpl consecutive channels of a head:
 //   float          : 4 channels  (LDG.E.128)
 //   __nv_bfloat16  : 8 channels  (LDG.E.128), widened to fp32 in registers
+//   __half         : 8 channels  (LDG.E.128), widened to fp32 in registers (opt-in fp16 I/O, set_amp_value_dtype)
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 struct Vec;
@@ -185,6 +187,39 @@ struct Vec<__nv_bfloat16> {
     return *reinterpret_cast<const unsigned*>(&h);
   }
   __device__ __forceinline__ void store(__nv_bfloat16* p) const {
+    uint4 t;
+    t.x = pack2(v[0], v[1]); t.y = pack2(v[2], v[3]);
+    t.z = pack2(v[4], v[5]); t.w = pack2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = t;
+  }
+};
+
+template <>
+struct Vec<__half> {
+  static constexpr int kCpl = 8;
+  float v[8];
+  __device__ __forceinline__ static Vec load(const __half* p) {
+    const uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+    const unsigned u[4] = {t.x, t.y, t.z, t.w};
+    Vec r;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u[i]));
+      r.v[2 * i] = f.x; r.v[2 * i + 1] = f.y;
+    }
+    return r;
+  }
+  __device__ __forceinline__ static Vec zero() {
+    Vec r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = 0.f;
+    return r;
+  }
+  __device__ __forceinline__ static unsigned pack2(float lo, float hi) {
+    const __half2 h = __floats2half2_rn(lo, hi);  // .x = lo (low 16 bits)
+    return *reinterpret_cast<const unsigned*>(&h);
+  }
+  __device__ __forceinline__ void store(__half* p) const {
     uint4 t;
     t.x = pack2(v[0], v[1]); t.y = pack2(v[2], v[3]);
     t.z = pack2(v[4], v[5]); t.w = pack2(v[6], v[7]);
@@ -244,6 +279,11 @@ template <>
 struct LaneVec<__nv_bfloat16, 16> : Vec<__nv_bfloat16> {
   __device__ __forceinline__ static LaneVec load(const __nv_bfloat16* p) { LaneVec r; static_cast<Vec<__nv_bfloat16>&>(r) = Vec<__nv_bfloat16>::load(p); return r; }
   __device__ __forceinline__ static LaneVec zero() { LaneVec r; static_cast<Vec<__nv_bfloat16>&>(r) = Vec<__nv_bfloat16>::zero(); return r; }
+};
+template <>
+struct LaneVec<__half, 16> : Vec<__half> {
+  __device__ __forceinline__ static LaneVec load(const __half* p) { LaneVec r; static_cast<Vec<__half>&>(r) = Vec<__half>::load(p); return r; }
+  __device__ __forceinline__ static LaneVec zero() { LaneVec r; static_cast<Vec<__half>&>(r) = Vec<__half>::zero(); return r; }
 };
 template <>
 struct LaneVec<float, 32> {
@@ -322,6 +362,8 @@ __device__ __forceinline__ double ld_scalar(const double* p) { return __ldg(p); 
 
 __device__ __forceinline__ void st_scalar(float* p, float v) { *p = v; }
 __device__ __forceinline__ void st_scalar(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ float ld_scalar(const __half* p) { return __half2float(*p); }
+__device__ __forceinline__ void st_scalar(__half* p, float v) { *p = __float2half_rn(v); }
 __device__ __forceinline__ void st_scalar(double* p, double v) { *p = v; }
 
 // Block -> (batch, query chunk, head) decomposition shared by forward and backward.

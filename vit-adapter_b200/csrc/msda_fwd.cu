@@ -272,6 +272,9 @@ cudaError_t launch_forward_fused(const Params& p, int dtype, int G, cudaStream_t
   if (dtype == MSDA_F32) {
     if (G == 8) return launch_fused_g<float, 8>(p, grid, s);
     if (G == 16) return launch_fused_g<float, 16>(p, grid, s);
+  } else if (dtype == MSDA_F16) {
+    if (G == 4) return launch_fused_g<__half, 4>(p, grid, s);
+    if (G == 8) return launch_fused_g<__half, 8>(p, grid, s);
   } else if (dtype == MSDA_BF16) {
     if (G == 4) return launch_fused_g<__nv_bfloat16, 4>(p, grid, s);
     if (G == 8) return launch_fused_g<__nv_bfloat16, 8>(p, grid, s);
@@ -294,7 +297,7 @@ static cudaError_t launch_vec(const Params& p, int G, int minb, dim3 grid, cudaS
 // Returns true when the vector kernels support (dtype, D): D*sizeof(T) is a multiple of 16 bytes and
 // D / (16/sizeof(T)) is a power of two in [2, 32].
 bool vec_supported(int dtype, int D, int* G_out) {
-  int cpl = dtype == MSDA_F32 ? 4 : dtype == MSDA_BF16 ? 8 : 0;
+  int cpl = dtype == MSDA_F32 ? 4 : (dtype == MSDA_BF16 || dtype == MSDA_F16) ? 8 : 0;
   if (cpl == 0 || D % cpl != 0) return false;
   const int G = D / cpl;
   if (G < 2 || G > 32 || (G & (G - 1)) != 0) return false;
@@ -306,11 +309,13 @@ cudaError_t launch_forward(const Params& p, int dtype, bool vec_ok, int G, int m
   const dim3 grid((unsigned)((size_t)p.N * p.nchunk * p.M));
   if (vec_ok) {
     if (dtype == MSDA_F32) return launch_vec<float>(p, G, minb, grid, s);
+    if (dtype == MSDA_F16) return launch_vec<__half>(p, G, minb, grid, s);
     return launch_vec<__nv_bfloat16>(p, G, minb, grid, s);
   }
   switch (dtype) {
     case MSDA_F32: msda_fwd_generic_kernel<float, float><<<grid, kThreads, 0, s>>>(p); break;
     case MSDA_BF16: msda_fwd_generic_kernel<__nv_bfloat16, float><<<grid, kThreads, 0, s>>>(p); break;
+    case MSDA_F16: msda_fwd_generic_kernel<__half, float><<<grid, kThreads, 0, s>>>(p); break;
     case MSDA_F64: msda_fwd_generic_kernel<double, double><<<grid, kThreads, 0, s>>>(p); break;
     default: return cudaErrorInvalidValue;
   }

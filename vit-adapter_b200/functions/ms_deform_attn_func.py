@@ -8,7 +8,7 @@ declared in include/msda_b200.h (called through `_cabi`); there is no PyTorch / 
 AMP: the reference decorates forward with `custom_fwd(cast_inputs=torch.float32)` (:21), i.e. under
 autocast everything is up-cast to fp32. That stays the default. `set_amp_value_dtype(torch.bfloat16)`
 opts in to the bf16 I/O kernels under autocast (value / out in bf16, locations and weights fp32,
-fp32 accumulation) — a capability the reference does not have.
+fp32 accumulation) — a capability the reference does not have; `torch.float16` does the same for fp16 autocast.
 """
 import torch
 from torch.autograd import Function
@@ -22,8 +22,8 @@ _AMP_VALUE_DTYPE = torch.float32
 def set_amp_value_dtype(dtype):
     """dtype `value` is cast to when the op runs under torch.autocast (float32 = reference behaviour)."""
     global _AMP_VALUE_DTYPE
-    if dtype not in (torch.float32, torch.bfloat16):
-        raise ValueError('amp value dtype must be torch.float32 or torch.bfloat16')
+    if dtype not in (torch.float32, torch.bfloat16, torch.float16):
+        raise ValueError('amp value dtype must be torch.float32, torch.bfloat16 or torch.float16')
     _AMP_VALUE_DTYPE = dtype
 
 
@@ -38,8 +38,8 @@ class MSDeformAttnFunction(Function):
                 sampling_locations, attention_weights, im2col_step):
         if torch.is_autocast_enabled('cuda') and value.is_cuda:
             value = value.to(_AMP_VALUE_DTYPE)
-        if value.dtype == torch.float16:
-            value = value.float()
+        if value.dtype == torch.float16 and _AMP_VALUE_DTYPE != torch.float16:
+            value = value.float()   # the reference's behaviour for fp16 AMP: the core runs in fp32
         cdt = _coord_dtype(value.dtype)
         # .to() is a no-op (same tensor) when the dtype already matches
         sampling_locations = sampling_locations.to(cdt)
@@ -80,8 +80,8 @@ class MSDeformAttnFusedFunction(Function):
                 attn_logits):
         if torch.is_autocast_enabled('cuda') and value.is_cuda:
             value = value.to(_AMP_VALUE_DTYPE)
-        if value.dtype == torch.float16:
-            value = value.float()
+        if value.dtype == torch.float16 and _AMP_VALUE_DTYPE != torch.float16:
+            value = value.float()   # the reference's behaviour for fp16 AMP: the core runs in fp32
         reference_points = reference_points.float().contiguous()
         sampling_offsets = sampling_offsets.float().contiguous()
         attn_logits = attn_logits.float().contiguous()
@@ -113,8 +113,8 @@ class MSDeformAttnMergedFunction(Function):
     def forward(ctx, value, value_spatial_shapes, value_level_start_index, reference_points, merged, n_levels, n_points):
         if torch.is_autocast_enabled('cuda') and value.is_cuda:
             value = value.to(_AMP_VALUE_DTYPE)
-        if value.dtype == torch.float16:
-            value = value.float()
+        if value.dtype == torch.float16 and _AMP_VALUE_DTYPE != torch.float16:
+            value = value.float()   # the reference's behaviour for fp16 AMP: the core runs in fp32
         reference_points = reference_points.float().contiguous()
         merged = merged.float().contiguous()
         ctx.lp = (int(n_levels), int(n_points))
