@@ -440,22 +440,6 @@ static cudaError_t launch_fused_g(const Params& p, dim3 grid, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-// fused entry: `p.grad_value` is the zero-filled fp32 accumulator (as in launch_backward)
-cudaError_t launch_backward_fused(const Params& p, int dtype, int G, cudaStream_t s) {
-  const dim3 grid((unsigned)((size_t)p.N * p.nchunk * p.M));
-  if (dtype == MSDA_F32) {
-    if (G == 8) return launch_fused_g<float, 8>(p, grid, s);
-    if (G == 16) return launch_fused_g<float, 16>(p, grid, s);
-  } else if (dtype == MSDA_BF16) {
-    if (G == 8) return launch_fused_g<__nv_bfloat16, 8>(p, grid, s);
-    if (G == 16) return launch_fused_g<__nv_bfloat16, 16>(p, grid, s);
-  } else if (dtype == MSDA_F16) {
-    if (G == 8) return launch_fused_g<__half, 8>(p, grid, s);
-    if (G == 16) return launch_fused_g<__half, 16>(p, grid, s);
-  }
-  return cudaErrorNotSupported;
-}
-
 template <typename T>
 static cudaError_t launch_vec(const Params& p, int G, int minb, dim3 grid, cudaStream_t s) {
   switch (G) {
@@ -468,19 +452,75 @@ static cudaError_t launch_vec(const Params& p, int G, int minb, dim3 grid, cudaS
   }
 }
 
-// `p.grad_value` must point at the ACCUMULATOR (T storage for f32/f64, fp32 scratch for bf16),
+template <typename T>
+static cudaError_t launch_fused_t(const Params& p, int G, dim3 grid, cudaStream_t s) {
+  if (G == 8) return launch_fused_g<T, 8>(p, grid, s);
+  if (G == 16) return launch_fused_g<T, 16>(p, grid, s);
+  return cudaErrorNotSupported;
+}
+
+template <typename TO>
+static cudaError_t launch_cvt_t(const float* src, void* dst, size_t n, cudaStream_t s) {
+  size_t blocks = (n / 8 + kThreads - 1) / kThreads;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148u * 16u) blocks = 148u * 16u;
+  msda_cvt_f32_bf16_kernel<TO><<<(unsigned)blocks, kThreads, 0, s>>>(src, reinterpret_cast<TO*>(dst), n);
+  return cudaGetLastError();
+}
+
+// The file is compiled once per value dtype (build.py: -DMSDA_TU=0 f32 + f64 + dispatch, 1 bf16, 2 f16) so that the three
+// sets of instantiations build in parallel; each part exports its entry points under a dtype suffix.
+#ifndef MSDA_TU
+#define MSDA_TU 0
+#endif
+cudaError_t bwd_vec_bf16(const Params& p, int G, int minb, dim3 grid, cudaStream_t s);
+cudaError_t bwd_fused_bf16(const Params& p, int G, dim3 grid, cudaStream_t s);
+cudaError_t bwd_generic_bf16(const Params& p, dim3 grid, cudaStream_t s);
+cudaError_t bwd_cvt_bf16(const float* src, void* dst, size_t n, cudaStream_t s);
+cudaError_t bwd_vec_f16(const Params& p, int G, int minb, dim3 grid, cudaStream_t s);
+cudaError_t bwd_fused_f16(const Params& p, int G, dim3 grid, cudaStream_t s);
+cudaError_t bwd_generic_f16(const Params& p, dim3 grid, cudaStream_t s);
+cudaError_t bwd_cvt_f16(const float* src, void* dst, size_t n, cudaStream_t s);
+
+#if MSDA_TU == 1
+cudaError_t bwd_vec_bf16(const Params& p, int G, int minb, dim3 grid, cudaStream_t s) { return launch_vec<__nv_bfloat16>(p, G, minb, grid, s); }
+cudaError_t bwd_fused_bf16(const Params& p, int G, dim3 grid, cudaStream_t s) { return launch_fused_t<__nv_bfloat16>(p, G, grid, s); }
+cudaError_t bwd_generic_bf16(const Params& p, dim3 grid, cudaStream_t s) {
+  msda_bwd_generic_kernel<__nv_bfloat16, float, float><<<grid, kThreads, 0, s>>>(p);
+  return cudaGetLastError();
+}
+cudaError_t bwd_cvt_bf16(const float* src, void* dst, size_t n, cudaStream_t s) { return launch_cvt_t<__nv_bfloat16>(src, dst, n, s); }
+#elif MSDA_TU == 2
+cudaError_t bwd_vec_f16(const Params& p, int G, int minb, dim3 grid, cudaStream_t s) { return launch_vec<__half>(p, G, minb, grid, s); }
+cudaError_t bwd_fused_f16(const Params& p, int G, dim3 grid, cudaStream_t s) { return launch_fused_t<__half>(p, G, grid, s); }
+cudaError_t bwd_generic_f16(const Params& p, dim3 grid, cudaStream_t s) {
+  msda_bwd_generic_kernel<__half, float, float><<<grid, kThreads, 0, s>>>(p);
+  return cudaGetLastError();
+}
+cudaError_t bwd_cvt_f16(const float* src, void* dst, size_t n, cudaStream_t s) { return launch_cvt_t<__half>(src, dst, n, s); }
+#else
+// fused entry: `p.grad_value` is the zero-filled fp32 accumulator (as in launch_backward)
+cudaError_t launch_backward_fused(const Params& p, int dtype, int G, cudaStream_t s) {
+  const dim3 grid((unsigned)((size_t)p.N * p.nchunk * p.M));
+  if (dtype == MSDA_F32) return launch_fused_t<float>(p, G, grid, s);
+  if (dtype == MSDA_BF16) return bwd_fused_bf16(p, G, grid, s);
+  if (dtype == MSDA_F16) return bwd_fused_f16(p, G, grid, s);
+  return cudaErrorNotSupported;
+}
+
+// `p.grad_value` must point at the ACCUMULATOR (T storage for f32/f64, fp32 scratch for bf16 / f16),
 // already zero-filled on `s`.
 cudaError_t launch_backward(const Params& p, int dtype, bool vec_ok, int G, int minb, cudaStream_t s) {
   const dim3 grid((unsigned)((size_t)p.N * p.nchunk * p.M));
   if (vec_ok) {
     if (dtype == MSDA_F32) return launch_vec<float>(p, G, minb, grid, s);
-    if (dtype == MSDA_F16) return launch_vec<__half>(p, G, minb, grid, s);
-    return launch_vec<__nv_bfloat16>(p, G, minb, grid, s);
+    if (dtype == MSDA_F16) return bwd_vec_f16(p, G, minb, grid, s);
+    return bwd_vec_bf16(p, G, minb, grid, s);
   }
   switch (dtype) {
     case MSDA_F32: msda_bwd_generic_kernel<float, float, float><<<grid, kThreads, 0, s>>>(p); break;
-    case MSDA_BF16: msda_bwd_generic_kernel<__nv_bfloat16, float, float><<<grid, kThreads, 0, s>>>(p); break;
-    case MSDA_F16: msda_bwd_generic_kernel<__half, float, float><<<grid, kThreads, 0, s>>>(p); break;
+    case MSDA_BF16: return bwd_generic_bf16(p, grid, s);
+    case MSDA_F16: return bwd_generic_f16(p, grid, s);
     case MSDA_F64: msda_bwd_generic_kernel<double, double, double><<<grid, kThreads, 0, s>>>(p); break;
     default: return cudaErrorInvalidValue;
   }
@@ -488,14 +528,8 @@ cudaError_t launch_backward(const Params& p, int dtype, bool vec_ok, int G, int 
 }
 
 cudaError_t launch_cvt_f32_bf16(const float* src, void* dst, size_t n, int dtype, cudaStream_t s) {
-  size_t blocks = (n / 8 + kThreads - 1) / kThreads;
-  if (blocks < 1) blocks = 1;
-  if (blocks > 148u * 16u) blocks = 148u * 16u;
-  if (dtype == MSDA_F16)
-    msda_cvt_f32_bf16_kernel<__half><<<(unsigned)blocks, kThreads, 0, s>>>(src, reinterpret_cast<__half*>(dst), n);
-  else
-    msda_cvt_f32_bf16_kernel<__nv_bfloat16><<<(unsigned)blocks, kThreads, 0, s>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
-  return cudaGetLastError();
+  return dtype == MSDA_F16 ? bwd_cvt_f16(src, dst, n, s) : bwd_cvt_bf16(src, dst, n, s);
 }
+#endif  // MSDA_TU
 
 }  // namespace msda

@@ -233,6 +233,65 @@ static cudaError_t launch_vec_g(const Params& p, int minb, dim3 grid, cudaStream
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The file is compiled once per value dtype (build.py: -DMSDA_TU=0 f32 + f64 + dispatch, 1 bf16, 2 f16) so that the
+// three sets of instantiations build in parallel; each part exports its entry points under a dtype suffix.
+// ---------------------------------------------------------------------------------------------
+#ifndef MSDA_TU
+#define MSDA_TU 0
+#endif
+
+// fused entry (raw offsets + logits + reference points): static (L,P) in {(3,4),(1,4)} only
+template <typename T, int G>
+static cudaError_t launch_fused_g(const Params& p, dim3 grid, cudaStream_t s) {
+  if (p.L == 3 && p.P == 4) msda_fwd_vec_kernel<T, G, 3, 4, 4, 16, true><<<grid, kThreads, 0, s>>>(p);
+  else if (p.L == 1 && p.P == 4) msda_fwd_vec_kernel<T, G, 1, 4, 4, 16, true><<<grid, kThreads, 0, s>>>(p);
+  else return cudaErrorNotSupported;
+  return cudaGetLastError();
+}
+
+template <typename T>
+static cudaError_t launch_vec(const Params& p, int G, int minb, dim3 grid, cudaStream_t s) {
+  switch (G) {
+    case 2: return launch_vec_gm<T, 2, 4>(p, grid, s);
+    case 4: return launch_vec_g<T, 4>(p, minb, grid, s);
+    case 8: return launch_vec_g<T, 8>(p, minb, grid, s);
+    case 16: return launch_vec_g<T, 16>(p, minb, grid, s);
+    case 32: return launch_vec_gm<T, 32, 4>(p, grid, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// 16-bit value types: 8 channels per lane -> fused kernels at G = 4 (D = 32) and 8 (D = 64)
+template <typename T>
+static cudaError_t launch_fused_lowp(const Params& p, int G, dim3 grid, cudaStream_t s) {
+  if (G == 4) return launch_fused_g<T, 4>(p, grid, s);
+  if (G == 8) return launch_fused_g<T, 8>(p, grid, s);
+  return cudaErrorNotSupported;
+}
+
+cudaError_t fwd_vec_bf16(const Params& p, int G, int minb, dim3 grid, cudaStream_t s);
+cudaError_t fwd_fused_bf16(const Params& p, int G, dim3 grid, cudaStream_t s);
+cudaError_t fwd_generic_bf16(const Params& p, dim3 grid, cudaStream_t s);
+cudaError_t fwd_vec_f16(const Params& p, int G, int minb, dim3 grid, cudaStream_t s);
+cudaError_t fwd_fused_f16(const Params& p, int G, dim3 grid, cudaStream_t s);
+cudaError_t fwd_generic_f16(const Params& p, dim3 grid, cudaStream_t s);
+
+#if MSDA_TU == 1
+cudaError_t fwd_vec_bf16(const Params& p, int G, int minb, dim3 grid, cudaStream_t s) { return launch_vec<__nv_bfloat16>(p, G, minb, grid, s); }
+cudaError_t fwd_fused_bf16(const Params& p, int G, dim3 grid, cudaStream_t s) { return launch_fused_lowp<__nv_bfloat16>(p, G, grid, s); }
+cudaError_t fwd_generic_bf16(const Params& p, dim3 grid, cudaStream_t s) {
+  msda_fwd_generic_kernel<__nv_bfloat16, float><<<grid, kThreads, 0, s>>>(p);
+  return cudaGetLastError();
+}
+#elif MSDA_TU == 2
+cudaError_t fwd_vec_f16(const Params& p, int G, int minb, dim3 grid, cudaStream_t s) { return launch_vec<__half>(p, G, minb, grid, s); }
+cudaError_t fwd_fused_f16(const Params& p, int G, dim3 grid, cudaStream_t s) { return launch_fused_lowp<__half>(p, G, grid, s); }
+cudaError_t fwd_generic_f16(const Params& p, dim3 grid, cudaStream_t s) {
+  msda_fwd_generic_kernel<__half, float><<<grid, kThreads, 0, s>>>(p);
+  return cudaGetLastError();
+}
+#else
 // 32-byte lanes (fp32): G = D / 8
 template <int G>
 static cudaError_t launch_wide_g(const Params& p, int minb, dim3 grid, cudaStream_t s) {
@@ -258,40 +317,17 @@ cudaError_t launch_forward_wide(const Params& p, int G, int minb, cudaStream_t s
   }
 }
 
-// fused entry (raw offsets + logits + reference points): static (L,P) in {(3,4),(1,4)} only
-template <typename T, int G>
-static cudaError_t launch_fused_g(const Params& p, dim3 grid, cudaStream_t s) {
-  if (p.L == 3 && p.P == 4) msda_fwd_vec_kernel<T, G, 3, 4, 4, 16, true><<<grid, kThreads, 0, s>>>(p);
-  else if (p.L == 1 && p.P == 4) msda_fwd_vec_kernel<T, G, 1, 4, 4, 16, true><<<grid, kThreads, 0, s>>>(p);
-  else return cudaErrorNotSupported;
-  return cudaGetLastError();
-}
-
 cudaError_t launch_forward_fused(const Params& p, int dtype, int G, cudaStream_t s) {
   const dim3 grid((unsigned)((size_t)p.N * p.nchunk * p.M));
   if (dtype == MSDA_F32) {
     if (G == 8) return launch_fused_g<float, 8>(p, grid, s);
     if (G == 16) return launch_fused_g<float, 16>(p, grid, s);
   } else if (dtype == MSDA_F16) {
-    if (G == 4) return launch_fused_g<__half, 4>(p, grid, s);
-    if (G == 8) return launch_fused_g<__half, 8>(p, grid, s);
+    return fwd_fused_f16(p, G, grid, s);
   } else if (dtype == MSDA_BF16) {
-    if (G == 4) return launch_fused_g<__nv_bfloat16, 4>(p, grid, s);
-    if (G == 8) return launch_fused_g<__nv_bfloat16, 8>(p, grid, s);
+    return fwd_fused_bf16(p, G, grid, s);
   }
   return cudaErrorNotSupported;
-}
-
-template <typename T>
-static cudaError_t launch_vec(const Params& p, int G, int minb, dim3 grid, cudaStream_t s) {
-  switch (G) {
-    case 2: return launch_vec_gm<T, 2, 4>(p, grid, s);
-    case 4: return launch_vec_g<T, 4>(p, minb, grid, s);
-    case 8: return launch_vec_g<T, 8>(p, minb, grid, s);
-    case 16: return launch_vec_g<T, 16>(p, minb, grid, s);
-    case 32: return launch_vec_gm<T, 32, 4>(p, grid, s);
-    default: return cudaErrorInvalidValue;
-  }
 }
 
 // Returns true when the vector kernels support (dtype, D): D*sizeof(T) is a multiple of 16 bytes and
@@ -309,17 +345,18 @@ cudaError_t launch_forward(const Params& p, int dtype, bool vec_ok, int G, int m
   const dim3 grid((unsigned)((size_t)p.N * p.nchunk * p.M));
   if (vec_ok) {
     if (dtype == MSDA_F32) return launch_vec<float>(p, G, minb, grid, s);
-    if (dtype == MSDA_F16) return launch_vec<__half>(p, G, minb, grid, s);
-    return launch_vec<__nv_bfloat16>(p, G, minb, grid, s);
+    if (dtype == MSDA_F16) return fwd_vec_f16(p, G, minb, grid, s);
+    return fwd_vec_bf16(p, G, minb, grid, s);
   }
   switch (dtype) {
     case MSDA_F32: msda_fwd_generic_kernel<float, float><<<grid, kThreads, 0, s>>>(p); break;
-    case MSDA_BF16: msda_fwd_generic_kernel<__nv_bfloat16, float><<<grid, kThreads, 0, s>>>(p); break;
-    case MSDA_F16: msda_fwd_generic_kernel<__half, float><<<grid, kThreads, 0, s>>>(p); break;
+    case MSDA_BF16: return fwd_generic_bf16(p, grid, s);
+    case MSDA_F16: return fwd_generic_f16(p, grid, s);
     case MSDA_F64: msda_fwd_generic_kernel<double, double><<<grid, kThreads, 0, s>>>(p); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
 }
+#endif  // MSDA_TU
 
 }  // namespace msda
