@@ -1,0 +1,134 @@
+"""GPU parity tests of the cell-bucketed backward (csrc/msda_bwd_cell.cu) against the C oracle, the general
+(query-order) backward of the same library and, where built, the reference's own CUDA kernels.
+
+The cell kernel is opt-in for D in {32, 64} (`set_tuning(bwd_cell=2)`; it measured slower than the query-order kernel);
+`bwd_cell_chunk=n` forces short query chunks so that chunk boundaries, partially filled batches of 32 and cell runs that straddle two
+warps are all exercised on small inputs. Tolerances: fp32 gradients 1e-4 relative (summation order), bf16 1e-2."""
+import pytest
+import torch
+
+from conftest import make_inputs
+from oracle import c_oracle, refcuda
+
+import vit_adapter_b200 as vab
+from vit_adapter_b200 import _cabi
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _scale(t):
+    return float(t.abs().max()) + 1e-30
+
+
+def _bwd(inp, dtype, **tuning):
+    g = {k: v.to(DEV) for k, v in inp.items()}
+    _cabi.set_tuning(**tuning)
+    try:
+        gv, gl, ga = _cabi.backward(g['value'].to(dtype), g['shapes'], g['lsi'], g['loc'], g['aw'], g['grad_out'].to(dtype), 64)
+        torch.cuda.synchronize()
+    finally:
+        _cabi.set_tuning(**{k: 0 for k in tuning})
+    return gv.float().cpu(), gl.cpu(), ga.cpu()
+
+
+CASES = [
+    # name, N, M, D, Lq, shapes, P, dist
+    ('B-injector', 2, 12, 32, 256, [(32, 32), (16, 16), (8, 8)], 4, 'adapter'),
+    ('B-extractor', 2, 12, 32, 1344, [(16, 16)], 4, 'adapter'),
+    ('S-injector-d64', 2, 6, 64, 256, [(32, 32), (16, 16), (8, 8)], 4, 'adapter'),
+    ('edges-3lvl', 1, 16, 32, 196, [(28, 28), (14, 14), (7, 7)], 4, 'edges'),
+    ('uniform-d64', 1, 16, 64, 196, [(28, 28), (14, 14), (7, 7)], 4, 'uniform'),
+    ('ragged-runtime-LP', 3, 5, 32, 37, [(7, 9), (3, 4), (1, 1), (2, 5)], 3, 'edges'),
+    ('one-query', 1, 1, 32, 1, [(2, 2)], 1, 'edges'),
+    ('p8-one-level', 2, 3, 64, 45, [(12, 10)], 8, 'edges'),
+    ('tiny-map-many-points', 1, 2, 32, 700, [(2, 3)], 4, 'uniform'),   # ~470 points per cell: long runs, hot ATOMS keys
+    ('wide-row', 1, 2, 32, 90, [(1, 40), (40, 1)], 4, 'edges'),
+]
+
+
+@pytest.mark.parametrize('chunk', [0, 7, 33], ids=['chunk-auto', 'chunk-7', 'chunk-33'])
+@pytest.mark.parametrize('cfg', CASES, ids=[c[0] for c in CASES])
+def test_cell_backward_vs_oracle_f32(cfg, chunk):
+    _, N, M, D, Lq, shapes, P, dist = cfg
+    inp = make_inputs(N, M, D, Lq, shapes, P, seed=11, dist=dist)
+    wgv, wgl, wga = c_oracle.backward(inp['value'], inp['shapes'], inp['lsi'], inp['loc'], inp['aw'], inp['grad_out'])
+    gv, gl, ga = _bwd(inp, torch.float32, bwd_cell=2, bwd_cell_chunk=chunk)
+    torch.testing.assert_close(gv, wgv, rtol=1e-4, atol=1e-4 * _scale(wgv))
+    torch.testing.assert_close(gl, wgl, rtol=1e-4, atol=1e-4 * _scale(wgl))
+    torch.testing.assert_close(ga, wga, rtol=1e-4, atol=1e-4 * _scale(wga))
+    # and against the query-order kernel of this library (same tolerance: only the summation order differs)
+    ogv, ogl, oga = _bwd(inp, torch.float32, bwd_cell=1)
+    torch.testing.assert_close(gv, ogv, rtol=1e-4, atol=1e-4 * _scale(ogv))
+    torch.testing.assert_close(gl, ogl, rtol=1e-4, atol=1e-4 * _scale(ogl))
+    torch.testing.assert_close(ga, oga, rtol=1e-4, atol=1e-4 * _scale(oga))
+
+
+@pytest.mark.parametrize('low', [torch.bfloat16, torch.float16], ids=['bf16', 'f16'])
+@pytest.mark.parametrize('cfg', CASES[:6], ids=[c[0] for c in CASES[:6]])
+def test_cell_backward_vs_oracle_16bit(cfg, low):
+    _, N, M, D, Lq, shapes, P, dist = cfg
+    inp = make_inputs(N, M, D, Lq, shapes, P, seed=12, dist=dist)
+    vq, goq = inp['value'].to(low).float(), inp['grad_out'].to(low).float()
+    wgv, wgl, wga = c_oracle.backward(vq, inp['shapes'], inp['lsi'], inp['loc'], inp['aw'], goq)
+    tol = 1e-2 if low == torch.bfloat16 else 2e-3
+    gv, gl, ga = _bwd(inp, low, bwd_cell=2, bwd_cell_chunk=19)
+    torch.testing.assert_close(gv, wgv, rtol=tol, atol=tol * _scale(wgv))
+    # location / weight gradients are fp32 sums of exactly representable products: fp32-grade agreement
+    torch.testing.assert_close(gl, wgl, rtol=1e-4, atol=1e-4 * _scale(wgl))
+    torch.testing.assert_close(ga, wga, rtol=1e-4, atol=1e-4 * _scale(wga))
+
+
+def test_cell_backward_out_of_range_points_get_zero_gradients():
+    inp = make_inputs(1, 2, 32, 40, [(5, 6), (3, 3)], 4, seed=13, dist='uniform')
+    inp['loc'][:, ::2] = 7.5          # every other query samples far outside the maps
+    inp['loc'][:, 1, :, :, 0] = -3.0
+    gv, gl, ga = _bwd(inp, torch.float32, bwd_cell=2)
+    wgv, wgl, wga = c_oracle.backward(inp['value'], inp['shapes'], inp['lsi'], inp['loc'], inp['aw'], inp['grad_out'])
+    assert float(gl[:, ::2].abs().max()) == 0.0 and float(ga[:, ::2].abs().max()) == 0.0
+    torch.testing.assert_close(gv, wgv, rtol=1e-4, atol=1e-4 * _scale(wgv))
+    torch.testing.assert_close(gl, wgl, rtol=1e-4, atol=1e-4 * _scale(wgl))
+    torch.testing.assert_close(ga, wga, rtol=1e-4, atol=1e-4 * _scale(wga))
+    # nothing in range at all: grad_value stays zero, the other gradients are written (not left uninitialised)
+    inp['loc'][:] = 9.0
+    gv, gl, ga = _bwd(inp, torch.float32, bwd_cell=2)
+    assert float(gv.abs().max()) == 0.0 and float(gl.abs().max()) == 0.0 and float(ga.abs().max()) == 0.0
+
+
+def test_cell_backward_all_points_in_one_cell():
+    """Every sample of every query lands in the same bilinear cell: one run per warp range, hot counters."""
+    inp = make_inputs(2, 4, 32, 333, [(9, 9)], 4, seed=14, dist='uniform')
+    inp['loc'] = (0.5 + 0.02 * (inp['loc'] - 0.5)).contiguous()
+    gv, gl, ga = _bwd(inp, torch.float32, bwd_cell=2)
+    wgv, wgl, wga = c_oracle.backward(inp['value'], inp['shapes'], inp['lsi'], inp['loc'], inp['aw'], inp['grad_out'])
+    torch.testing.assert_close(gv, wgv, rtol=1e-4, atol=1e-4 * _scale(wgv))
+    torch.testing.assert_close(gl, wgl, rtol=1e-4, atol=1e-4 * _scale(wgl))
+    torch.testing.assert_close(ga, wga, rtol=1e-4, atol=1e-4 * _scale(wga))
+
+
+@pytest.mark.skipif(not refcuda.available(), reason='oracle/_ref not built')
+@pytest.mark.parametrize('cfg', CASES[:5], ids=[c[0] for c in CASES[:5]])
+def test_cell_backward_vs_reference_cuda(cfg):
+    _, N, M, D, Lq, shapes, P, dist = cfg
+    inp = make_inputs(N, M, D, Lq, shapes, P, seed=15, dist=dist)
+    g = {k: v.to(DEV) for k, v in inp.items()}
+    rgv, rgl, rga = refcuda.backward(g['value'], g['shapes'], g['lsi'], g['loc'], g['aw'], g['grad_out'])
+    gv, gl, ga = _bwd(inp, torch.float32, bwd_cell=2, bwd_cell_chunk=50)
+    torch.testing.assert_close(gv, rgv.cpu(), rtol=1e-4, atol=1e-4 * _scale(rgv))
+    torch.testing.assert_close(gl, rgl.cpu(), rtol=1e-4, atol=1e-4 * _scale(rgl))
+    torch.testing.assert_close(ga, rga.cpu(), rtol=1e-4, atol=1e-4 * _scale(rga))
+
+
+def test_cell_backward_is_opt_in():
+    """Without tuning the query-order kernel runs (the cell kernel measured slower); with bwd_cell=2 the
+    cell kernel runs. Both are one launch per call and agree to summation order."""
+    inp = make_inputs(2, 12, 32, 256, [(32, 32), (16, 16), (8, 8)], 4, seed=16, dist='adapter')
+    n0 = _cabi.launch_count()
+    gv, gl, ga = _bwd(inp, torch.float32)
+    assert _cabi.launch_count() - n0 == 1
+    dgv, dgl, dga = _bwd(inp, torch.float32, bwd_cell=1)
+    assert torch.equal(gl, dgl) and torch.equal(ga, dga)   # same kernel: deterministic outputs are bit-identical
+    cgv, cgl, cga = _bwd(inp, torch.float32, bwd_cell=2)
+    torch.testing.assert_close(cgv, gv, rtol=1e-4, atol=1e-4 * _scale(gv))
+    torch.testing.assert_close(cgl, gl, rtol=1e-4, atol=1e-4 * _scale(gl))
+    torch.testing.assert_close(cga, ga, rtol=1e-4, atol=1e-4 * _scale(ga))

@@ -12,12 +12,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'lib')
 LIBNAME = 'libmsda_b200.so'
-SOURCES = ['msda_fwd.cu', 'msda_fwd_smem.cu', 'msda_bwd.cu', 'adapter_dwconv.cu', 'adapter_layernorm.cu', 'adapter_colsum.cu', 'adapter_residual.cu', 'msda_abi.cu']
+SOURCES = ['msda_fwd.cu', 'msda_fwd_smem.cu', 'msda_bwd.cu', 'msda_bwd_cell.cu', 'adapter_dwconv.cu', 'adapter_layernorm.cu', 'adapter_colsum.cu', 'adapter_residual.cu', 'msda_abi.cu']
 # (source, extra flags, object name): msda_fwd.cu / msda_bwd.cu are compiled once per value dtype so that the three sets
 # of template instantiations build in parallel (MSDA_TU = 0: f32 + f64 + dispatch, 1: bf16, 2: f16)
 UNITS = [(s, [], s.replace('.cu', '.o')) for s in SOURCES] + [
     ('msda_fwd.cu', ['-DMSDA_TU=1'], 'msda_fwd_bf16.o'), ('msda_fwd.cu', ['-DMSDA_TU=2'], 'msda_fwd_f16.o'),
-    ('msda_bwd.cu', ['-DMSDA_TU=1'], 'msda_bwd_bf16.o'), ('msda_bwd.cu', ['-DMSDA_TU=2'], 'msda_bwd_f16.o')]
+    ('msda_bwd.cu', ['-DMSDA_TU=1'], 'msda_bwd_bf16.o'), ('msda_bwd.cu', ['-DMSDA_TU=2'], 'msda_bwd_f16.o'),
+    ('msda_bwd_cell.cu', ['-DMSDA_TU=1'], 'msda_bwd_cell_bf16.o'), ('msda_bwd_cell.cu', ['-DMSDA_TU=2'], 'msda_bwd_cell_f16.o')]
 HEADERS = ['msda_common.cuh', os.path.join('..', '..', 'include', 'msda_b200.h')]
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',

@@ -53,12 +53,19 @@ bool colsum_supported(int dtype, int C);
 size_t colsum_workspace_bytes(int dtype, long long rows, int C);
 cudaError_t launch_colsum(int dtype, const void* x, long long rows, int C, float* out, float* partial, cudaStream_t s);
 cudaError_t launch_forward_wide(const Params& p, int G, int minb, cudaStream_t s);
+struct CellPlan {
+  unsigned off_tl, off_go, off_scr, off_ubuf, off_hist, total;
+  int hist_cap;
+};
+int backward_cell_max_points();
+bool plan_backward_cell(int D, int LP, int esize, int qc, int hist_cap, unsigned budget, CellPlan* cp);
+cudaError_t launch_backward_cell(const Params& p, const CellPlan& cp, int dtype, cudaStream_t s);
 cudaError_t launch_forward_smem(const Params& p, const SmemPlan& plan, int dtype, int G, int nt, cudaStream_t s);
 
 static thread_local char g_err[512] = "";
 constexpr bool kFwdWideDefault = false;  // flipped once measured faster (tuning key "fwd_wide" = 2 forces it)
 static std::atomic<uint64_t> g_launches{0};
-static std::atomic<int> g_qc_fwd{0}, g_qc_bwd{0}, g_minb_fwd{0}, g_minb_bwd{0}, g_smem_mode{0}, g_smem_nt{0}, g_smem_chunks{0}, g_fwd_wide{0};
+static std::atomic<int> g_qc_fwd{0}, g_qc_bwd{0}, g_minb_fwd{0}, g_minb_bwd{0}, g_smem_mode{0}, g_smem_nt{0}, g_smem_chunks{0}, g_fwd_wide{0}, g_bwd_cell{0}, g_bwd_cell_qc{0};
 
 static int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -98,6 +105,19 @@ static int check_dims(const msda_dims* d, int dtype) {
 
 static bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
+// SMs of the current device (cudaDevAttrMultiProcessorCount, cached per device ordinal).
+static int sm_count() {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int n = cache[dev].load();
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev].store(n);
+  }
+  return n;
+}
+
 // queries per CTA chunk: enough CTAs to fill 148 SMs x ~8 resident CTAs, chunks as long as possible
 // otherwise (longer chunk = more L1 reuse of the value rows around neighbouring queries).
 static int pick_chunk(const msda_dims* d, int per_iter, int override_qc) {
@@ -106,7 +126,7 @@ static int pick_chunk(const msda_dims* d, int per_iter, int override_qc) {
     qc = override_qc;
   } else {
     const int64_t bm = (int64_t)d->batch * d->num_heads;
-    const int64_t target_ctas = 148 * 8;
+    const int64_t target_ctas = (int64_t)sm_count() * 8;
     int64_t chunks = (target_ctas + bm - 1) / bm;
     if (chunks < 1) chunks = 1;
     qc = (int)((d->num_query + chunks - 1) / chunks);
@@ -198,6 +218,55 @@ static bool plan_forward_smem(const msda_dims* d, int dtype, int G, const int64_
   return true;
 }
 
+// Cell-bucketed backward (msda_bwd_cell.cu): queries per chunk, histogram window and the shared-memory plan. The chunk is
+// made as long as the shared memory of a CTA allows at 3 (else 2, else 1) resident CTAs per SM - longer chunks mean longer
+// runs of points per bilinear cell - then shortened while the grid would leave SMs idle.
+static bool plan_cell(const msda_dims* d, int dtype, Params& p, CellPlan* cp) {
+  // MEASURED OUTCOME (profiles/r2_bwd_cell_*.{json,txt}): the cell-bucketed backward cuts the row atomics that reach the L2
+  // 3.5x (58 M -> 17 M RED sectors at ViT-Adapter-B bs 16) but spends as many instructions per point on bucketing and
+  // record handling as the query-order kernel spends on its gathers, at fewer eligible warps: 360 vs 320 us (Extractor),
+  // 335 vs 240 us (Injector). So it is OPT-IN (tuning key "bwd_cell" = 2); 0 / 1 = off.
+  const int mode = g_bwd_cell.load();
+  if (mode != 2) return false;
+  if (!(dtype == MSDA_F32 || dtype == MSDA_BF16 || dtype == MSDA_F16)) return false;
+  if (!(d->channels == 32 || d->channels == 64)) return false;
+  if (d->spatial_size >= (1 << 19)) return false;  // cell words keep the corner token in 20 bits
+  const int LP = d->num_levels * d->num_point, es = (int)elem_size(dtype);
+  const int max_qc = backward_cell_max_points() / LP;
+  if (max_qc < 1) return false;
+  // 228 KB per SM, 1 KB reserved per resident CTA, a few hundred bytes of static shared memory
+  const unsigned budgets[3] = {74u * 1024u, 112u * 1024u, 226u * 1024u};
+  const int per_cta[3] = {3, 2, 1};
+  const int forced = g_bwd_cell_qc.load();
+  const int hist_cap = d->spatial_size < 4096 ? d->spatial_size : 4096;  // one key window; larger bands take several
+  for (int t = 0; t < 3; ++t) {
+    int lo = forced > 0 ? forced : 1;
+    if (lo > d->num_query) lo = d->num_query;
+    if (lo > max_qc) lo = max_qc;
+    CellPlan probe;
+    if (!plan_backward_cell(d->channels, LP, es, lo, hist_cap, budgets[t], &probe)) continue;
+    int qc = lo;
+    if (forced <= 0) {
+      const long long per_q = (long long)LP * 20 + (long long)d->channels * es;
+      qc = (int)(lo + ((long long)budgets[t] - (long long)probe.total) / per_q);
+      if (qc > d->num_query) qc = d->num_query;
+      if (qc > max_qc) qc = max_qc;
+      while (qc > lo && !plan_backward_cell(d->channels, LP, es, qc, hist_cap, budgets[t], &probe)) --qc;  // rounding slack
+      // keep every SM busy for at least two rounds of resident CTAs when the problem is large enough
+      const long long want = 2ll * sm_count() * per_cta[t];
+      const long long bm = (long long)d->batch * d->num_heads;
+      while (qc > 64 && bm * ((d->num_query + qc - 1) / qc) < want) qc = (qc + 1) / 2;
+      const int nchunk = (d->num_query + qc - 1) / qc;
+      qc = (d->num_query + nchunk - 1) / nchunk;  // equal chunks
+    }
+    if (!plan_backward_cell(d->channels, LP, es, qc, hist_cap, budgets[t], cp)) continue;
+    p.qc = qc;
+    p.nchunk = (d->num_query + qc - 1) / qc;
+    return true;
+  }
+  return false;
+}
+
 static void fill_params(Params& p, const msda_dims* d) {
   memset(&p, 0, sizeof(p));
   p.N = d->batch; p.S = d->spatial_size; p.M = d->num_heads; p.D = d->channels;
@@ -243,6 +312,8 @@ int msda_set_tuning(const char* key, int32_t value) {
   else if (!strcmp(key, "fwd_smem_threads")) slot = &g_smem_nt;
   else if (!strcmp(key, "fwd_smem_chunks")) slot = &g_smem_chunks;
   else if (!strcmp(key, "fwd_wide")) slot = &g_fwd_wide;
+  else if (!strcmp(key, "bwd_cell")) slot = &g_bwd_cell;
+  else if (!strcmp(key, "bwd_cell_chunk")) slot = &g_bwd_cell_qc;
   if (!slot) return fail(MSDA_E_NULL, "msda_set_tuning: unknown key '%s'", key);
   slot->store(value);
   return 0;
@@ -365,8 +436,14 @@ int msda_backward(const msda_dims* dims, int dtype, const void* value, const int
 
   cudaError_t e = cudaMemsetAsync(accum, 0, accum_bytes, s);
   if (e != cudaSuccess) return cuda_fail(e, "msda_backward memset(grad_value)");
-  e = launch_backward(p, dtype, vec, G, g_minb_bwd.load(), s);
-  if (e != cudaSuccess) return cuda_fail(e, "msda_backward launch");
+  CellPlan cplan;
+  if (vec && plan_cell(dims, dtype, p, &cplan)) {
+    e = launch_backward_cell(p, cplan, dtype, s);
+    if (e != cudaSuccess) return cuda_fail(e, "msda_backward (cell-bucketed) launch");
+  } else {
+    e = launch_backward(p, dtype, vec, G, g_minb_bwd.load(), s);
+    if (e != cudaSuccess) return cuda_fail(e, "msda_backward launch");
+  }
   g_launches.fetch_add(1);
   if (lowp) {
     e = launch_cvt_f32_bf16(reinterpret_cast<const float*>(accum), grad_value, nvalue, dtype, s);
