@@ -18,7 +18,9 @@
  *     cudaError_t for CUDA runtime/launch errors (the reference only printf()s launch errors,
  *     ms_deform_im2col_cuda.cuh:948-952,1321-1325; here they are surfaced).
  *     msda_last_error() returns a thread-local human-readable message for the last failure.
- *   - Thread-safe and re-entrant; no global mutable state.
+ *   - Thread-safe and re-entrant. The only process-wide mutable state is (a) the benchmark knobs of msda_set_tuning()
+ *     (atomics; 0 = heuristic, never needed for correctness), (b) the launch counter of msda_launch_count() and (c) a
+ *     per-device cache of the SM count. Results never depend on any of them beyond the summation order of atomics.
  *
  * Tensor layouts (identical to the reference, ms_deform_attn_func.py:20-33):
  *   value              [N, S, M, D]        dtype T   (T = f32 | bf16 | f16 | f64)

@@ -133,6 +133,75 @@ def module_case(ref_mod, name, d_model, n_levels, n_heads, n_points, ratio, N, L
     print(name)
 
 
+def module_grad_case(ref_mod, name, d_model, n_levels, n_heads, n_points, ratio, N, Lq, shapes, seed, ref_levels):
+    """The reference MSDeformAttn module forward AND backward (fp64 autograd through its own pure-PyTorch core):
+    gradients w.r.t. query, feat and every parameter, for a given grad_out. Reference points as the adapter passes them
+    ([1, Lq, 1, 2], broadcast over batch and levels) or per level."""
+    torch.manual_seed(seed)
+    m = ref_mod.MSDeformAttn(d_model, n_levels, n_heads, n_points, ratio).double()
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(torch.randn_like(p) * 0.05)
+    shapes = torch.as_tensor(shapes, dtype=torch.long)
+    S = int(shapes.prod(1).sum())
+    query = torch.randn(N, Lq, d_model, dtype=torch.double, requires_grad=True)
+    feat = torch.randn(N, S, d_model, dtype=torch.double, requires_grad=True)
+    ref_pts = torch.rand(1, Lq, ref_levels, 2, dtype=torch.double)
+    grad_out = torch.randn(N, Lq, d_model, dtype=torch.double)
+    out = m(query, ref_pts, feat, shapes, level_start(shapes), None)
+    out.backward(grad_out)
+    arrays = {('sd.' + k): v.numpy() for k, v in m.state_dict().items()}
+    arrays.update({('grad.' + k): v.grad.numpy() for k, v in m.named_parameters()})
+    arrays.update(query=query.detach().numpy(), feat=feat.detach().numpy(), ref_pts=ref_pts.numpy(), shapes=shapes.numpy(),
+                  out=out.detach().numpy(), grad_out=grad_out.numpy(), grad_query=query.grad.numpy(), grad_feat=feat.grad.numpy(),
+                  cfg=np.array([d_model, n_levels, n_heads, n_points], dtype=np.int64), ratio=np.array(ratio))
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), **arrays)
+    print(name)
+
+
+def load_reference_seg_adapter():
+    """segmentation/mmseg_custom/models/backbones/adapter_modules.py: the copy that has InteractionBlockWithCls."""
+    sys.path.insert(0, os.path.join(REF, 'segmentation'))
+    spec = importlib.util.spec_from_file_location(
+        'ref_seg_adapter_modules', os.path.join(REF, 'segmentation/mmseg_custom/models/backbones/adapter_modules.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def vit_block_stand_in(x, H, W):
+    """A deterministic, parameter-free stand-in for the ViT blocks between Injector and Extractor (the trunk is out of
+    scope); it mixes the class token into the patch tokens so that the cls re-attachment order matters."""
+    return x * 1.25 + 0.5 * x.mean(1, keepdim=True) + 0.01 * (H - W)
+
+
+def adapter_cls_case(ref_seg_adapter, name, dim, heads, ratio, H, W, N, seed):
+    """InteractionBlockWithCls.forward of the segmentation copy (:194-234): injector -> cat(cls, x) -> blocks ->
+    split -> extractor + 2 extra extractors."""
+    torch.manual_seed(seed)
+    blk = ref_seg_adapter.InteractionBlockWithCls(dim=dim, num_heads=heads, n_points=4, init_values=0., deform_ratio=ratio,
+                                                  extra_extractor=True, with_cffn=True, cffn_ratio=0.25).double()
+    with torch.no_grad():
+        for p in blk.parameters():
+            p.add_(torch.randn_like(p) * 0.05)
+    img = torch.zeros(N, 3, H, W)
+    di1, di2 = ref_seg_adapter.deform_inputs(img)
+    h, w = H // 16, W // 16
+    x = torch.randn(N, h * w, dim, dtype=torch.double)
+    c = torch.randn(N, (2 * h) * (2 * w) + h * w + (h // 2) * (w // 2), dim, dtype=torch.double)
+    cls = torch.randn(N, 1, dim, dtype=torch.double)
+    di1d = [di1[0].double(), di1[1], di1[2]]
+    di2d = [di2[0].double(), di2[1], di2[2]]
+    xo, co, clso = blk(x, c, cls, [vit_block_stand_in, vit_block_stand_in], di1d, di2d, h, w)
+    arrays = {('sd.' + k): v.numpy() for k, v in blk.state_dict().items()}
+    arrays.update(x=x.numpy(), c=c.numpy(), cls=cls.numpy(), x_out=xo.detach().numpy(), c_out=co.detach().numpy(),
+                  cls_out=clso.detach().numpy(), ref1=di1[0].numpy(), shapes1=di1[1].numpy(), lsi1=di1[2].numpy(),
+                  ref2=di2[0].numpy(), shapes2=di2[1].numpy(), lsi2=di2[2].numpy(),
+                  cfg=np.array([dim, heads, H, W, N], dtype=np.int64), ratio=np.array(ratio))
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), **arrays)
+    print(name)
+
+
 def init_case(ref_mod, name):
     """The reference's deterministic init of sampling_offsets.bias for the adapter head counts."""
     arrays = {}
@@ -207,6 +276,13 @@ def layernorm_case(ref_adapter, name, C, shape, seed, heads=4):
 
 def main():
     ref_func, ref_mod, ref_adapter = load_reference()
+    if 'round2' in sys.argv[1:]:      # only the fixtures added in round 2 (the others are unchanged)
+        module_grad_case(ref_mod, 'module_l3_grads', d_model=128, n_levels=3, n_heads=4, n_points=4, ratio=1.0, N=2, Lq=16,
+                         shapes=[(8, 8), (4, 4), (2, 2)], seed=61, ref_levels=1)
+        module_grad_case(ref_mod, 'module_l1_grads', d_model=128, n_levels=1, n_heads=4, n_points=4, ratio=1.0, N=2, Lq=84,
+                         shapes=[(4, 4)], seed=62, ref_levels=1)
+        adapter_cls_case(load_reference_seg_adapter(), 'adapter_block_cls', dim=32, heads=4, ratio=0.5, H=64, W=96, N=2, seed=63)
+        return
     if 'layernorm' in sys.argv[1:]:   # only the N2 fixtures (the others are unchanged)
         layernorm_case(ref_adapter, 'layernorm_c96', C=96, shape=(2, 21), seed=51)
         layernorm_case(ref_adapter, 'layernorm_c768', C=768, shape=(1, 5), seed=52, heads=12)
@@ -235,6 +311,13 @@ def main():
     # 8. the LayerNorm in front of the adapter's Linears
     layernorm_case(ref_adapter, 'layernorm_c96', C=96, shape=(2, 21), seed=51)
     layernorm_case(ref_adapter, 'layernorm_c768', C=768, shape=(1, 5), seed=52, heads=12)
+    # 9. round 2: module gradients at head widths the fused kernels take (D = 32, three levels and one level), and
+    #    the class-token interaction block of the segmentation copy
+    module_grad_case(ref_mod, 'module_l3_grads', d_model=128, n_levels=3, n_heads=4, n_points=4, ratio=1.0, N=2, Lq=16,
+                     shapes=[(8, 8), (4, 4), (2, 2)], seed=61, ref_levels=1)
+    module_grad_case(ref_mod, 'module_l1_grads', d_model=128, n_levels=1, n_heads=4, n_points=4, ratio=1.0, N=2, Lq=84,
+                     shapes=[(4, 4)], seed=62, ref_levels=1)
+    adapter_cls_case(load_reference_seg_adapter(), 'adapter_block_cls', dim=32, heads=4, ratio=0.5, H=64, W=96, N=2, seed=63)
 
 
 if __name__ == '__main__':

@@ -53,3 +53,23 @@ def test_spatial_prior_module_shapes_and_keys():
     for k in ('stem.0.weight', 'stem.1.weight', 'stem.3.weight', 'stem.6.weight', 'stem.7.running_mean', 'conv2.0.weight',
               'conv3.1.bias', 'conv4.0.weight', 'fc1.weight', 'fc4.bias'):
         assert k in keys, k
+
+
+def test_deform_inputs_cache_survives_inference_mode_and_caller_edits():
+    """the first call for a resolution may happen under inference_mode (a sanity validation pass); the memoised
+    tensors must still be usable in a later training forward (not inference tensors), and a caller editing the returned
+    lists must not corrupt the cache."""
+    from vit_adapter_b200.adapter import adapter_modules as am
+    am._DEFORM_CACHE.clear()
+    with torch.inference_mode():
+        d1, d2 = deform_inputs(torch.zeros(1, 3, 96, 64))
+    assert not d1[0].is_inference() and not d2[1].is_inference()
+    w = torch.ones(1, requires_grad=True)
+    (d1[0] * w).sum().backward()                     # saving the memoised tensor for backward works
+    assert w.grad is not None
+    d1[0] = None                                     # caller-side edit of ITS list
+    d2.append('junk')
+    e1, e2 = deform_inputs(torch.zeros(2, 3, 96, 64))
+    assert e1[0] is not None and len(e2) == 3
+    f1, _ = deform_inputs(torch.zeros(2, 3, 96, 64))
+    assert f1[0] is e1[0] and f1 is not e1           # same memoised tensors, fresh containers

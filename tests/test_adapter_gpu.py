@@ -6,7 +6,7 @@ import torch
 from conftest import load_golden
 
 from vit_adapter_b200 import MSDeformAttn
-from vit_adapter_b200.adapter import InteractionBlock, deform_inputs
+from vit_adapter_b200.adapter import InteractionBlock, InteractionBlockWithCls, deform_inputs
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
@@ -89,3 +89,34 @@ def test_interaction_block_trains_f32_with_checkpointing():
     for n, p in blk.named_parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all(), n
     assert x.grad is not None and c.grad is not None
+
+
+def _vit_block_stand_in(x, H, W):
+    """Same parameter-free stand-in for the ViT blocks as tests/golden/make_golden.py::vit_block_stand_in."""
+    return x * 1.25 + 0.5 * x.mean(1, keepdim=True) + 0.01 * (H - W)
+
+
+def test_interaction_block_with_cls_matches_reference_f64():
+    """Forward parity of InteractionBlockWithCls against the segmentation copy of the reference
+    (segmentation/mmseg_custom/models/backbones/adapter_modules.py:194-234): class token re-attached around the blocks."""
+    g = load_golden('adapter_block_cls')
+    dim, heads, H, W, N = [int(v) for v in g['cfg']]
+    blk = InteractionBlockWithCls(dim=dim, num_heads=heads, n_points=4, init_values=0., deform_ratio=float(g['ratio']),
+                                  extra_extractor=True, with_cffn=True, cffn_ratio=0.25).double()
+    blk.load_state_dict({k[3:]: v for k, v in g.items() if k.startswith('sd.')}, strict=True)
+    blk = blk.to(DEV)
+    d1 = [g['ref1'].double().to(DEV), g['shapes1'].to(DEV), g['lsi1'].to(DEV)]
+    d2 = [g['ref2'].double().to(DEV), g['shapes2'].to(DEV), g['lsi2'].to(DEV)]
+    x, c, cls = blk(g['x'].to(DEV), g['c'].to(DEV), g['cls'].to(DEV), [_vit_block_stand_in, _vit_block_stand_in], d1, d2,
+                    H // 16, W // 16)
+    torch.testing.assert_close(x.cpu(), g['x_out'], rtol=1e-8, atol=1e-9)
+    torch.testing.assert_close(c.cpu(), g['c_out'], rtol=1e-8, atol=1e-9)
+    torch.testing.assert_close(cls.cpu(), g['cls_out'], rtol=1e-8, atol=1e-9)
+    # and in fp32 through the vector / fused kernels
+    blk32 = blk.float()
+    d1f = [d1[0].float(), d1[1], d1[2]]
+    d2f = [d2[0].float(), d2[1], d2[2]]
+    x, c, cls = blk32(g['x'].float().to(DEV), g['c'].float().to(DEV), g['cls'].float().to(DEV),
+                      [_vit_block_stand_in, _vit_block_stand_in], d1f, d2f, H // 16, W // 16)
+    torch.testing.assert_close(x.cpu().double(), g['x_out'], rtol=1e-4, atol=1e-4 * float(g['x_out'].abs().max()))
+    torch.testing.assert_close(c.cpu().double(), g['c_out'], rtol=1e-4, atol=1e-4 * float(g['c_out'].abs().max()))

@@ -177,3 +177,114 @@ def test_module_fused_matches_reference_golden_f32():
     # d_model 32 / 4 heads = 8 channels: no fused kernel -> the module must transparently use the plain path
     out = m(g['query'].float().to(DEV), g['ref_pts'].float().to(DEV), g['feat'].float().to(DEV), shapes, lsi)
     torch.testing.assert_close(out.cpu().double(), g['out_nomask'], rtol=1e-4, atol=1e-4)
+
+
+def test_learned_reference_points_take_the_differentiable_path():
+    """the fused kernels return no gradient for reference_points. A caller whose reference points
+    require grad must get the reference's op sequence (which differentiates them, ms_deform_attn.py:115-119) - and the same
+    gradient as with fused=False - not a silent zero."""
+    from vit_adapter_b200.modules import MSDeformAttn
+    torch.manual_seed(0)
+    m = MSDeformAttn(d_model=96, n_levels=3, n_heads=3, n_points=4).to(DEV)
+    with torch.no_grad():
+        m.sampling_offsets.weight.normal_(0, 0.02)
+        m.attention_weights.weight.normal_(0, 0.5)
+    shapes = torch.as_tensor([(8, 8), (4, 4), (2, 2)], dtype=torch.long, device=DEV)
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    q = torch.randn(2, 10, 96, device=DEV)
+    feat = torch.randn(2, 84, 96, device=DEV)
+    res = {}
+    for fused in (True, False):
+        m.fused = fused
+        ref = torch.rand(2, 10, 1, 2, device=DEV).mul_(0).add_(torch.linspace(0.1, 0.9, 10, device=DEV).view(1, 10, 1, 1)).requires_grad_()
+        out = m(q, ref, feat, shapes, lsi)
+        out.square().sum().backward()
+        assert ref.grad is not None and float(ref.grad.abs().max()) > 0
+        res[fused] = (out.detach(), ref.grad.clone())
+    torch.testing.assert_close(res[True][0], res[False][0], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(res[True][1], res[False][1], rtol=1e-5, atol=1e-6)
+    # and with constant reference points the fused path is still the one that runs (no grad asked, none returned)
+    m.fused = True
+    ref = torch.rand(1, 10, 1, 2, device=DEV)
+    n0 = _cabi.launch_count()
+    m(q, ref, feat, shapes, lsi).sum().backward()
+    assert _cabi.launch_count() - n0 >= 2 and ref.grad is None
+
+
+def test_fused_entry_rejects_short_level_metadata():
+    """the fused kernels index spatial_shapes / level_start_index with the module's level count; metadata with
+    fewer rows must raise on the host instead of being read out of bounds on the device."""
+    from vit_adapter_b200.modules import MSDeformAttn
+    m = MSDeformAttn(d_model=96, n_levels=3, n_heads=3, n_points=4).to(DEV)
+    shapes = torch.as_tensor([(8, 8), (4, 4)], dtype=torch.long, device=DEV)       # only two rows
+    lsi = torch.as_tensor([0, 64], dtype=torch.long, device=DEV)
+    q = torch.randn(1, 10, 96, device=DEV)
+    feat = torch.randn(1, 80, 96, device=DEV)
+    ref = torch.rand(1, 10, 1, 2, device=DEV)
+    with pytest.raises(RuntimeError, match='spatial_shapes must be'):
+        m(q, ref, feat, shapes, lsi)
+
+
+def test_merged_query_weights_are_cached_until_a_parameter_changes():
+    from vit_adapter_b200.modules import MSDeformAttn
+    torch.manual_seed(1)
+    m = MSDeformAttn(d_model=96, n_levels=1, n_heads=3, n_points=4).to(DEV)
+    shapes = torch.as_tensor([(6, 6)], dtype=torch.long, device=DEV)
+    lsi = shapes.new_zeros((1,))
+    q = torch.randn(2, 12, 96, device=DEV)
+    feat = torch.randn(2, 36, 96, device=DEV)
+    ref = torch.rand(1, 12, 1, 2, device=DEV)
+    out1 = m(q, ref, feat, shapes, lsi)
+    key1, w1, _ = m._merged_cache
+    out2 = m(q, ref, feat, shapes, lsi)
+    assert m._merged_cache[0] == key1 and m._merged_cache[1] is w1 and torch.equal(out1, out2)
+    out2.sum().backward()
+    assert m.sampling_offsets.weight.grad is not None and m.attention_weights.weight.grad is not None
+    assert m.sampling_offsets.bias.grad is not None and m.attention_weights.bias.grad is not None
+    # gradients equal those of the un-merged path
+    g_merged = [p.grad.clone() for p in (m.sampling_offsets.weight, m.attention_weights.weight, m.sampling_offsets.bias, m.attention_weights.bias)]
+    m.zero_grad()
+    m.merge_query_linears = False
+    m(q, ref, feat, shapes, lsi).sum().backward()
+    for a, p in zip(g_merged, (m.sampling_offsets.weight, m.attention_weights.weight, m.sampling_offsets.bias, m.attention_weights.bias)):
+        torch.testing.assert_close(a, p.grad, rtol=1e-4, atol=1e-5 * float(p.grad.abs().max()) + 1e-12)
+    m.merge_query_linears = True
+    with torch.no_grad():
+        m.attention_weights.bias.add_(torch.randn_like(m.attention_weights.bias))      # an optimizer step
+    out3 = m(q, ref, feat, shapes, lsi)
+    assert m._merged_cache[0] != key1 and m._merged_cache[1] is w1                     # refreshed in place, same buffer
+    assert not torch.equal(out3, out1)
+    m.merge_query_linears = False
+    torch.testing.assert_close(out3, m(q, ref, feat, shapes, lsi), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('merge', [True, False], ids=['merged-gemm', 'two-linears'])
+@pytest.mark.parametrize('name', ['module_l3_grads', 'module_l1_grads'])
+def test_fused_module_gradients_match_reference_goldens(name, merge):
+    """the fused / merged paths were only checked against this repo's own unfused path. Here the module's
+    default (fused) path is checked DIRECTLY against outputs and fp64 autograd gradients of the real reference module
+    (tests/golden/make_golden.py::module_grad_case): every parameter, query and feat. fp32 kernels vs fp64 reference:
+    forward 1e-5 relative, gradients 1e-4 relative (the north star's fp32 tolerances)."""
+    from vit_adapter_b200.modules import MSDeformAttn
+    g = load_golden(name)
+    d_model, L, M, P = [int(x) for x in g['cfg']]
+    m = MSDeformAttn(d_model, L, M, P, float(g['ratio']))
+    m.load_state_dict({k[3:]: v.float() for k, v in g.items() if k.startswith('sd.')}, strict=True)
+    m = m.to(DEV)
+    m.merge_query_linears = merge
+    shapes = g['shapes'].to(DEV)
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    q = g['query'].float().to(DEV).requires_grad_()
+    feat = g['feat'].float().to(DEV).requires_grad_()
+    assert _cabi.fused_supported(torch.empty(1, 1, M, int(float(g['ratio']) * d_model) // M, device=DEV), L, P)
+    n0 = _cabi.launch_count()
+    out = m(q, g['ref_pts'].float().to(DEV), feat, shapes, lsi)
+    out.backward(g['grad_out'].float().to(DEV))
+    torch.cuda.synchronize()
+    assert _cabi.launch_count() - n0 >= 2          # forward + backward kernels of this library ran
+    torch.testing.assert_close(out.detach().cpu().double(), g['out'], rtol=1e-5, atol=1e-5 * _scale(g['out']))
+    torch.testing.assert_close(q.grad.cpu().double(), g['grad_query'], rtol=1e-4, atol=1e-4 * _scale(g['grad_query']))
+    torch.testing.assert_close(feat.grad.cpu().double(), g['grad_feat'], rtol=1e-4, atol=1e-4 * _scale(g['grad_feat']))
+    for k, p_ in m.named_parameters():
+        want = g['grad.' + k]
+        torch.testing.assert_close(p_.grad.cpu().double(), want, rtol=1e-4, atol=1e-4 * _scale(want), msg=lambda s, k=k: k + ': ' + s)

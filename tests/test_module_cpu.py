@@ -58,3 +58,28 @@ def test_len_in_assert():
     shapes = torch.as_tensor([(2, 2)], dtype=torch.long)
     with pytest.raises(AssertionError):
         m(torch.zeros(1, 3, 32), torch.zeros(1, 3, 1, 2), torch.zeros(1, 5, 32), shapes, torch.zeros(1, dtype=torch.long))
+
+
+def test_tensor_memo_and_module_pickle_after_use():
+    """the shape-check memo holds weak references with callbacks; it must pickle (as an empty memo) so that
+    torch.save(model) / copy.deepcopy / mp.spawn work after the first forward, as they do for the reference module."""
+    import copy
+    import io
+    import pickle
+    from vit_adapter_b200 import _cabi
+    from vit_adapter_b200.modules import MSDeformAttn
+    m = MSDeformAttn(d_model=64, n_levels=2, n_heads=4, n_points=2)
+    shapes = torch.as_tensor([(4, 4), (2, 2)], dtype=torch.long)
+    m._check_len_in(shapes, 20)                      # what the first forward does: populates the memo
+    assert m._checked_shapes.get(shapes, 20)
+    m2 = pickle.loads(pickle.dumps(m))
+    assert isinstance(m2._checked_shapes, _cabi.TensorMemo) and m2._checked_shapes.get(shapes, 20) is None
+    m3 = copy.deepcopy(m)
+    assert m3._checked_shapes.get(shapes, 20) is None and m3._merged_cache is None
+    buf = io.BytesIO()
+    torch.save(m, buf)
+    buf.seek(0)
+    m4 = torch.load(buf, weights_only=False)
+    assert torch.equal(m4.sampling_offsets.bias, m.sampling_offsets.bias)
+    m4._check_len_in(shapes, 20)                     # and the restored memo works
+    assert m4._checked_shapes.get(shapes, 20)

@@ -277,6 +277,13 @@ FULL = [
     ('S-injector-bs16', 16, 6, 64, 1024, [(64, 64), (32, 32), (16, 16)], 4),
     ('L-injector-896', 1, 16, 32, 3136, [(112, 112), (56, 56), (28, 28)], 4),
     ('HTC-extractor-1024', 1, 16, 32, 21504, [(64, 64)], 4),
+    # round 2: the remaining BASELINE.json call shapes
+    ('S-extractor-bs16', 16, 6, 64, 5376, [(32, 32)], 4),
+    ('L-extractor-896', 1, 16, 32, 16464, [(56, 56)], 4),
+    ('L64-injector-896', 1, 16, 64, 3136, [(112, 112), (56, 56), (28, 28)], 4),
+    ('L64-extractor-896', 1, 16, 64, 16464, [(56, 56)], 4),
+    ('HTC-injector-1024', 1, 16, 32, 4096, [(128, 128), (64, 64), (32, 32)], 4),
+    ('M2F-encoder-896', 1, 32, 32, 16464, [(112, 112), (56, 56), (28, 28)], 4),
 ]
 
 
@@ -508,3 +515,32 @@ def test_guard_bands_and_head_isolation(cfg, dtype):
     # total mass check: sum(grad_value) == sum over points of (sum of valid corner weights) * aw * sum_c(grad_out)
     idx = c_oracle.point_index(inp['shapes'], inp['lsi'], inp['loc'], M, D)
     assert (idx[:, 3] >= -(max(w for _, w in shapes) + 2) * M * D).all()
+
+
+# ---------------------------------------------------------------------------------------------------
+# the stand-in for the reference's pybind module (vision.cpp:13-16), called the way the reference's Python calls it
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('case', ['op_kat_seed3', 'op_inj_edges', 'op_d32_edges', 'op_d64_edges'])
+def test_pybind_compat_module_on_goldens(case):
+    import importlib
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, 'vit-adapter_b200', 'pybind_compat'))
+    try:
+        sys.modules.pop('MultiScaleDeformableAttention', None)
+        MSDA = importlib.import_module('MultiScaleDeformableAttention')
+    finally:
+        sys.path.pop(0)
+    g = _cuda(load_golden(case))
+    out = MSDA.ms_deform_attn_forward(g['value'], g['shapes'], g['lsi'], g['loc'], g['aw'], 64)
+    assert tuple(out.shape) == (g['value'].shape[0], g['loc'].shape[1], g['value'].shape[2] * g['value'].shape[3])
+    torch.testing.assert_close(out.cpu().double(), g['out_f64'].cpu(), rtol=1e-5, atol=1e-6)
+    res = MSDA.ms_deform_attn_backward(g['value'], g['shapes'], g['lsi'], g['loc'], g['aw'], g['grad_out'], 64)
+    assert isinstance(res, list) and len(res) == 3                     # std::vector<at::Tensor> of the reference
+    for got, key in zip(res, ('grad_value_f64', 'grad_loc_f64', 'grad_aw_f64')):
+        want = g[key].cpu()
+        torch.testing.assert_close(got.cpu().double(), want, rtol=1e-4, atol=1e-4 * _scale(want))
+    with pytest.raises(RuntimeError, match='must divide'):
+        MSDA.ms_deform_attn_forward(g['value'].repeat(3, 1, 1, 1), g['shapes'], g['lsi'], g['loc'].repeat(3, 1, 1, 1, 1, 1),
+                                    g['aw'].repeat(3, 1, 1, 1, 1), 2)

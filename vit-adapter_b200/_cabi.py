@@ -193,6 +193,18 @@ class TensorMemo:
             return ent[2]
         return None
 
+    # A memo is derived state: it pickles (torch.save(model), copy.deepcopy, mp.spawn) as an empty memo. The weak
+    # references and their callbacks it holds are not picklable and would mean nothing in another process anyway.
+    def __getstate__(self):
+        return {'_limit': self._limit}
+
+    def __setstate__(self, state):
+        self._d = {}
+        self._limit = state.get('_limit', 256)
+
+    def __deepcopy__(self, memo):
+        return TensorMemo(self._limit)
+
     def put(self, t, value, extra=None):
         import weakref
         if len(self._d) > self._limit:
@@ -288,6 +300,17 @@ def fused_supported(value, n_levels, n_points):
     return D % cpl == 0 and (D // cpl) in (4, 8, 16)
 
 
+def _check_fused_meta(spatial_shapes, level_start_index, reference_points, L):
+    """The fused kernels index spatial_shapes / level_start_index with the MODULE's level count: a metadata tensor with
+    fewer rows would be read out of bounds on the device (the reference fails with a broadcasting error instead)."""
+    _check_meta(spatial_shapes, level_start_index)
+    if tuple(spatial_shapes.shape) != (L, 2) or level_start_index.numel() != L:
+        raise RuntimeError('fused MSDeformAttn: spatial_shapes must be [%d, 2] and level_start_index [%d], got %s and %s'
+                           % (L, L, tuple(spatial_shapes.shape), tuple(level_start_index.shape)))
+    if reference_points.dim() != 4 or reference_points.shape[-1] != 2:
+        raise RuntimeError('fused MSDeformAttn: reference_points must be [Nr, Lq, Lr, 2], got %s' % (tuple(reference_points.shape),))
+
+
 def _fused_dims(value, reference_points, sampling_offsets, attn_logits):
     if value.dim() != 4 or sampling_offsets.dim() != 6 or reference_points.dim() != 4 or reference_points.shape[-1] != 2:
         raise RuntimeError('expected value [N,S,M,D], reference_points [Nr,Lq,Lr,2], sampling_offsets [N,Lq,M,L,P,2]')
@@ -305,8 +328,8 @@ def forward_fused(value, spatial_shapes, level_start_index, reference_points, sa
     lib = load()
     dev = _check_cuda(value=value, spatial_shapes=spatial_shapes, level_start_index=level_start_index,
                       reference_points=reference_points, sampling_offsets=sampling_offsets, attn_logits=attn_logits)
-    _check_meta(spatial_shapes, level_start_index)
     dims, rb, rl = _fused_dims(value, reference_points, sampling_offsets, attn_logits)
+    _check_fused_meta(spatial_shapes, level_start_index, reference_points, dims.num_levels)
     code = _DTYPES.get(value.dtype)
     with _on(dev):
         out = torch.empty((dims.batch, dims.num_query, dims.num_heads * dims.channels), dtype=value.dtype, device=dev)
@@ -319,6 +342,9 @@ def forward_fused(value, spatial_shapes, level_start_index, reference_points, sa
 
 
 def _merged_dims(value, reference_points, merged, n_levels, n_points):
+    if value.dim() != 4 or reference_points.dim() != 4 or reference_points.shape[-1] != 2:
+        raise RuntimeError('fused MSDeformAttn (merged): expected value [N,S,M,D] and reference_points [Nr,Lq,Lr,2], got %s and %s'
+                           % (tuple(value.shape), tuple(reference_points.shape)))
     N, S, M, D = value.shape
     Lq = reference_points.shape[1]
     width = M * n_levels * n_points * 3
@@ -334,8 +360,8 @@ def forward_fused_merged(value, spatial_shapes, level_start_index, reference_poi
     lib = load()
     dev = _check_cuda(value=value, spatial_shapes=spatial_shapes, level_start_index=level_start_index,
                       reference_points=reference_points, merged=merged)
-    _check_meta(spatial_shapes, level_start_index)
     dims, rb, rl, width = _merged_dims(value, reference_points, merged, n_levels, n_points)
+    _check_fused_meta(spatial_shapes, level_start_index, reference_points, dims.num_levels)
     code = _DTYPES.get(value.dtype)
     with _on(dev):
         out = torch.empty((dims.batch, dims.num_query, dims.num_heads * dims.channels), dtype=value.dtype, device=dev)
@@ -354,6 +380,7 @@ def backward_fused_merged(value, spatial_shapes, level_start_index, reference_po
     dev = _check_cuda(value=value, spatial_shapes=spatial_shapes, level_start_index=level_start_index,
                       reference_points=reference_points, merged=merged, grad_output=grad_output)
     dims, rb, rl, width = _merged_dims(value, reference_points, merged, n_levels, n_points)
+    _check_fused_meta(spatial_shapes, level_start_index, reference_points, dims.num_levels)
     code = _DTYPES.get(value.dtype)
     if grad_output.dtype != value.dtype:
         raise RuntimeError('grad_output dtype %s != value dtype %s' % (grad_output.dtype, value.dtype))
@@ -381,6 +408,7 @@ def backward_fused(value, spatial_shapes, level_start_index, reference_points, s
                       reference_points=reference_points, sampling_offsets=sampling_offsets, attn_logits=attn_logits,
                       grad_output=grad_output)
     dims, rb, rl = _fused_dims(value, reference_points, sampling_offsets, attn_logits)
+    _check_fused_meta(spatial_shapes, level_start_index, reference_points, dims.num_levels)
     code = _DTYPES.get(value.dtype)
     if grad_output.dtype != value.dtype:
         raise RuntimeError('grad_output dtype %s != value dtype %s' % (grad_output.dtype, value.dtype))
@@ -473,7 +501,8 @@ def launch_count():
 
 def set_tuning(**kv):
     """Benchmark knobs, e.g. set_tuning(fwd_chunk=64, fwd_smem=1); value 0 restores the heuristic.
-    Keys: fwd_chunk, bwd_chunk, fwd_min_ctas, bwd_min_ctas, fwd_smem, fwd_smem_threads, fwd_smem_chunks."""
+    Keys: fwd_chunk, bwd_chunk, fwd_min_ctas, bwd_min_ctas, fwd_smem, fwd_smem_threads, fwd_smem_chunks, fwd_wide,
+    bwd_cell (2 = the cell-bucketed backward), bwd_cell_chunk. The knobs are process-wide (see include/msda_b200.h)."""
     global _WANT_HOST_SHAPES
     lib = load()
     for k, v in kv.items():

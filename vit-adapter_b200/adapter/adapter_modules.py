@@ -67,12 +67,19 @@ def deform_inputs(x):
     """x: image batch [N, 3, H, W] (only its shape / device are used). Returns
     deform_inputs1 = [ref points of the H/16 grid, shapes of the H/8, H/16, H/32 levels, level starts]  (Injector)
     deform_inputs2 = [ref points of the three levels, shape of the H/16 grid, [0]]                     (Extractor)
-    exactly as reference adapter_modules.py:28-47, memoised per (H, W, device)."""
+    exactly as reference adapter_modules.py:28-47, memoised per (H, W, device). The memoised tensors are built outside
+    inference mode (an inference tensor could not be saved for a later training backward) and are READ-ONLY by contract;
+    every call returns fresh list containers around them, so a caller that edits its lists cannot disturb another."""
     _, _, h, w = x.shape
     key = (int(h), int(w), str(x.device))
     hit = _DEFORM_CACHE.get(key)
     if hit is not None:
-        return hit
+        return list(hit[0]), list(hit[1])
+    with torch.inference_mode(False), torch.no_grad():
+        return _build_deform_inputs(x, key, h, w)
+
+
+def _build_deform_inputs(x, key, h, w):
     pyramid = [(h // 8, w // 8), (h // 16, w // 16), (h // 32, w // 32)]
     vit_grid = [(h // 16, w // 16)]
     shapes1, lsi1 = _level_meta(pyramid, x.device)
@@ -83,7 +90,7 @@ def deform_inputs(x):
     if len(_DEFORM_CACHE) > 32:
         _DEFORM_CACHE.clear()
     _DEFORM_CACHE[key] = out
-    return out
+    return list(out[0]), list(out[1])
 
 
 class _LayerNormRows(torch.autograd.Function):

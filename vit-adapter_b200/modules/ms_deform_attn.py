@@ -22,6 +22,39 @@ from .. import _cabi
 from ..functions import MSDeformAttnFunction, MSDeformAttnFusedFunction, MSDeformAttnMergedFunction, linear
 
 
+class _MergedQueryParams(torch.autograd.Function):
+    """cat(sampling_offsets.weight, attention_weights.weight) and cat(their biases) in two PERSISTENT buffers owned by the
+    module. The buffers are rewritten only when one of the four parameters changed (version counters / storage), so an
+    inference loop or a checkpointed re-forward issues no cat kernel at all, and the backward hands the two halves of the
+    merged gradient back as views (no split kernels). State-dict keys are untouched: the buffers are plain attributes."""
+
+    @staticmethod
+    def forward(ctx, w_off, w_attn, b_off, b_attn, owner):
+        key = tuple((t._version, t.data_ptr(), t.dtype, t.device) for t in (w_off, w_attn, b_off, b_attn))
+        cache = owner.__dict__.get('_merged_cache')
+        if cache is None or cache[0] != key:
+            n = w_off.shape[0] + w_attn.shape[0]
+            if cache is not None and cache[1].shape == (n, w_off.shape[1]) and cache[1].dtype == w_off.dtype and cache[1].device == w_off.device:
+                w, b = cache[1], cache[2]
+            else:
+                w = torch.empty((n, w_off.shape[1]), dtype=w_off.dtype, device=w_off.device)
+                b = torch.empty((n,), dtype=b_off.dtype, device=b_off.device)
+            torch.cat([w_off.detach(), w_attn.detach()], 0, out=w)
+            torch.cat([b_off.detach(), b_attn.detach()], 0, out=b)
+            owner.__dict__['_merged_cache'] = (key, w, b)
+        else:
+            w, b = cache[1], cache[2]
+        ctx.n_off = w_off.shape[0]
+        # views of the buffers, so that autograd sees fresh outputs of this node every call
+        return w.view_as(w), b.view_as(b)
+
+    @staticmethod
+    def backward(ctx, gw, gb):
+        n = ctx.n_off
+        return (gw[:n] if gw is not None else None, gw[n:] if gw is not None else None,
+                gb[:n] if gb is not None else None, gb[n:] if gb is not None else None, None)
+
+
 def _is_power_of_2(n):
     if not isinstance(n, int) or n < 0:
         raise ValueError('invalid input for _is_power_of_2: {} (type: {})'.format(n, type(n)))
@@ -50,6 +83,7 @@ class MSDeformAttn(nn.Module):
         self.value_proj = nn.Linear(d_model, d_value)
         self.output_proj = nn.Linear(d_value, d_model)
         self._checked_shapes = _cabi.TensorMemo(limit=64)
+        self._merged_cache = None   # (key, weight, bias) of _MergedQueryParams
         # fuse softmax + location arithmetic into the sampling kernel when a fused kernel exists (2-d reference
         # points, CUDA, fp32/bf16, (L,P) in {(3,4),(1,4)}); results differ from the unfused path only by the
         # rounding of the softmax normalisation. Set to False to force the reference's op sequence.
@@ -79,6 +113,11 @@ class MSDeformAttn(nn.Module):
             nn.init.xavier_uniform_(self.output_proj.weight)
             self.output_proj.bias.zero_()
 
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state['_merged_cache'] = None   # derived from the four parameters; rebuilt on the next forward
+        return state
+
     def _check_len_in(self, spatial_shapes, len_in):
         # memo keyed by tensor identity + version (NOT data_ptr: freed addresses are reused by the allocator)
         if self._checked_shapes.get(spatial_shapes, int(len_in)):
@@ -103,12 +142,17 @@ class MSDeformAttn(nn.Module):
             value = value.masked_fill(input_padding_mask[..., None], float(0))
         value = value.view(N, len_in, M, int(self.ratio * self.d_model) // M)
 
-        if self.fused and reference_points.shape[-1] == 2 and _cabi.fused_supported(value, L, P):
+        # The fused kernels return no gradient for reference_points (a constant grid in the adapter). A caller that learns
+        # its reference points (Deformable-DETR style decoders, ms_deform_attn.py:115-119 differentiates them) takes the
+        # reference's op sequence below, which does.
+        ref_needs_grad = torch.is_grad_enabled() and reference_points.requires_grad
+        if self.fused and not ref_needs_grad and reference_points.dim() == 4 and reference_points.shape[-1] == 2 \
+                and _cabi.fused_supported(value, L, P):
             if self.merge_query_linears:
                 # sampling_offsets and attention_weights read the same query: ONE GEMM over the concatenated weights
-                # (state-dict keys untouched); the kernels consume its output in place
-                w = torch.cat([self.sampling_offsets.weight, self.attention_weights.weight], 0)
-                b = torch.cat([self.sampling_offsets.bias, self.attention_weights.bias], 0)
+                # (state-dict keys untouched, cached until a parameter changes); the kernels consume its output in place
+                w, b = _MergedQueryParams.apply(self.sampling_offsets.weight, self.attention_weights.weight,
+                                                self.sampling_offsets.bias, self.attention_weights.bias, self)
                 merged = linear(query, w, b, cs)
                 output = MSDeformAttnMergedFunction.apply(value, input_spatial_shapes, input_level_start_index,
                                                           reference_points, merged, L, P)
