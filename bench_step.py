@@ -161,14 +161,7 @@ def use_reference_cuda_core():
     mod.MSDeformAttnFunction = RefFn
 
 
-def main():
-    sys.stdout.flush()
-    real_stdout = os.dup(1)   # NCCL prints its version banner on fd 1: keep stdout for the one JSON line
-    os.dup2(2, 1)
-    ap = argparse.ArgumentParser()
-    ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
-    ap.add_argument('--warmup', type=int, default=3)
+def add_step_args(ap):
     ap.add_argument('--variant', default='B', choices=sorted(CFG))
     ap.add_argument('--mode', default='train', choices=['train', 'infer'])
     ap.add_argument('--image', type=int, default=512)
@@ -184,11 +177,163 @@ def main():
                          '(segmentation/README.md:24); off by default in the torch of this image')
     ap.add_argument('--graph', action='store_true',
                     help='capture the whole step (forward, backward, optimizer, and under torchrun the DDP all-reduce) in ONE CUDA graph and replay it')
-    args = ap.parse_args()
 
-    if args.tf32:
+
+def step_bench(variant='B', mode='train', image=512, batch=2, amp=False, with_cp=False, op='ours', reference_sequence=False,
+               tf32=False, graph=False, steps=10, warmup=3, measure_comm=True):
+    """One model-level measurement on the CURRENT device / process group (the caller owns torch.distributed): returns the
+    result dict. Under a process group the net is wrapped in DDP (gradient all-reduce over NCCL) with SyncBatchNorm, as the
+    reference trains (segmentation/dist_train.sh:8-9, configs/_base_/default_runtime.py:9).
+
+    measure_comm (eager DDP training only): the same K steps are timed again under `model.no_sync()` - identical compute,
+    no gradient all-reduce - and the difference is reported as the all-reduce time that is NOT hidden behind the backward
+    (`allreduce_ms_exposed`)."""
+    import vit_adapter_b200 as vab
+    from vit_adapter_b200 import _cabi
+    from vit_adapter_b200.graphs import GraphedStep
+    from vit_adapter_b200.sharding import max_over_ranks
+
+    if tf32:
         torch.backends.cuda.matmul.allow_tf32 = True
         torch.backends.cudnn.allow_tf32 = True
+    ddp = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    world = dist.get_world_size() if ddp else 1
+    rank = dist.get_rank() if ddp else 0
+    dev = torch.device('cuda', torch.cuda.current_device())
+    if reference_sequence:
+        op = 'ref_cuda'
+    if op == 'ref_cuda':
+        use_reference_cuda_core()
+    vab.set_amp_value_dtype(torch.bfloat16 if amp else torch.float32)
+
+    torch.manual_seed(1234 + rank)
+    net = Net(variant, sync_bn=ddp, with_cp=with_cp).to(dev)
+    if reference_sequence:
+        for m in net.modules():
+            for flag in ('fused_norm', 'token_kernel', 'fused', 'merge_query_linears', 'colsum_bias_grad'):
+                if hasattr(m, flag):
+                    setattr(m, flag, False)
+    n_params = sum(p.numel() for p in net.parameters())
+    n_adapter = sum(p.numel() for n, p in net.named_parameters() if 'interactions' in n or 'spm' in n)
+    model = net
+    if ddp and mode == 'train':
+        if graph:
+            # DDP under whole-step capture (torch docs, "Usage with DistributedDataParallel"): construct DDP on a side
+            # stream, and warm up >= 11 eager iterations so that bucket rebuilding is over before the capture
+            side0 = torch.cuda.Stream()
+            with torch.cuda.stream(side0):
+                model = nn.parallel.DistributedDataParallel(net, device_ids=[dev.index], gradient_as_bucket_view=True)
+            torch.cuda.current_stream().wait_stream(side0)
+            warmup = max(warmup, 11)
+        else:
+            model = nn.parallel.DistributedDataParallel(net, device_ids=[dev.index], gradient_as_bucket_view=True)
+    opt = torch.optim.AdamW(net.parameters(), lr=6e-5, weight_decay=0.01, fused=True, capturable=graph) if mode == 'train' else None
+    img = torch.randn(batch, 3, image, image, device=dev)
+    lab = torch.randint(0, 150, (batch, image // 4, image // 4), device=dev)
+
+    def forward_loss():
+        with torch.autocast('cuda', dtype=torch.bfloat16, enabled=amp):
+            if mode == 'train':
+                return F.cross_entropy(model(img).float(), lab)
+            with torch.no_grad():
+                return model(img)
+
+    def eager_step():
+        out = forward_loss()
+        if mode == 'train':
+            opt.zero_grad(set_to_none=True)
+            out.backward()
+            opt.step()
+        return out
+
+    def captured_body():   # the eager step minus zero_grad: the captured backward owns the gradient buffers
+        out = forward_loss()
+        if mode == 'train':
+            out.backward()
+            opt.step()
+        return out
+
+    if mode == 'infer':
+        net.eval()
+
+    def barrier():
+        if ddp:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        eager_step()
+    barrier()
+    step = eager_step
+    launches_per_replay = 0
+    if graph:
+        # whole-step capture: at 2 images per GPU the step is ~1 900 kernels of a few microseconds each and the Python /
+        # launch path is as long as the GPU work; one graph launch replaces it. Everything on the path is capturable:
+        # no host sync (MSDeformAttn's shape check is memoised), no allocation outside torch's graph pool, the library
+        # launches on the capturing stream it is handed.
+        gs = GraphedStep(captured_body, warmup=(11 if ddp else 3), warm_fn=eager_step,
+                         before_capture=(lambda: opt.zero_grad(set_to_none=True)) if opt is not None else None)
+        launches_per_replay = gs.launches
+        step = gs
+        for _ in range(2):
+            step()
+        barrier()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            out = fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1), dev), out
+
+    l0 = _cabi.launch_count()
+    ms, out = timed(step, steps)
+    launches = _cabi.launch_count() - l0 + launches_per_replay * steps
+    allreduce_bytes = 4 * n_params if (ddp and mode == 'train') else 0   # fp32 gradient buckets, every parameter once per step
+    exposed = None
+    if ddp and mode == 'train' and not graph and measure_comm:
+        def nosync_step():
+            with model.no_sync():
+                return eager_step()
+        for _ in range(2):
+            nosync_step()
+        ms_nosync, _ = timed(nosync_step, steps)
+        exposed = max(0.0, (ms - ms_nosync) / steps)
+    res = {
+        'metric': 'vit_adapter_%s_%s_img_per_s' % (variant, mode), 'value': world * batch * steps / (ms * 1e-3),
+        'unit': 'img/s', 'n_gpus': world, 'steps': steps, 'warmup': warmup, 'ms_per_step': ms / steps,
+        'higher_is_better': True, 'scaling': 'weak', 'dtype': 'bf16-autocast' if amp else 'f32', 'data': 'synthetic',
+        'op': op, 'adapter': 'reference op sequence' if reference_sequence else 'this repo (fused norm / dwconv / softmax+locations)',
+        'msda_kernel_launches': launches, 'cuda_graph': bool(graph), 'tf32_gemm': bool(tf32),
+        'allreduce_bytes': allreduce_bytes, 'allreduce_ms_exposed': exposed,
+        'config': {'workload': 'ViT-Adapter-%s backbone (this repo\'s adapter modules + MSDeformAttn) + stand-in head, %dx%d, '
+                               '%d img/GPU, %s' % (variant, image, image, batch, mode),
+                   'params_total': n_params, 'params_adapter': n_adapter, 'with_cp': with_cp,
+                   'parallelism': 'dp%d (DDP all-reduce over NCCL, SyncBN)' % world if world > 1 else 'single GPU',
+                   'note': 'ViT trunk and head are minimal stand-ins (mmcv/mmseg/timm absent); adapter path is the drop-in code'},
+        'final': float(out.detach().float().mean()) if torch.is_tensor(out) else None,
+    }
+    vab.set_amp_value_dtype(torch.float32)
+    del model, net, opt, step
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    return res
+
+
+def main():
+    sys.stdout.flush()
+    real_stdout = os.dup(1)   # NCCL prints its version banner on fd 1: keep stdout for the one JSON line
+    os.dup2(2, 1)
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    add_step_args(ap)
+    args = ap.parse_args()
+
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -199,128 +344,13 @@ def main():
         if args.graph:
             os.environ.setdefault('TORCH_NCCL_ASYNC_ERROR_HANDLING', '0')   # NCCL work captured in a graph has no watchdog-visible events
         dist.init_process_group('nccl', device_id=dev)
-
-    import vit_adapter_b200 as vab
-    from vit_adapter_b200 import _cabi
-    if args.reference_sequence:
-        args.op = 'ref_cuda'
-    if args.op == 'ref_cuda':
-        use_reference_cuda_core()
-    if args.amp:
-        vab.set_amp_value_dtype(torch.bfloat16)
-
-    torch.manual_seed(1234 + rank)
-    net = Net(args.variant, sync_bn=(world > 1), with_cp=args.with_cp).to(dev)
-    if args.reference_sequence:
-        for m in net.modules():
-            for flag in ('fused_norm', 'token_kernel', 'fused', 'merge_query_linears', 'colsum_bias_grad'):
-                if hasattr(m, flag):
-                    setattr(m, flag, False)
-    n_params = sum(p.numel() for p in net.parameters())
-    n_adapter = sum(p.numel() for n, p in net.named_parameters() if 'interactions' in n or 'spm' in n)
-    model = net
-    use_graph = args.graph
-    if world > 1 and args.mode == 'train':
-        if use_graph:
-            # DDP under whole-step capture (torch docs, "Usage with DistributedDataParallel"): construct DDP on a side
-            # stream, and warm up >= 11 eager iterations so that bucket rebuilding is over before the capture
-            side0 = torch.cuda.Stream()
-            with torch.cuda.stream(side0):
-                model = nn.parallel.DistributedDataParallel(net, device_ids=[local_rank], gradient_as_bucket_view=True)
-            torch.cuda.current_stream().wait_stream(side0)
-            args.warmup = max(args.warmup, 11)
-        else:
-            model = nn.parallel.DistributedDataParallel(net, device_ids=[local_rank], gradient_as_bucket_view=True)
-    opt = torch.optim.AdamW(net.parameters(), lr=6e-5, weight_decay=0.01, fused=True, capturable=use_graph) if args.mode == 'train' else None
-    img = torch.randn(args.batch, 3, args.image, args.image, device=dev)
-    lab = torch.randint(0, 150, (args.batch, args.image // 4, args.image // 4), device=dev)
-
-    def step():
-        with torch.autocast('cuda', dtype=torch.bfloat16, enabled=args.amp):
-            if args.mode == 'train':
-                loss = F.cross_entropy(model(img).float(), lab)
-            else:
-                with torch.no_grad():
-                    return model(img)
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        opt.step()
-        return loss
-
-    if args.mode == 'infer':
-        net.eval()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    launches_per_replay = 0
-    if use_graph:
-        # whole-step capture: at 2 images per GPU the step is ~1 900 kernels of a few microseconds each and the Python /
-        # launch path is as long as the GPU work; one graph launch replaces it. Everything on the path is capturable:
-        # no host sync (MSDeformAttn's shape check is memoised), no allocation outside torch's graph pool, the library
-        # launches on the capturing stream it is handed.
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(11 if world > 1 else 3):
-                step()
-        torch.cuda.current_stream().wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
-        if opt is not None:
-            opt.zero_grad(set_to_none=True)
-        c0 = _cabi.launch_count()
-        with torch.cuda.graph(graph):
-            with torch.autocast('cuda', dtype=torch.bfloat16, enabled=args.amp):
-                if args.mode == 'train':
-                    static_out = F.cross_entropy(model(img).float(), lab)
-                else:
-                    with torch.no_grad():
-                        static_out = model(img)
-            if args.mode == 'train':
-                static_out.backward()
-                opt.step()
-        launches_per_replay = _cabi.launch_count() - c0
-
-        def step():  # noqa: F811
-            graph.replay()
-            return static_out
-        for _ in range(2):
-            step()
-        barrier()
-    l0 = _cabi.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        out = step()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = _cabi.launch_count() - l0 + launches_per_replay * args.steps
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    res = step_bench(variant=args.variant, mode=args.mode, image=args.image, batch=args.batch, amp=args.amp, with_cp=args.with_cp,
+                     op=args.op, reference_sequence=args.reference_sequence, tf32=args.tf32, graph=args.graph, steps=args.steps,
+                     warmup=args.warmup)
     if rank == 0:
-        os.write(real_stdout, (json.dumps({
-            'metric': 'vit_adapter_%s_%s_img_per_s' % (args.variant, args.mode), 'value': world * args.batch * args.steps / (ms * 1e-3),
-            'unit': 'img/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
-            'higher_is_better': True, 'scaling': 'weak', 'dtype': 'bf16-autocast' if args.amp else 'f32', 'data': 'synthetic',
-            'op': args.op, 'adapter': 'reference op sequence' if args.reference_sequence else 'this repo (fused norm / dwconv / softmax+locations)',
-            'msda_kernel_launches': launches, 'cuda_graph': bool(use_graph), 'tf32_gemm': bool(args.tf32),
-            'config': {'workload': 'ViT-Adapter-%s backbone (this repo\'s adapter modules + MSDeformAttn) + stand-in head, %dx%d, '
-                                   '%d img/GPU, %s' % (args.variant, args.image, args.image, args.batch, args.mode),
-                       'params_total': n_params, 'params_adapter': n_adapter, 'with_cp': args.with_cp,
-                       'parallelism': 'dp%d (DDP all-reduce over NCCL, SyncBN)' % world if world > 1 else 'single GPU',
-                       'note': 'ViT trunk and head are minimal stand-ins (mmcv/mmseg/timm absent); adapter path is the drop-in code'},
-            'final': float(out.detach().float().mean()) if torch.is_tensor(out) else None,
-        }) + '\n').encode())
+        os.write(real_stdout, (json.dumps(res) + '\n').encode())
     if world > 1:
-        if use_graph:
+        if args.graph:
             # tearing the NCCL communicator down after its collectives were captured in a graph hung on the test box:
             # the result is out, every rank is synchronised - leave without the destructor
             torch.cuda.synchronize()

@@ -34,18 +34,6 @@ def run(nbytes, n_streams, do_h2d, do_d2h, reps=10):
     return nbytes / dt / 1e9
 
 
-def main():
-    nbytes = 384 << 20
-    for ns in (1, 2, 4):
-        print(json.dumps({'streams_per_direction': ns, 'MB_per_direction': nbytes >> 20,
-                          'h2d_only_GBps': run(nbytes, ns, True, False), 'd2h_only_GBps': run(nbytes, ns, False, True),
-                          'both_GBps_each': run(nbytes, ns, True, True)}), flush=True)
-
-
-if __name__ == '__main__':
-    main()
-
-
 def bench_like(dep):
     """bench.py's per-step traffic: 8 tensors in, 8 out, of the adapter's sizes; `dep`: copy-out of step k waits for copy-in of step k
     (as the compute in between does)."""
@@ -82,3 +70,49 @@ if __name__ == '__main__':
     for dep in (False, True):
         g, ms = bench_like(dep)
         print(json.dumps({'pattern': 'bench-like 8+8 tensors per step', 'copy_out_waits_for_copy_in': dep, 'GBps_each': g, 'ms_per_step': ms}), flush=True)
+
+
+def main():
+    """Alone:   python tools/pcie_probe.py
+    All GPUs of the box at once (what bench.py --gpus N does to the host):
+             python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/pcie_probe.py
+    Every rank drives its own GPU; the measurements start together (barrier) and rank 0 prints, per case, the slowest and
+    the mean per-GPU rate and the aggregate over the box."""
+    import os
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('gloo')
+
+    def together(fn):
+        if world > 1:
+            dist.barrier()
+        v = fn()
+        if world == 1:
+            return {'per_gpu_min': v, 'per_gpu_mean': v, 'aggregate': v}
+        got = [None] * world
+        dist.all_gather_object(got, v)
+        return {'per_gpu_min': min(got), 'per_gpu_mean': sum(got) / world, 'aggregate': sum(got)}
+
+    nbytes = 384 << 20
+    for ns in (1, 2):
+        row = {'gpus_at_once': world, 'streams_per_direction': ns, 'MB_per_direction': nbytes >> 20,
+               'h2d_only_GBps': together(lambda: run(nbytes, ns, True, False)),
+               'd2h_only_GBps': together(lambda: run(nbytes, ns, False, True)),
+               'both_GBps_each_direction': together(lambda: run(nbytes, ns, True, True))}
+        if rank == 0:
+            print(json.dumps(row), flush=True)
+    for dep in (False, True):
+        r = together(lambda: bench_like(dep)[0])
+        if rank == 0:
+            print(json.dumps({'gpus_at_once': world, 'bench_like_traffic': 'copy-out waits for copy-in' if dep else 'independent directions',
+                              'GBps_each_direction': r}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -18,20 +18,33 @@ import torch
 
 
 class GraphedStep:
-    def __init__(self, fn, warmup=3, stream=None):
+    """Capture `fn` (a fixed-shape step) once and replay it.
+
+    warm_fn         what the eager warm-up iterations run (default: `fn`). A training step usually warms up with the full
+                    eager step (zero_grad + forward + backward + optimizer) and captures the same without the zero_grad.
+    before_capture  called once between warm-up and capture (e.g. `optimizer.zero_grad(set_to_none=True)`, so that the
+                    captured backward allocates the gradients inside the graph's pool and every replay overwrites them).
+    After construction `launches` holds the number of kernels of THIS library inside one replay."""
+
+    def __init__(self, fn, warmup=3, stream=None, warm_fn=None, before_capture=None):
         if not torch.cuda.is_available():
             raise RuntimeError('GraphedStep needs a CUDA device (Not implemented on the CPU)')
+        from . import _cabi
         self._fn = fn
         side = stream if stream is not None else torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):   # warm-up off the default stream, as torch.cuda.graph requires
             for _ in range(max(1, int(warmup))):
-                fn()
+                (warm_fn or fn)()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        if before_capture is not None:
+            before_capture()
         self.graph = torch.cuda.CUDAGraph()
+        c0 = _cabi.launch_count()
         with torch.cuda.graph(self.graph):
             self.outputs = fn()
+        self.launches = _cabi.launch_count() - c0
 
     def __call__(self):
         self.graph.replay()
