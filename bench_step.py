@@ -177,10 +177,13 @@ def add_step_args(ap):
                          '(segmentation/README.md:24); off by default in the torch of this image')
     ap.add_argument('--graph', action='store_true',
                     help='capture the whole step (forward, backward, optimizer, and under torchrun the DDP all-reduce) in ONE CUDA graph and replay it')
+    ap.add_argument('--bn', default='sync', choices=['sync', 'local'],
+                    help="'local': plain BatchNorm under DDP (NOT the reference's training recipe) - isolates what SyncBatchNorm's "
+                         'forward costs the eager step: three host synchronisations per layer')
 
 
 def step_bench(variant='B', mode='train', image=512, batch=2, amp=False, with_cp=False, op='ours', reference_sequence=False,
-               tf32=False, graph=False, steps=10, warmup=3, measure_comm=True):
+               tf32=False, graph=False, steps=10, warmup=3, measure_comm=True, bn='sync'):
     """One model-level measurement on the CURRENT device / process group (the caller owns torch.distributed): returns the
     result dict. Under a process group the net is wrapped in DDP (gradient all-reduce over NCCL) with SyncBatchNorm, as the
     reference trains (segmentation/dist_train.sh:8-9, configs/_base_/default_runtime.py:9).
@@ -207,7 +210,7 @@ def step_bench(variant='B', mode='train', image=512, batch=2, amp=False, with_cp
     vab.set_amp_value_dtype(torch.bfloat16 if amp else torch.float32)
 
     torch.manual_seed(1234 + rank)
-    net = Net(variant, sync_bn=ddp, with_cp=with_cp).to(dev)
+    net = Net(variant, sync_bn=(ddp and bn == 'sync'), with_cp=with_cp).to(dev)
     if reference_sequence:
         for m in net.modules():
             for flag in ('fused_norm', 'token_kernel', 'fused', 'merge_query_linears', 'colsum_bias_grad'):
@@ -308,7 +311,7 @@ def step_bench(variant='B', mode='train', image=512, batch=2, amp=False, with_cp
         'higher_is_better': True, 'scaling': 'weak', 'dtype': 'bf16-autocast' if amp else 'f32', 'data': 'synthetic',
         'op': op, 'adapter': 'reference op sequence' if reference_sequence else 'this repo (fused norm / dwconv / softmax+locations)',
         'msda_kernel_launches': launches, 'cuda_graph': bool(graph), 'tf32_gemm': bool(tf32),
-        'allreduce_bytes': allreduce_bytes, 'allreduce_ms_exposed': exposed,
+        'allreduce_bytes': allreduce_bytes, 'allreduce_ms_exposed': exposed, 'batchnorm': 'SyncBatchNorm' if (ddp and bn == 'sync') else 'BatchNorm2d',
         'config': {'workload': 'ViT-Adapter-%s backbone (this repo\'s adapter modules + MSDeformAttn) + stand-in head, %dx%d, '
                                '%d img/GPU, %s' % (variant, image, image, batch, mode),
                    'params_total': n_params, 'params_adapter': n_adapter, 'with_cp': with_cp,
@@ -346,7 +349,7 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
     res = step_bench(variant=args.variant, mode=args.mode, image=args.image, batch=args.batch, amp=args.amp, with_cp=args.with_cp,
                      op=args.op, reference_sequence=args.reference_sequence, tf32=args.tf32, graph=args.graph, steps=args.steps,
-                     warmup=args.warmup)
+                     warmup=args.warmup, bn=args.bn)
     if rank == 0:
         os.write(real_stdout, (json.dumps(res) + '\n').encode())
     if world > 1:

@@ -66,12 +66,6 @@ def bench_like(dep):
     return sum(mb) * (1 << 20) / dt / 1e9, dt * 1e3
 
 
-if __name__ == '__main__':
-    for dep in (False, True):
-        g, ms = bench_like(dep)
-        print(json.dumps({'pattern': 'bench-like 8+8 tensors per step', 'copy_out_waits_for_copy_in': dep, 'GBps_each': g, 'ms_per_step': ms}), flush=True)
-
-
 def main():
     """Alone:   python tools/pcie_probe.py
     All GPUs of the box at once (what bench.py --gpus N does to the host):
