@@ -271,6 +271,10 @@ uint64_t msda_launch_count(void);
  *   "fwd_wide"                      fp32 forward with 32-byte lanes (LDG.256): 1 = off, 2 = on
  *   "fwd_smem_threads"              512 | 1024 threads per CTA of the shared-memory forward
  *   "fwd_smem_chunks"               query chunks per (batch, head) of the shared-memory forward
+ *   "bwd_cell"                      2 = the cell-bucketed backward (msda_bwd_cell.cu; D in {32, 64}); default: the query-order kernel
+ *   "bwd_cell_chunk"                queries per chunk of the cell-bucketed backward
+ *   "bwd_packed16"                  2 = bf16 / f16 backward with packed 16-bit reductions straight into grad_value (no fp32
+ *                                   scratch, no convert kernel; every contribution rounded to 16 bits - looser numerics)
  * Returns 0, or MSDA_E_NULL for an unknown key. */
 int msda_set_tuning(const char* key, int32_t value);
 

@@ -58,8 +58,11 @@ def test_kernel_matches_reference_golden(name, dtype):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('cfg', [(192, 32, 32, 2), (96, 8, 12, 3), (48, 56, 56, 1), (40, 6, 14, 2), (1024, 2, 2, 1)],
-                         ids=['B-512', 'S-small', 'L-896-C48', 'ragged-runs', 'C1024'])
+@pytest.mark.parametrize('cfg', [(192, 32, 32, 2), (96, 8, 12, 3), (48, 56, 56, 1), (40, 6, 14, 2), (1024, 2, 2, 1),
+                                 # shared-memory tile kernels (map widths multiples of 4, C % 32 == 0): 64- and 32-channel blocks,
+                                 # bands that do not divide the map height, the ViT-Adapter-L shape, a non-square grid
+                                 (96, 16, 8, 2), (256, 56, 56, 1), (64, 8, 16, 1), (192, 24, 40, 1)],
+                         ids=['B-512', 'S-small', 'L-896-C48', 'ragged-runs', 'C1024', 'tile-C96', 'tile-L-896', 'tile-C64-rect', 'tile-odd-bands'])
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16, torch.float16], ids=['f32', 'bf16', 'f16'])
 def test_kernel_vs_oracle_adapter_shapes(cfg, dtype):
     from vit_adapter_b200.adapter import DWConv

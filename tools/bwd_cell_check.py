@@ -26,6 +26,7 @@ def main():
     ap.add_argument('--chunks', default='0')
     ap.add_argument('--iters', type=int, default=20)
     ap.add_argument('--dist', default='adapter')
+    ap.add_argument('--mode', default='cell', choices=['cell', 'packed16'], help='which opt-in backward to compare with the default')
     ap.add_argument('--out', default=os.path.join(ROOT, 'gpurun_out', 'bwd_cell_check.jsonl'))
     args = ap.parse_args()
     peak = 6533.8
@@ -52,19 +53,24 @@ def main():
                 torch.cuda.synchronize()
                 nbytes = algorithmic_bytes(N, M, D, Lq, shapes, inp['value'].element_size())['bwd']
                 for ch in args.chunks.split(','):
-                    _cabi.set_tuning(bwd_cell=2, bwd_cell_chunk=int(ch))
+                    if args.mode == 'packed16':
+                        if dn == 'f32':
+                            continue
+                        _cabi.set_tuning(bwd_cell=0, bwd_packed16=2)
+                    else:
+                        _cabi.set_tuning(bwd_cell=2, bwd_cell_chunk=int(ch))
                     got = call()
                     torch.cuda.synchronize()
                     errs = [float((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-30)) for a, b in zip(got, ref)]
                     t_new = timeit(call, args.iters, 3, flush)
-                    row = dict(variant=variant, call=name, dtype=dn, chunk=int(ch), dist=args.dist, old_us=round(t_old['med'] * 1e3, 1),
+                    row = dict(mode=args.mode, variant=variant, call=name, dtype=dn, chunk=int(ch), dist=args.dist, old_us=round(t_old['med'] * 1e3, 1),
                                cell_us=round(t_new['med'] * 1e3, 1), cell_min_us=round(t_new['min'] * 1e3, 1),
                                speedup=round(t_old['med'] / t_new['med'], 2), hbm_frac=round(nbytes / (t_new['med'] * 1e-3) / 1e9 / peak, 3),
                                gsamples=round(n_points(N, M, Lq, len(shapes)) / (t_new['med'] * 1e-3) / 1e9, 2),
                                rel_err_gv_gl_ga=['%.2e' % e for e in errs])
                     print(json.dumps(row), flush=True)
                     out.write(json.dumps(row) + '\n')
-                _cabi.set_tuning(bwd_cell=0, bwd_cell_chunk=0)
+                _cabi.set_tuning(bwd_cell=0, bwd_cell_chunk=0, bwd_packed16=0)
     out.close()
 
 

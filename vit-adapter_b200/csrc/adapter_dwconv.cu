@@ -271,6 +271,26 @@ template <> struct Quad<__half> {
   }
 };
 
+// Packed fp32 pairs: Blackwell issues two IEEE fp32 FMAs per instruction (FFMA2, PTX fma.rn.f32x2) on 64-bit register
+// pairs. The run kernels below are issue-bound in the 16-bit types (36 FMAs + 15 unpack instructions per 8 output
+// bytes), so the 36 FMAs of an output quad go out as 18 FFMA2; each lane's result is bit-identical to the scalar form.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 p, float& lo, float& hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(p)); }
+__device__ __forceinline__ void ffma2(f32x2& acc, f32x2 a, f32x2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
+__device__ __forceinline__ void fadd2(f32x2& acc, f32x2 a) { asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(a)); }
+template <typename T>
+__device__ __forceinline__ void unpack_pairs(const typename Quad<T>::Raw& q, f32x2 (&v)[2]) {
+  float f[4];
+  Quad<T>::unpack(q, f);
+  v[0] = pk2(f[0], f[1]);
+  v[1] = pk2(f[2], f[3]);
+}
+
 // the kRun + 2 tokens (columns w0-1 .. w0+kRun) of one map row, zero outside the map: all loads issued back to back
 template <typename T>
 __device__ __forceinline__ void dw_load_row(const T* row, int C, int w0, int mw, bool row_ok, typename Quad<T>::Raw (&raw)[kRun + 2]) {
@@ -292,13 +312,20 @@ __global__ void __launch_bounds__(256, 2) adapter_dwconv_run_kernel(const DwPara
   const int cv = threadIdx.x % cvec, ty = threadIdx.x / cvec;
   const T* __restrict__ x = reinterpret_cast<const T*>(p.x);
   T* __restrict__ y = reinterpret_cast<T*>(p.y);
-  float tp[9][4], bias[4];
+  f32x2 tp[9][2], bias[2];
+  {
+    float tf[9][4], bf[4];
 #pragma unroll
-  for (int v = 0; v < 4; ++v) {
-    const T* wv = reinterpret_cast<const T*>(p.w) + (cv * 4 + v) * 9;
+    for (int v = 0; v < 4; ++v) {
+      const T* wv = reinterpret_cast<const T*>(p.w) + (cv * 4 + v) * 9;
 #pragma unroll
-    for (int k = 0; k < 9; ++k) tp[FLIP ? 8 - k : k][v] = dw_ld<T>(wv + k);
-    bias[v] = (!FLIP && p.bias) ? dw_ld<T>(reinterpret_cast<const T*>(p.bias) + cv * 4 + v) : 0.f;
+      for (int k = 0; k < 9; ++k) tf[FLIP ? 8 - k : k][v] = dw_ld<T>(wv + k);
+      bf[v] = (!FLIP && p.bias) ? dw_ld<T>(reinterpret_cast<const T*>(p.bias) + cv * 4 + v) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { tp[k][0] = pk2(tf[k][0], tf[k][1]); tp[k][1] = pk2(tf[k][2], tf[k][3]); }
+    bias[0] = pk2(bf[0], bf[1]);
+    bias[1] = pk2(bf[2], bf[3]);
   }
   for (int item = blockIdx.x * ty_count + ty; item < g.total; item += gridDim.x * ty_count) {
     int b, t0, mh, mw, h, w0;
@@ -308,11 +335,9 @@ __global__ void __launch_bounds__(256, 2) adapter_dwconv_run_kernel(const DwPara
     T* yr = y + row_tok * p.C + cv * 4;
     const ptrdiff_t rs = (ptrdiff_t)mw * p.C;  // one map row in elements
     const bool rok[3] = {h > 0, true, h + 1 < mh};
-    float acc[kRun][4];
+    f32x2 acc[kRun][2];
 #pragma unroll
-    for (int j = 0; j < kRun; ++j)
-#pragma unroll
-      for (int v = 0; v < 4; ++v) acc[j][v] = bias[v];
+    for (int j = 0; j < kRun; ++j) { acc[j][0] = bias[0]; acc[j][1] = bias[1]; }
     Raw cur[kRun + 2], nxt[kRun + 2];
     dw_load_row<T>(xr - rs, p.C, w0, mw, rok[0], cur);
 #pragma unroll
@@ -320,14 +345,14 @@ __global__ void __launch_bounds__(256, 2) adapter_dwconv_run_kernel(const DwPara
       if (kAhead && r < 2) dw_load_row<T>(xr + (r == 0 ? 0 : rs), p.C, w0, mw, rok[r + 1], nxt);
 #pragma unroll
       for (int jj = 0; jj < kRun + 2; ++jj) {
-        float val[4];
-        Quad<T>::unpack(cur[jj], val);
+        f32x2 val[2];
+        unpack_pairs<T>(cur[jj], val);
 #pragma unroll
         for (int dx = 2; dx >= 0; --dx) {   // token jj is column dx of output j = jj - dx; dx descending keeps the
           const int j = jj - dx;            // per-output order (row-major over the taps)
           if (j < 0 || j >= kRun) continue;
-#pragma unroll
-          for (int v = 0; v < 4; ++v) acc[j][v] = fmaf(val[v], tp[r * 3 + dx][v], acc[j][v]);
+          ffma2(acc[j][0], val[0], tp[r * 3 + dx][0]);
+          ffma2(acc[j][1], val[1], tp[r * 3 + dx][1]);
         }
       }
       if (r < 2) {
@@ -341,7 +366,12 @@ __global__ void __launch_bounds__(256, 2) adapter_dwconv_run_kernel(const DwPara
     }
 #pragma unroll
     for (int j = 0; j < kRun; ++j)
-      if (w0 + j < mw) Quad<T>::st(yr + (ptrdiff_t)(w0 + j) * p.C, acc[j]);
+      if (w0 + j < mw) {
+        float o[4];
+        upk2(acc[j][0], o[0], o[1]);
+        upk2(acc[j][1], o[2], o[3]);
+        Quad<T>::st(yr + (ptrdiff_t)(w0 + j) * p.C, o);
+      }
   }
 }
 
@@ -358,11 +388,9 @@ __global__ void __launch_bounds__(256, 2) adapter_dwconv_wgrad_run_kernel(const 
   const int cv = threadIdx.x % cvec, ty = threadIdx.x / cvec;
   const T* __restrict__ x = reinterpret_cast<const T*>(p.x);
   const T* __restrict__ gy = reinterpret_cast<const T*>(grad_y_);
-  float s[10][4];
+  f32x2 s[10][2];
 #pragma unroll
-  for (int k = 0; k < 10; ++k)
-#pragma unroll
-    for (int v = 0; v < 4; ++v) s[k][v] = 0.f;
+  for (int k = 0; k < 10; ++k) { s[k][0] = pk2(0.f, 0.f); s[k][1] = pk2(0.f, 0.f); }
   for (int item = blockIdx.x * ty_count + ty; item < g.total; item += gridDim.x * ty_count) {
     int b, t0, mh, mw, h, w0;
     dw_run_locate(item, p, g, b, t0, mh, mw, h, w0);
@@ -371,39 +399,40 @@ __global__ void __launch_bounds__(256, 2) adapter_dwconv_wgrad_run_kernel(const 
     const T* gr = gy + row_tok * p.C + cv * 4;
     const ptrdiff_t rs = (ptrdiff_t)mw * p.C;
     const bool rok[3] = {h > 0, true, h + 1 < mh};
-    Raw graw[kRun];
+    f32x2 gq[kRun][2];
 #pragma unroll
-    for (int j = 0; j < kRun; ++j) graw[j] = Quad<T>::ld(gr + (ptrdiff_t)(w0 + j) * p.C, w0 + j < mw);
+    for (int j = 0; j < kRun; ++j) {
+      const Raw graw = Quad<T>::ld(gr + (ptrdiff_t)(w0 + j) * p.C, w0 + j < mw);
+      unpack_pairs<T>(graw, gq[j]);
+      fadd2(s[9][0], gq[j][0]);
+      fadd2(s[9][1], gq[j][1]);
+    }
     Raw cur[kRun + 2];
     dw_load_row<T>(xr - rs, p.C, w0, mw, rok[0], cur);
 #pragma unroll
-    for (int j = 0; j < kRun; ++j) {
-      float gq[4];
-      Quad<T>::unpack(graw[j], gq);
-#pragma unroll
-      for (int v = 0; v < 4; ++v) s[9][v] += gq[v];
-    }
-#pragma unroll
     for (int r = 0; r < 3; ++r) {
+      f32x2 val[kRun + 2][2];
+#pragma unroll
+      for (int jj = 0; jj < kRun + 2; ++jj) unpack_pairs<T>(cur[jj], val[jj]);
+      if (r < 2) dw_load_row<T>(xr + (r == 0 ? 0 : rs), p.C, w0, mw, rok[r + 1], cur);   // the next row is in flight during the FMAs
 #pragma unroll
       for (int j = 0; j < kRun; ++j) {
-        float gq[4];
-        Quad<T>::unpack(graw[j], gq);
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
-          float val[4];
-          Quad<T>::unpack(cur[j + dx], val);
-#pragma unroll
-          for (int v = 0; v < 4; ++v) s[r * 3 + dx][v] = fmaf(gq[v], val[v], s[r * 3 + dx][v]);
+          ffma2(s[r * 3 + dx][0], gq[j][0], val[j + dx][0]);
+          ffma2(s[r * 3 + dx][1], gq[j][1], val[j + dx][1]);
         }
       }
-      if (r < 2) dw_load_row<T>(xr + (r == 0 ? 0 : rs), p.C, w0, mw, rok[r + 1], cur);
     }
   }
 #pragma unroll
-  for (int k = 0; k < 10; ++k)
+  for (int k = 0; k < 10; ++k) {
+    float f[4];
+    upk2(s[k][0], f[0], f[1]);
+    upk2(s[k][1], f[2], f[3]);
 #pragma unroll
-    for (int v = 0; v < 4; ++v) red[(ty * 40 + k * 4 + v) * cvec + cv] = s[k][v];
+    for (int v = 0; v < 4; ++v) red[(ty * 40 + k * 4 + v) * cvec + cv] = f[v];
+  }
   __syncthreads();
   float* mine = partial + (size_t)blockIdx.x * 40 * cvec;
   for (int i = threadIdx.x; i < 40 * cvec; i += blockDim.x) {
@@ -443,6 +472,222 @@ __global__ void __launch_bounds__(1024) adapter_dwconv_wgrad_sum_kernel(const fl
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Tile kernels (round 2). The run kernels above keep their loads in registers, so the bytes a thread has in flight are
+// bounded by its register file: 16 warps x 20 loads x 8 bytes per lane in bf16 - half of what fp32 gets with the same
+// code, which is why bf16 ran in the same TIME as fp32 (0.35 vs 0.61 of the HBM roofline) and why packing the FMAs
+// (FFMA2) changed nothing. Here a CTA owns (batch, map, band of output rows, block of channels) and brings the band's
+// input rows (+1 halo row above and below, +1 zero token left and right) into shared memory with cp.async - all of
+// it in flight at once, no registers held - then every thread computes runs of 4 output tokens for its channel quad
+// from shared memory (18 LDS per 4 outputs) with the taps in registers.
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int kTileRun = 4;
+
+struct DwTileGeom {
+  int rb[3];        // output rows per band, per map
+  int bands[3];     // bands per map
+  int nblk;         // channel blocks (C / (4 * CBQ))
+  int items[3];     // bands * nblk per map (per batch)
+  int per_batch, total;
+  unsigned row_bytes_max;  // bytes of one padded tile row of the widest map
+  unsigned smem;           // dynamic shared memory: (max rb + 2) rows of the widest configuration
+};
+
+template <typename T>
+static bool dw_tile_geom(const DwParams& p, int cbq, DwTileGeom* g) {
+  const int CB = 4 * cbq;
+  if (p.C % CB != 0) return false;
+  const int mh[3] = {2 * p.H, p.H, p.H / 2}, mw[3] = {2 * p.W, p.W, p.W / 2};
+  g->nblk = p.C / CB;
+  g->per_batch = 0;
+  g->smem = 0;
+  g->row_bytes_max = 0;
+  for (int i = 0; i < 3; ++i) {
+    if (mw[i] % kTileRun != 0 || mw[i] < kTileRun) return false;   // whole runs only (the adapter's maps are multiples of 4 wide)
+    const unsigned row_bytes = (unsigned)(mw[i] + 2) * CB * sizeof(T);
+    // band height: as many rows as keep the tile at ~70 KB (3 resident CTAs per SM, which is also what the registers
+    // allow), at least 2, at most the map
+    int rb = (int)(70u * 1024u / row_bytes) - 2;
+    if (rb < 2) rb = 2;
+    if (rb > 8) rb = 8;
+    if (rb > mh[i]) rb = mh[i];
+    g->rb[i] = rb;
+    g->bands[i] = (mh[i] + rb - 1) / rb;
+    g->items[i] = g->bands[i] * g->nblk;
+    g->per_batch += g->items[i];
+    const unsigned need = (unsigned)(rb + 2) * row_bytes + (unsigned)CB * 9u * (unsigned)sizeof(T) + 16u;   // + the block's taps
+    if (need > g->smem) g->smem = need;
+    if (row_bytes > g->row_bytes_max) g->row_bytes_max = row_bytes;
+  }
+  g->total = g->per_batch * p.B;
+  return g->smem <= 200u * 1024u;
+}
+
+template <typename T, bool FLIP, int CBQ>
+__global__ void __launch_bounds__(256, 3) adapter_dwconv_tile_kernel(const DwParams p, const DwTileGeom g) {
+  using Raw = typename Quad<T>::Raw;
+  constexpr int CB = 4 * CBQ;                       // channels per block
+  constexpr unsigned kTokB = CB * sizeof(T);        // bytes of one token of the block
+  constexpr int kVecPerTok = kTokB / 16;            // 16-byte chunks per token
+  extern __shared__ __align__(16) unsigned char dw_tile[];
+  const int tid = threadIdx.x;
+
+  // ---- work item -> (batch, map, band, channel block) ----------------------------------------------------------------
+  int item = blockIdx.x;
+  const int b = item / g.per_batch;
+  item -= b * g.per_batch;
+  int mi = 0;
+  if (item >= g.items[0]) { item -= g.items[0]; mi = 1; }
+  if (mi == 1 && item >= g.items[1]) { item -= g.items[1]; mi = 2; }
+  const int mh = mi == 0 ? 2 * p.H : mi == 1 ? p.H : p.H / 2;
+  const int mw = mi == 0 ? 2 * p.W : mi == 1 ? p.W : p.W / 2;
+  const int t0 = mi == 0 ? 0 : mi == 1 ? 4 * p.H * p.W : 5 * p.H * p.W;
+  const int band = item / g.nblk, cblk = item - band * g.nblk;
+  const int rb = g.rb[mi];
+  const int h0 = band * rb;
+  const int nrow = min(rb, mh - h0);                // output rows of this band
+  const unsigned row_bytes = (unsigned)(mw + 2) * kTokB;
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(dw_tile);
+  const size_t map_tok = (size_t)b * p.Ntok + t0;
+  const T* __restrict__ xin = reinterpret_cast<const T*>(p.x) + map_tok * p.C + cblk * CB;
+  T* __restrict__ yout = reinterpret_cast<T*>(p.y) + map_tok * p.C + cblk * CB;
+
+  // ---- stage rows h0-1 .. h0+nrow of the map: interior by cp.async, everything outside the map is zero. Two commit
+  //      groups: the rows the first half of the output rows needs, then the rest - the first half is computed while the
+  //      second is still on its way. The block's 9 x CB taps (contiguous in the [C,1,3,3] weight) ride in the first group.
+  const int nrowA = (nrow + 1) / 2;                 // output rows of the first half: needs tile rows 0 .. nrowA+1
+  const unsigned taps_s = sbase + (unsigned)(rb + 2) * row_bytes;
+  {
+    constexpr int kTapChunks = (CB * 9 * (int)sizeof(T)) / 16;   // CB in {32, 64}: a whole number of 16-byte chunks
+    const char* wsrc = reinterpret_cast<const char*>(reinterpret_cast<const T*>(p.w) + (size_t)cblk * CB * 9);
+    for (int i = tid; i < kTapChunks; i += 256)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(taps_s + i * 16), "l"(wsrc + i * 16) : "memory");
+  }
+  for (int r = 0; r < nrow + 2; ++r) {
+    if (r == nrowA + 2) asm volatile("cp.async.commit_group;" ::: "memory");
+    const int h = h0 - 1 + r;
+    const unsigned srow = sbase + r * row_bytes;
+    if (h >= 0 && h < mh) {
+      // thread -> (16-byte chunk c of a token, tokens wq, wq + 256 / kVecPerTok, ...): constant strides, no division in the loop
+      const int c = tid % kVecPerTok, wq = tid / kVecPerTok;
+      const char* src = reinterpret_cast<const char*>(xin + (size_t)h * mw * p.C) + (size_t)wq * p.C * sizeof(T) + c * 16;
+      unsigned dst = srow + (unsigned)(wq + 1) * kTokB + c * 16;
+      const size_t sstep = (size_t)(256 / kVecPerTok) * p.C * sizeof(T);
+      for (int w = wq; w < mw; w += 256 / kVecPerTok, src += sstep, dst += (256 / kVecPerTok) * kTokB)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+      if (tid < 2 * kVecPerTok) {   // the zero token left of column 0 and right of column mw-1
+        const unsigned dst = srow + (tid < kVecPerTok ? 0u : (unsigned)(mw + 1) * kTokB) + (tid % kVecPerTok) * 16;
+        asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(dst), "r"(0u) : "memory");
+      }
+    } else {
+      for (unsigned o = tid * 16u; o < row_bytes; o += 256u * 16u)
+        asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(srow + o), "r"(0u) : "memory");
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  const bool two_groups = (nrow + 2) > (nrowA + 2);
+
+  // ---- this thread's channel quad: taps and bias in registers (packed pairs) --------------------------------------------
+  const int quad = tid % CBQ;
+  if (two_groups) asm volatile("cp.async.wait_group 1;" ::: "memory");
+  else asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  f32x2 tp[9][2], bias[2];
+  {
+    float tf[9][4], bf[4];
+    const T* ws = reinterpret_cast<const T*>(dw_tile + (size_t)(rb + 2) * row_bytes) + quad * 36;   // 4 channels x 9 taps, contiguous
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) tf[FLIP ? 8 - k : k][v] = dw_ld<T>(ws + v * 9 + k);
+      bf[v] = (!FLIP && p.bias) ? dw_ld<T>(reinterpret_cast<const T*>(p.bias) + cblk * CB + quad * 4 + v) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { tp[k][0] = pk2(tf[k][0], tf[k][1]); tp[k][1] = pk2(tf[k][2], tf[k][3]); }
+    bias[0] = pk2(bf[0], bf[1]);
+    bias[1] = pk2(bf[2], bf[3]);
+  }
+
+  // ---- compute: unit = (output row, run of 4 tokens, quad); quads fastest so a warp reads whole tokens -----------------
+  const int nrun = mw / kTileRun;
+  const unsigned qoff = (unsigned)quad * (4u * sizeof(T));
+  for (int half = 0; half < 2; ++half) {
+    const int r_begin = half == 0 ? 0 : nrowA, r_end = half == 0 ? nrowA : nrow;
+    if (half == 1) {
+      if (r_begin >= r_end) break;
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+    }
+    const int units = (r_end - r_begin) * nrun * CBQ;
+    for (int u = tid; u < units; u += 256) {
+      const int rr = r_begin + u / (nrun * CBQ);
+      const int run = (u % (nrun * CBQ)) / CBQ;
+      const int w0 = run * kTileRun;
+      f32x2 acc[kTileRun][2];
+#pragma unroll
+      for (int j = 0; j < kTileRun; ++j) { acc[j][0] = bias[0]; acc[j][1] = bias[1]; }
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const unsigned srow = sbase + (unsigned)(rr + r) * row_bytes + (unsigned)w0 * kTokB + qoff;   // padded column w0 = map column w0 - 1
+#pragma unroll
+        for (int jj = 0; jj < kTileRun + 2; ++jj) {
+          Raw raw;
+          if constexpr (sizeof(T) == 4) {
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(raw.x), "=f"(raw.y), "=f"(raw.z), "=f"(raw.w) : "r"(srow + jj * kTokB));
+          } else {
+            asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(raw.x), "=r"(raw.y) : "r"(srow + jj * kTokB));
+          }
+          f32x2 val[2];
+          unpack_pairs<T>(raw, val);
+#pragma unroll
+          for (int dx = 2; dx >= 0; --dx) {
+            const int j = jj - dx;
+            if (j < 0 || j >= kTileRun) continue;
+            ffma2(acc[j][0], val[0], tp[r * 3 + dx][0]);
+            ffma2(acc[j][1], val[1], tp[r * 3 + dx][1]);
+          }
+        }
+      }
+      T* dst = yout + ((size_t)(h0 + rr) * mw + w0) * p.C + quad * 4;
+#pragma unroll
+      for (int j = 0; j < kTileRun; ++j) {
+        float o[4];
+        upk2(acc[j][0], o[0], o[1]);
+        upk2(acc[j][1], o[2], o[3]);
+        Quad<T>::st(dst + (size_t)j * p.C, o);
+      }
+    }
+  }
+}
+
+template <typename T, bool FLIP>
+static cudaError_t launch_dw_tile(const DwParams& p, cudaStream_t s, bool* taken) {
+  *taken = false;
+  if (p.H % 2 != 0 || p.W % 2 != 0) return cudaSuccess;
+  const uintptr_t al = 15;
+  if ((reinterpret_cast<uintptr_t>(p.x) & al) || (reinterpret_cast<uintptr_t>(p.y) & al) || (reinterpret_cast<uintptr_t>(p.w) & al)) return cudaSuccess;
+  DwTileGeom g;
+  int cbq = 0;
+  // 16 bytes per cp.async: a token of the block must be a multiple of 16 bytes -> CB * sizeof(T) % 16 == 0
+  if (p.C % 64 == 0 && dw_tile_geom<T>(p, 16, &g)) cbq = 16;
+  else if (p.C % 32 == 0 && dw_tile_geom<T>(p, 8, &g)) cbq = 8;
+  if (!cbq || (size_t)p.C * sizeof(T) % 16 != 0) return cudaSuccess;
+  *taken = true;
+  cudaError_t e;
+  if (cbq == 16) {
+    auto k = adapter_dwconv_tile_kernel<T, FLIP, 16>;
+    e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+    if (e != cudaSuccess) return e;
+    k<<<(unsigned)g.total, 256, g.smem, s>>>(p, g);
+  } else {
+    auto k = adapter_dwconv_tile_kernel<T, FLIP, 8>;
+    e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+    if (e != cudaSuccess) return e;
+    k<<<(unsigned)g.total, 256, g.smem, s>>>(p, g);
+  }
+  return cudaGetLastError();
+}
+
 // fast-path eligibility + launch shape: blockDim = cvec * ty_count <= 256
 template <typename T>
 static bool dw_run_shape(const DwParams& p, const void* extra, int& cvec, int& ty_count) {
@@ -465,6 +710,11 @@ template <typename T, bool FLIP>
 static cudaError_t launch_dw(const DwParams& p, cudaStream_t s) {
   using A = typename DwAcc<T>::type;
   if constexpr (sizeof(T) <= 4) {
+    if constexpr (sizeof(T) == 2) {   // fp32 measured faster on the run kernel (bytes in flight are not its limit)
+      bool taken = false;
+      const cudaError_t et = launch_dw_tile<T, FLIP>(p, s, &taken);
+      if (taken) return et;
+    }
     int cvec, ty_count;
     if (dw_run_shape<T>(p, nullptr, cvec, ty_count)) {
       const DwRunGeom g = dw_run_geom(p);

@@ -16,6 +16,7 @@ bool vec_supported(int dtype, int D, int* G_out);
 cudaError_t launch_forward(const Params& p, int dtype, bool vec_ok, int G, int minb, cudaStream_t s);
 cudaError_t launch_backward(const Params& p, int dtype, bool vec_ok, int G, int minb, cudaStream_t s);
 cudaError_t launch_cvt_f32_bf16(const float* src, void* dst, size_t n, int dtype, cudaStream_t s);
+cudaError_t launch_backward_packed16(const Params& p, int dtype, int G, bool fused, cudaStream_t s);
 cudaError_t launch_forward_fused(const Params& p, int dtype, int G, cudaStream_t s);
 cudaError_t launch_backward_fused(const Params& p, int dtype, int G, cudaStream_t s);
 struct DwParams {
@@ -65,7 +66,7 @@ cudaError_t launch_forward_smem(const Params& p, const SmemPlan& plan, int dtype
 static thread_local char g_err[512] = "";
 constexpr bool kFwdWideDefault = false;  // flipped once measured faster (tuning key "fwd_wide" = 2 forces it)
 static std::atomic<uint64_t> g_launches{0};
-static std::atomic<int> g_qc_fwd{0}, g_qc_bwd{0}, g_minb_fwd{0}, g_minb_bwd{0}, g_smem_mode{0}, g_smem_nt{0}, g_smem_chunks{0}, g_fwd_wide{0}, g_bwd_cell{0}, g_bwd_cell_qc{0};
+static std::atomic<int> g_qc_fwd{0}, g_qc_bwd{0}, g_minb_fwd{0}, g_minb_bwd{0}, g_smem_mode{0}, g_smem_nt{0}, g_smem_chunks{0}, g_fwd_wide{0}, g_bwd_cell{0}, g_bwd_cell_qc{0}, g_bwd_packed16{0};
 
 static int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -183,7 +184,9 @@ static bool plan_forward_smem(const msda_dims* d, int dtype, int G, const int64_
       const int l = order[a];
       // pass 0 sizes the candidate set without the null block; pass 1 re-fits with it (may drop the largest)
       const int64_t reserve = pass == 0 ? (int64_t)(plan->W[l] + 4) * rowB : 0;
-      if (total + bytes[l] + reserve > (int64_t)kSmemBudget) break;
+      // static shared memory of the kernel: the per-warp tap scratch, (nt / 32) warps x (32 / G) groups x (2G + 1) x 16 bytes
+      const int64_t scratch = (int64_t)(nt / 32) * (32 / G) * (2 * G + 1) * 16 + 512;
+      if (total + bytes[l] + reserve + scratch > (int64_t)kSmemBudget) break;
       plan->smem_off[l] = (unsigned)total;
       plan->staged |= 1u << l;
       total += bytes[l];
@@ -314,6 +317,7 @@ int msda_set_tuning(const char* key, int32_t value) {
   else if (!strcmp(key, "fwd_wide")) slot = &g_fwd_wide;
   else if (!strcmp(key, "bwd_cell")) slot = &g_bwd_cell;
   else if (!strcmp(key, "bwd_cell_chunk")) slot = &g_bwd_cell_qc;
+  else if (!strcmp(key, "bwd_packed16")) slot = &g_bwd_packed16;
   if (!slot) return fail(MSDA_E_NULL, "msda_set_tuning: unknown key '%s'", key);
   slot->store(value);
   return 0;
@@ -434,6 +438,16 @@ int msda_backward(const msda_dims* dims, int dtype, const void* value, const int
   p.qc = pick_chunk(dims, per_iter, g_qc_bwd.load());
   p.nchunk = (p.Lq + p.qc - 1) / p.qc;
 
+  // opt-in: packed 16-bit reductions straight into grad_value (no fp32 scratch, no convert; see msda_bwd.cu red_add_16x4)
+  if (lowp && vec && g_bwd_packed16.load() == 2 && (G == 8 || G == 16) && ((p.L == 3 || p.L == 1) && p.P == 4) && aligned(grad_value, 8)) {
+    p.grad_value = grad_value;
+    cudaError_t ep = cudaMemsetAsync(grad_value, 0, nvalue * es, s);
+    if (ep != cudaSuccess) return cuda_fail(ep, "msda_backward memset(grad_value)");
+    ep = launch_backward_packed16(p, dtype, G, false, s);
+    if (ep != cudaSuccess) return cuda_fail(ep, "msda_backward (packed 16-bit reductions) launch");
+    g_launches.fetch_add(1);
+    return 0;
+  }
   cudaError_t e = cudaMemsetAsync(accum, 0, accum_bytes, s);
   if (e != cudaSuccess) return cuda_fail(e, "msda_backward memset(grad_value)");
   CellPlan cplan;
@@ -535,6 +549,15 @@ int msda_backward_fused(const msda_dims* dims, int dtype, const void* value, con
     return fail(MSDA_E_ALIGN, "msda_backward_fused: misaligned pointer");
   p.qc = pick_chunk(dims, kWarps * (32 / G), g_qc_bwd.load());
   p.nchunk = (p.Lq + p.qc - 1) / p.qc;
+  if (lowp && g_bwd_packed16.load() == 2 && aligned(grad_value, 8)) {
+    p.grad_value = grad_value;
+    cudaError_t ep = cudaMemsetAsync(grad_value, 0, nvalue * elem_size(dtype), s);
+    if (ep != cudaSuccess) return cuda_fail(ep, "msda_backward_fused memset(grad_value)");
+    ep = launch_backward_packed16(p, dtype, G, true, s);
+    if (ep != cudaSuccess) return cuda_fail(ep, "msda_backward_fused (packed 16-bit reductions) launch");
+    g_launches.fetch_add(1);
+    return 0;
+  }
   cudaError_t e = cudaMemsetAsync(accum, 0, nvalue * 4u, s);
   if (e != cudaSuccess) return cuda_fail(e, "msda_backward_fused memset(grad_value)");
   e = launch_backward_fused(p, dtype, G, s);

@@ -73,6 +73,27 @@ struct VecB<__half> {
   }
 };
 
+// OPT-IN scatter for 16-bit I/O (tuning key "bwd_packed16" = 2): 4 channels go out as ONE packed reduction straight into the
+// bf16 / fp16 grad_value (REDG.E.ADD.BF16x4 / F16x4, 8 bytes per lane, 64-byte rows for D = 32) instead of an fp32 vector
+// reduction into a scratch that is zero-filled before and converted after. Half the atomic payload (the L2 served 1.67x
+// the rows per ns in the round-1 microbenchmark), no 4-byte-per-element memset, no convert kernel - but every CONTRIBUTION is
+// rounded to 16 bits and the running sum is kept in 16 bits, instead of one rounding of an fp32 sum: ~sqrt(n) * 2^-9
+// relative error for n contributions per element (n ~ 9 Injector, ~ 84 Extractor), outside the 1e-2 bf16 tolerance for
+// long sums. Not the default for that reason; tests/test_op_gpu.py::test_packed16_backward states its tolerance.
+template <typename T>
+__device__ __forceinline__ void red_add_16x4(char* p, float a, float b, float c, float d);
+template <>
+__device__ __forceinline__ void red_add_16x4<__nv_bfloat16>(char* p, float a, float b, float c, float d) {
+  asm volatile("red.global.v2.bf16x2.add.noftz [%0], {%1, %2};" ::"l"(p), "r"(Vec<__nv_bfloat16>::pack2(a, b)),
+               "r"(Vec<__nv_bfloat16>::pack2(c, d)) : "memory");
+}
+template <>
+__device__ __forceinline__ void red_add_16x4<__half>(char* p, float a, float b, float c, float d) {
+  asm volatile("red.global.v2.f16x2.add.noftz [%0], {%1, %2};" ::"l"(p), "r"(Vec<__half>::pack2(a, b)), "r"(Vec<__half>::pack2(c, d)) : "memory");
+}
+template <>
+__device__ __forceinline__ void red_add_16x4<float>(char*, float, float, float, float) {}
+
 template <int G>
 __device__ __forceinline__ float group_sum(float v) {
 #pragma unroll
@@ -109,9 +130,11 @@ __device__ __forceinline__ void group_transpose_sum(float (&v)[NV], int j) {
 // ---------------------------------------------------------------------------------------------
 // FUSED: `loc` / `aw` hold raw offsets / logits (see fused_resolve); grad_loc / grad_aw then receive the gradients
 // w.r.t. the raw offsets / logits (softmax backward and the 1/(W,H) scaling folded in).
-template <typename T, int G, int LT, int PT, int MINB, bool FUSED = false>
+// PACK (16-bit T only): grad_value is T storage and the scatter uses packed 16-bit reductions (see red_add_16x4).
+template <typename T, int G, int LT, int PT, int MINB, bool FUSED = false, bool PACK = false>
 __global__ void __launch_bounds__(kThreads, MINB) msda_bwd_vec_kernel(const Params p) {
   static_assert(!FUSED || LT > 0, "the fused entry needs compile-time L, P");
+  static_assert(!PACK || sizeof(T) == 2, "packed reductions are for the 16-bit value types");
   using V = VecB<T>;
   constexpr int kCpl = V::kCpl;
   constexpr int kGpw = 32 / G;
@@ -123,7 +146,7 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_bwd_vec_kernel(const Para
   const int LP = L * P;
   const int MD = p.M * p.D;
   const unsigned MDb = (unsigned)MD * (unsigned)sizeof(T);  // bytes between neighbouring tokens (value)
-  const unsigned MDf = (unsigned)MD * 4u;                    // same in the fp32 grad_value accumulator
+  const unsigned MDf = PACK ? MDb : (unsigned)MD * 4u;       // same in the grad_value accumulator (fp32, or T when PACK)
 
   __shared__ int sH[kMaxLevels], sW[kMaxLevels], sStart[kMaxLevels];
   if (threadIdx.x < L) {
@@ -143,7 +166,7 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_bwd_vec_kernel(const Para
 
   const size_t slab = (size_t)bc.b * p.S * MD + (size_t)bc.m * p.D;
   const char* __restrict__ vb = reinterpret_cast<const char*>(p.value) + slab * sizeof(T) + j * V::kLaneBytes;
-  char* __restrict__ gvb = reinterpret_cast<char*>(p.grad_value) + slab * 4u + j * (kCpl * 4);  // fp32 accumulator
+  char* __restrict__ gvb = reinterpret_cast<char*>(p.grad_value) + slab * (PACK ? sizeof(T) : 4u) + j * (kCpl * (PACK ? (int)sizeof(T) : 4));
   const float* __restrict__ loc = reinterpret_cast<const float*>(p.loc);
   const float* __restrict__ aw = reinterpret_cast<const float*>(p.aw);
   const T* __restrict__ gout = reinterpret_cast<const T*>(p.grad_out);
@@ -278,12 +301,20 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_bwd_vec_kernel(const Para
           s_h = hw * (u3 - u1) + flw * (u4 - u2);
           // scatter: grad_value[corner k] += (w_k * attn) * grad_out
           const float a1 = w1 * fa, a2 = w2 * fa, a3 = w3 * fa, a4 = w4 * fa;
+          if constexpr (PACK) {
+            static_assert(kCpl == 4, "one packed reduction per lane per corner");
+            if (m1) red_add_16x4<T>(const_cast<char*>(ptr_madd(gvb, t1, MDf)), a1 * go.v[0], a1 * go.v[1], a1 * go.v[2], a1 * go.v[3]);
+            if (m2) red_add_16x4<T>(const_cast<char*>(ptr_madd(gvb, t2, MDf)), a2 * go.v[0], a2 * go.v[1], a2 * go.v[2], a2 * go.v[3]);
+            if (m3) red_add_16x4<T>(const_cast<char*>(ptr_madd(gvb, t3, MDf)), a3 * go.v[0], a3 * go.v[1], a3 * go.v[2], a3 * go.v[3]);
+            if (m4) red_add_16x4<T>(const_cast<char*>(ptr_madd(gvb, t4, MDf)), a4 * go.v[0], a4 * go.v[1], a4 * go.v[2], a4 * go.v[3]);
+          } else {
 #pragma unroll
-          for (int c0 = 0; c0 < kCpl; c0 += 4) {
-            if (m1) red_add_v4(reinterpret_cast<float*>(const_cast<char*>(ptr_madd(gvb, t1, MDf))) + c0, a1 * go.v[c0], a1 * go.v[c0 + 1], a1 * go.v[c0 + 2], a1 * go.v[c0 + 3]);
-            if (m2) red_add_v4(reinterpret_cast<float*>(const_cast<char*>(ptr_madd(gvb, t2, MDf))) + c0, a2 * go.v[c0], a2 * go.v[c0 + 1], a2 * go.v[c0 + 2], a2 * go.v[c0 + 3]);
-            if (m3) red_add_v4(reinterpret_cast<float*>(const_cast<char*>(ptr_madd(gvb, t3, MDf))) + c0, a3 * go.v[c0], a3 * go.v[c0 + 1], a3 * go.v[c0 + 2], a3 * go.v[c0 + 3]);
-            if (m4) red_add_v4(reinterpret_cast<float*>(const_cast<char*>(ptr_madd(gvb, t4, MDf))) + c0, a4 * go.v[c0], a4 * go.v[c0 + 1], a4 * go.v[c0 + 2], a4 * go.v[c0 + 3]);
+            for (int c0 = 0; c0 < kCpl; c0 += 4) {
+              if (m1) red_add_v4(reinterpret_cast<float*>(const_cast<char*>(ptr_madd(gvb, t1, MDf))) + c0, a1 * go.v[c0], a1 * go.v[c0 + 1], a1 * go.v[c0 + 2], a1 * go.v[c0 + 3]);
+              if (m2) red_add_v4(reinterpret_cast<float*>(const_cast<char*>(ptr_madd(gvb, t2, MDf))) + c0, a2 * go.v[c0], a2 * go.v[c0 + 1], a2 * go.v[c0 + 2], a2 * go.v[c0 + 3]);
+              if (m3) red_add_v4(reinterpret_cast<float*>(const_cast<char*>(ptr_madd(gvb, t3, MDf))) + c0, a3 * go.v[c0], a3 * go.v[c0 + 1], a3 * go.v[c0 + 2], a3 * go.v[c0 + 3]);
+              if (m4) red_add_v4(reinterpret_cast<float*>(const_cast<char*>(ptr_madd(gvb, t4, MDf))) + c0, a4 * go.v[c0], a4 * go.v[c0 + 1], a4 * go.v[c0 + 2], a4 * go.v[c0 + 3]);
+            }
           }
         }
         if constexpr (kTranspose) {
@@ -459,6 +490,31 @@ static cudaError_t launch_fused_t(const Params& p, int G, dim3 grid, cudaStream_
   return cudaErrorNotSupported;
 }
 
+// opt-in packed 16-bit scatter (see red_add_16x4): the adapter configurations only - G in {8, 16}, (L, P) in {(3,4), (1,4)}
+template <typename T, int G>
+static cudaError_t launch_packed_g(const Params& p, bool fused, dim3 grid, cudaStream_t s) {
+  if constexpr (sizeof(T) == 2) {
+    const bool l3 = p.L == 3 && p.P == 4, l1 = p.L == 1 && p.P == 4;
+    if (!l3 && !l1) return cudaErrorNotSupported;
+    if (fused) {
+      if (l3) msda_bwd_vec_kernel<T, G, 3, 4, 3, true, true><<<grid, kThreads, 0, s>>>(p);
+      else msda_bwd_vec_kernel<T, G, 1, 4, 3, true, true><<<grid, kThreads, 0, s>>>(p);
+    } else {
+      if (l3) msda_bwd_vec_kernel<T, G, 3, 4, 3, false, true><<<grid, kThreads, 0, s>>>(p);
+      else msda_bwd_vec_kernel<T, G, 1, 4, 3, false, true><<<grid, kThreads, 0, s>>>(p);
+    }
+    return cudaGetLastError();
+  } else {
+    return cudaErrorNotSupported;
+  }
+}
+template <typename T>
+static cudaError_t launch_packed_t(const Params& p, int G, bool fused, dim3 grid, cudaStream_t s) {
+  if (G == 8) return launch_packed_g<T, 8>(p, fused, grid, s);
+  if (G == 16) return launch_packed_g<T, 16>(p, fused, grid, s);
+  return cudaErrorNotSupported;
+}
+
 template <typename TO>
 static cudaError_t launch_cvt_t(const float* src, void* dst, size_t n, cudaStream_t s) {
   size_t blocks = (n / 8 + kThreads - 1) / kThreads;
@@ -481,8 +537,11 @@ cudaError_t bwd_vec_f16(const Params& p, int G, int minb, dim3 grid, cudaStream_
 cudaError_t bwd_fused_f16(const Params& p, int G, dim3 grid, cudaStream_t s);
 cudaError_t bwd_generic_f16(const Params& p, dim3 grid, cudaStream_t s);
 cudaError_t bwd_cvt_f16(const float* src, void* dst, size_t n, cudaStream_t s);
+cudaError_t bwd_packed_bf16(const Params& p, int G, bool fused, dim3 grid, cudaStream_t s);
+cudaError_t bwd_packed_f16(const Params& p, int G, bool fused, dim3 grid, cudaStream_t s);
 
 #if MSDA_TU == 1
+cudaError_t bwd_packed_bf16(const Params& p, int G, bool fused, dim3 grid, cudaStream_t s) { return launch_packed_t<__nv_bfloat16>(p, G, fused, grid, s); }
 cudaError_t bwd_vec_bf16(const Params& p, int G, int minb, dim3 grid, cudaStream_t s) { return launch_vec<__nv_bfloat16>(p, G, minb, grid, s); }
 cudaError_t bwd_fused_bf16(const Params& p, int G, dim3 grid, cudaStream_t s) { return launch_fused_t<__nv_bfloat16>(p, G, grid, s); }
 cudaError_t bwd_generic_bf16(const Params& p, dim3 grid, cudaStream_t s) {
@@ -491,6 +550,7 @@ cudaError_t bwd_generic_bf16(const Params& p, dim3 grid, cudaStream_t s) {
 }
 cudaError_t bwd_cvt_bf16(const float* src, void* dst, size_t n, cudaStream_t s) { return launch_cvt_t<__nv_bfloat16>(src, dst, n, s); }
 #elif MSDA_TU == 2
+cudaError_t bwd_packed_f16(const Params& p, int G, bool fused, dim3 grid, cudaStream_t s) { return launch_packed_t<__half>(p, G, fused, grid, s); }
 cudaError_t bwd_vec_f16(const Params& p, int G, int minb, dim3 grid, cudaStream_t s) { return launch_vec<__half>(p, G, minb, grid, s); }
 cudaError_t bwd_fused_f16(const Params& p, int G, dim3 grid, cudaStream_t s) { return launch_fused_t<__half>(p, G, grid, s); }
 cudaError_t bwd_generic_f16(const Params& p, dim3 grid, cudaStream_t s) {
@@ -525,6 +585,14 @@ cudaError_t launch_backward(const Params& p, int dtype, bool vec_ok, int G, int 
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
+}
+
+// `p.grad_value` = the zero-filled bf16 / fp16 grad_value itself. cudaErrorNotSupported when there is no packed kernel.
+cudaError_t launch_backward_packed16(const Params& p, int dtype, int G, bool fused, cudaStream_t s) {
+  const dim3 grid((unsigned)((size_t)p.N * p.nchunk * p.M));
+  if (dtype == MSDA_BF16) return bwd_packed_bf16(p, G, fused, grid, s);
+  if (dtype == MSDA_F16) return bwd_packed_f16(p, G, fused, grid, s);
+  return cudaErrorNotSupported;
 }
 
 cudaError_t launch_cvt_f32_bf16(const float* src, void* dst, size_t n, int dtype, cudaStream_t s) {

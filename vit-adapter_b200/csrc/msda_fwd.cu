@@ -11,7 +11,9 @@
 //   * the geometry of a point is computed ONCE, by one lane of the group: corner rows are clamped
 //     into the level (so the four gathers need no predicate and no zero-fill), the bilinear weights
 //     are pre-multiplied with the attention weight and zeroed for corners the reference skips, and
-//     the lot is broadcast with 5 warp shuffles (packed offset+flags, 4 weights),
+//     the lot (packed offset+flags, 4 weights) is handed to the group through a 32-byte record in the
+//     warp's shared-memory scratch: one LDS.128 + one LDS.32 per point instead of 5 warp shuffles on
+//     the same LSU pipe the gathers saturate (round 1: 41 % of the pipe's wavefronts were shuffles),
 //   * out is written exactly once (no at::zeros memset as in ms_deform_attn_cuda.cu:54).
 #include "msda_common.cuh"
 
@@ -37,6 +39,10 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_fwd_vec_kernel(const Para
   const unsigned MDb = (unsigned)MD * (unsigned)sizeof(T);  // bytes between neighbouring tokens
 
   __shared__ int sH[kMaxLevels], sW[kMaxLevels], sStart[kMaxLevels];
+  // per-warp tap scratch: one row per (b,q,m) group of the warp, G records of 32 bytes (4 weights | offset+flags, row
+  // step) + 16 bytes of padding, so that the records the 32/G groups read together sit in different bank groups
+  constexpr int kTapRow = 2 * G + 1;  // uint4 per group row
+  __shared__ uint4 s_tap[kWarps * kGpw * kTapRow];
   if (threadIdx.x < L) {
     sH[threadIdx.x] = (int)p.shapes[2 * threadIdx.x];
     sW[threadIdx.x] = (int)p.shapes[2 * threadIdx.x + 1];
@@ -51,6 +57,8 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_fwd_vec_kernel(const Para
   const BlockCoord bc = block_coord(p);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = lane / G, j = lane % G;
+  const unsigned tap_row = (unsigned)__cvta_generic_to_shared(s_tap) + (unsigned)((warp * kGpw + grp) * kTapRow) * 16u;
+  const unsigned tap_mine = tap_row + (unsigned)j * 32u;
 
   // CTA-uniform slab base (batch b, head m) + this lane's 16 bytes inside a D-row
   const char* __restrict__ vb = reinterpret_cast<const char*>(p.value) +
@@ -131,20 +139,23 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_fwd_vec_kernel(const Para
         }
         tap = point_tap(xy.x, xy.y, a, sH[l], sW[l], sStart[l], MDb);
       }
+      // ---- hand-over: every lane publishes the point it prepared ------------------------------------
+      __syncwarp();  // the previous round's readers are done with the records
+      asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(tap_mine), "f"(tap.w[0]), "f"(tap.w[1]), "f"(tap.w[2]), "f"(tap.w[3]) : "memory");
+      asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(tap_mine + 16u), "r"(tap.offf), "r"(tap.rowstep) : "memory");
+      __syncwarp();
       // ---- consumers: every lane of the group gathers its 16 bytes for each prepared point ----
 #pragma unroll
       for (int jj = 0; jj < G; ++jj) {
         if (r0 + jj < LP) {  // uniform
-          const unsigned of = __shfl_sync(0xffffffffu, tap.offf, jj, G);
-          const float a1 = __shfl_sync(0xffffffffu, tap.w[0], jj, G);
-          const float a2 = __shfl_sync(0xffffffffu, tap.w[1], jj, G);
-          const float a3 = __shfl_sync(0xffffffffu, tap.w[2], jj, G);
-          const float a4 = __shfl_sync(0xffffffffu, tap.w[3], jj, G);
-          unsigned rs;
+          float a1, a2, a3, a4;
+          unsigned of, rs;
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a1), "=f"(a2), "=f"(a3), "=f"(a4) : "r"(tap_row + jj * 32u));
           if (kStatic) {
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(of) : "r"(tap_row + jj * 32u + 16u));
             rs = rsl[(r0 + jj) / (kStatic ? PT : 1)];  // level is a compile-time constant here
           } else {
-            rs = __shfl_sync(0xffffffffu, tap.rowstep, jj, G);
+            asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(of), "=r"(rs) : "r"(tap_row + jj * 32u + 16u));
           }
           // four corner addresses in 4 IMAD.WIDE (64-bit base + 32-bit offset / flag * step)
           const char* p1 = ptr_add(vb, of & ~15u);

@@ -5,10 +5,11 @@
 // addresses) at ~0.49 rows per SM-cycle (142 rows/ns chip-wide; the texture path is no better), and
 // the L1-path forward (msda_fwd.cu) sits on that ceiling; from shared memory the same pattern costs one
 // LSU wavefront (~1 cycle) per row.
-// Measured outcome (profiles/r1_fwd_smem_vs_l1.md): with the gathers at 1 cycle per row the 5 broadcast
+// Measured outcome, round 1 (profiles/r1_fwd_smem_vs_l1.md): with the gathers at 1 cycle per row the 5 broadcast
 // shuffles per point (also LSU wavefronts) become 1/4 of the pipe load, and the kernel ends up at ~79 % of
 // the same LSU data pipe: ViT-Adapter-B bs16 Extractor 115.6 vs 121.8 us fp32, 77.8 vs 97.3 us bf16;
-// Injector (levels 1+2 staged, level 0 still through L1) 98-115 vs 97 us. Not a robust win, so opt-in.
+// Injector (levels 1+2 staged, level 0 still through L1) 98-115 vs 97 us. Round 2 hands the taps over through
+// shared-memory records (one LDS.128 + one LDS.32 per point) instead of shuffles; see profiles/r2_fwd_smem_*.
 //
 // Design. A CTA owns (batch b, head m, a long chunk of queries). For every level that fits
 // (plan made on the host, plan_forward_smem in msda_abi.cu) it copies that head's [H*W, D] map into
@@ -66,12 +67,17 @@ __global__ void __launch_bounds__(NT, 1) msda_fwd_smem_kernel(const Params p, co
   constexpr unsigned kRowB = (unsigned)(G * 16);  // bytes of one head-row (D * sizeof(T))
 
   extern __shared__ __align__(128) unsigned char smem[];
+  // per-warp tap scratch (as in msda_fwd.cu): 32-byte records (4 weights | offset), rows padded by 16 bytes
+  constexpr int kTapRow = 2 * G + 1;
+  __shared__ uint4 s_tap[kWarpsNT * kGpw * kTapRow];
 
   const int MD = p.M * p.D;
   const unsigned MDb = (unsigned)MD * (unsigned)sizeof(T);
   const BlockCoord bc = block_coord(p);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = lane / G, j = lane % G;
+  const unsigned tap_row = smem_u32(s_tap) + (unsigned)((warp * kGpw + grp) * kTapRow) * 16u;
+  const unsigned tap_mine = tap_row + (unsigned)j * 32u;
 
   const char* __restrict__ slab = reinterpret_cast<const char*>(p.value) +
                                   ((size_t)bc.b * p.S * MD + (size_t)bc.m * p.D) * sizeof(T);
@@ -173,16 +179,20 @@ __global__ void __launch_bounds__(NT, 1) msda_fwd_smem_kernel(const Params p, co
           offf = tap_offset(g, H, W, plan.start[l], MDb);
         }
       }
+      // ---- hand-over through the warp's scratch (one LDS.128 + one LDS.32 per point instead of 5 shuffles) ------
+      __syncwarp();
+      asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(tap_mine), "f"(w0), "f"(w1), "f"(w2), "f"(w3) : "memory");
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(tap_mine + 16u), "r"(offf) : "memory");
+      __syncwarp();
       // ---- consumers -----------------------------------------------------------------------------------
 #pragma unroll
       for (int jj = 0; jj < G; ++jj) {
         if (r0 + jj < LP) {
           const int l = (r0 + jj) / PT;  // compile-time after unrolling
-          const unsigned of = __shfl_sync(0xffffffffu, offf, jj, G);
-          const float a1 = __shfl_sync(0xffffffffu, w0, jj, G);
-          const float a2 = __shfl_sync(0xffffffffu, w1, jj, G);
-          const float a3 = __shfl_sync(0xffffffffu, w2, jj, G);
-          const float a4 = __shfl_sync(0xffffffffu, w3, jj, G);
+          float a1, a2, a3, a4;
+          unsigned of;
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a1), "=f"(a2), "=f"(a3), "=f"(a4) : "r"(tap_row + jj * 32u));
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(of) : "r"(tap_row + jj * 32u + 16u));
           if (plan.staged & (1u << l)) {  // uniform
             const unsigned s1 = sb + of, s3 = s1 + rsl[l];
             const V v1 = lds_vec<T>(s1);
@@ -223,14 +233,9 @@ __global__ void __launch_bounds__(NT, 1) msda_fwd_smem_kernel(const Params p, co
 template <typename T, int G, int LT, int PT, int NT>
 static cudaError_t launch_one(const Params& p, const SmemPlan& plan, dim3 grid, cudaStream_t s) {
   auto kern = msda_fwd_smem_kernel<T, G, LT, PT, NT>;
-  static thread_local int configured_dev = -1;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (configured_dev != dev) {
-    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
-    if (e != cudaSuccess) return e;
-    configured_dev = dev;
-  }
+  // static (tap scratch) + dynamic (level maps) shared memory share the 227 KB of a CTA: ask for what this plan needs
+  const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total_bytes);
+  if (e != cudaSuccess) return e;
   kern<<<grid, NT, plan.total_bytes, s>>>(p, plan);
   return cudaGetLastError();
 }
