@@ -590,6 +590,9 @@ def run_ours(args):
         from bench_step import step_bench
         step_block = {}
         plans = [('B_512_train_bf16_2img_eager', dict(variant='B', image=512, batch=2, amp=True, graph=False, steps=10, warmup=5)),
+                 # the same eager step with vit_adapter_b200.adapter.SyncBatchNormNoHostSync in the SPM / output norms (identical
+                 # statistics and results; torch's SyncBatchNorm synchronises the host 3x per layer and forward)
+                 ('B_512_train_bf16_2img_eager_nosync_bn', dict(variant='B', image=512, batch=2, amp=True, graph=False, steps=10, warmup=5, bn='nosync')),
                  ('B_512_train_bf16_2img_graph', dict(variant='B', image=512, batch=2, amp=True, graph=True, steps=20, warmup=5)),
                  ('L_896_train_bf16_1img_cp_eager', dict(variant='L', image=896, batch=1, amp=True, with_cp=True, graph=False, steps=5, warmup=3)),
                  ('L_896_train_bf16_1img_cp_graph', dict(variant='L', image=896, batch=1, amp=True, with_cp=True, graph=True, steps=10, warmup=3))]
@@ -599,7 +602,7 @@ def run_ours(args):
                 used_graph_ddp = used_graph_ddp or (kw['graph'] and world > 1)
                 step_block[key] = {'img_per_s': r['value'], 'ms_per_step': r['ms_per_step'], 'n_gpus': r['n_gpus'],
                                    'allreduce_bytes': r['allreduce_bytes'], 'allreduce_ms_exposed': r['allreduce_ms_exposed'],
-                                   'cuda_graph': r['cuda_graph'], 'msda_kernel_launches': r['msda_kernel_launches'],
+                                   'cuda_graph': r['cuda_graph'], 'batchnorm': r['batchnorm'], 'msda_kernel_launches': r['msda_kernel_launches'],
                                    'params_total': r['config']['params_total'], 'params_adapter': r['config']['params_adapter'],
                                    'workload': r['config']['workload'], 'parallelism': r['config']['parallelism']}
             except Exception as exc:  # a failing model-level block must not cost the operator bench line

@@ -66,7 +66,10 @@ class MiniViTAdapter(nn.Module):
         from vit_adapter_b200.adapter import InteractionBlock, SpatialPriorModule
         c = CFG[variant]
         d = c['embed']
-        bn = nn.SyncBatchNorm if sync_bn else nn.BatchNorm2d
+        if sync_bn == 'nosync':
+            from vit_adapter_b200.adapter import SyncBatchNormNoHostSync as bn
+        else:
+            bn = nn.SyncBatchNorm if sync_bn else nn.BatchNorm2d
         self.embed = d
         self.idx = c['idx']
         self.patch_embed = nn.Conv2d(3, d, 16, 16)
@@ -177,13 +180,16 @@ def add_step_args(ap):
                          '(segmentation/README.md:24); off by default in the torch of this image')
     ap.add_argument('--graph', action='store_true',
                     help='capture the whole step (forward, backward, optimizer, and under torchrun the DDP all-reduce) in ONE CUDA graph and replay it')
-    ap.add_argument('--bn', default='sync', choices=['sync', 'local'],
+    ap.add_argument('--bucket-cap-mb', type=int, default=None, help='DDP bucket size (default: torch, 25 MB)')
+    ap.add_argument('--grad-bf16', action='store_true', help="DDP's stock bf16_compress_hook on the gradient all-reduce")
+    ap.add_argument('--bn', default='sync', choices=['sync', 'local', 'nosync'],
                     help="'local': plain BatchNorm under DDP (NOT the reference's training recipe) - isolates what SyncBatchNorm's "
-                         'forward costs the eager step: three host synchronisations per layer')
+                         "forward costs the eager step: three host synchronisations per layer; 'nosync': "
+                         'vit_adapter_b200.adapter.SyncBatchNormNoHostSync (same statistics, no host synchronisation)')
 
 
 def step_bench(variant='B', mode='train', image=512, batch=2, amp=False, with_cp=False, op='ours', reference_sequence=False,
-               tf32=False, graph=False, steps=10, warmup=3, measure_comm=True, bn='sync'):
+               tf32=False, graph=False, steps=10, warmup=3, measure_comm=True, bn='sync', bucket_cap_mb=None, grad_bf16=False):
     """One model-level measurement on the CURRENT device / process group (the caller owns torch.distributed): returns the
     result dict. Under a process group the net is wrapped in DDP (gradient all-reduce over NCCL) with SyncBatchNorm, as the
     reference trains (segmentation/dist_train.sh:8-9, configs/_base_/default_runtime.py:9).
@@ -210,7 +216,7 @@ def step_bench(variant='B', mode='train', image=512, batch=2, amp=False, with_cp
     vab.set_amp_value_dtype(torch.bfloat16 if amp else torch.float32)
 
     torch.manual_seed(1234 + rank)
-    net = Net(variant, sync_bn=(ddp and bn == 'sync'), with_cp=with_cp).to(dev)
+    net = Net(variant, sync_bn=(bn if ddp and bn in ('sync', 'nosync') else False), with_cp=with_cp).to(dev)
     if reference_sequence:
         for m in net.modules():
             for flag in ('fused_norm', 'token_kernel', 'fused', 'merge_query_linears', 'colsum_bias_grad'):
@@ -219,17 +225,21 @@ def step_bench(variant='B', mode='train', image=512, batch=2, amp=False, with_cp
     n_params = sum(p.numel() for p in net.parameters())
     n_adapter = sum(p.numel() for n, p in net.named_parameters() if 'interactions' in n or 'spm' in n)
     model = net
+    ddp_kw = {} if bucket_cap_mb is None else {'bucket_cap_mb': bucket_cap_mb}
     if ddp and mode == 'train':
         if graph:
             # DDP under whole-step capture (torch docs, "Usage with DistributedDataParallel"): construct DDP on a side
             # stream, and warm up >= 11 eager iterations so that bucket rebuilding is over before the capture
             side0 = torch.cuda.Stream()
             with torch.cuda.stream(side0):
-                model = nn.parallel.DistributedDataParallel(net, device_ids=[dev.index], gradient_as_bucket_view=True)
+                model = nn.parallel.DistributedDataParallel(net, device_ids=[dev.index], gradient_as_bucket_view=True, **ddp_kw)
             torch.cuda.current_stream().wait_stream(side0)
             warmup = max(warmup, 11)
         else:
-            model = nn.parallel.DistributedDataParallel(net, device_ids=[dev.index], gradient_as_bucket_view=True)
+            model = nn.parallel.DistributedDataParallel(net, device_ids=[dev.index], gradient_as_bucket_view=True, **ddp_kw)
+        if grad_bf16:   # DDP's stock communication hook: gradients cross NVLink in bf16 (half the all-reduce bytes)
+            from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+            model.register_comm_hook(None, default_hooks.bf16_compress_hook)
     opt = torch.optim.AdamW(net.parameters(), lr=6e-5, weight_decay=0.01, fused=True, capturable=graph) if mode == 'train' else None
     img = torch.randn(batch, 3, image, image, device=dev)
     lab = torch.randint(0, 150, (batch, image // 4, image // 4), device=dev)
@@ -311,7 +321,7 @@ def step_bench(variant='B', mode='train', image=512, batch=2, amp=False, with_cp
         'higher_is_better': True, 'scaling': 'weak', 'dtype': 'bf16-autocast' if amp else 'f32', 'data': 'synthetic',
         'op': op, 'adapter': 'reference op sequence' if reference_sequence else 'this repo (fused norm / dwconv / softmax+locations)',
         'msda_kernel_launches': launches, 'cuda_graph': bool(graph), 'tf32_gemm': bool(tf32),
-        'allreduce_bytes': allreduce_bytes, 'allreduce_ms_exposed': exposed, 'batchnorm': 'SyncBatchNorm' if (ddp and bn == 'sync') else 'BatchNorm2d',
+        'allreduce_bytes': allreduce_bytes // (2 if grad_bf16 else 1), 'ddp_bucket_cap_mb': bucket_cap_mb, 'ddp_grad_bf16': bool(grad_bf16), 'allreduce_ms_exposed': exposed, 'batchnorm': ('SyncBatchNorm' if bn == 'sync' else 'SyncBatchNormNoHostSync' if bn == 'nosync' else 'BatchNorm2d') if ddp else 'BatchNorm2d',
         'config': {'workload': 'ViT-Adapter-%s backbone (this repo\'s adapter modules + MSDeformAttn) + stand-in head, %dx%d, '
                                '%d img/GPU, %s' % (variant, image, image, batch, mode),
                    'params_total': n_params, 'params_adapter': n_adapter, 'with_cp': with_cp,
@@ -349,7 +359,7 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
     res = step_bench(variant=args.variant, mode=args.mode, image=args.image, batch=args.batch, amp=args.amp, with_cp=args.with_cp,
                      op=args.op, reference_sequence=args.reference_sequence, tf32=args.tf32, graph=args.graph, steps=args.steps,
-                     warmup=args.warmup, bn=args.bn)
+                     warmup=args.warmup, bn=args.bn, bucket_cap_mb=args.bucket_cap_mb, grad_bf16=args.grad_bf16)
     if rank == 0:
         os.write(real_stdout, (json.dumps(res) + '\n').encode())
     if world > 1:
