@@ -1,9 +1,11 @@
-"""GPU parity tests of the cell-bucketed backward (csrc/msda_bwd_cell.cu) against the C oracle, the general
-(query-order) backward of the same library and, where built, the reference's own CUDA kernels.
+"""GPU parity tests of the slab-sorted backward (csrc/msda_bwd_sorted.cu) against the C oracle, the query-order backward of
+the same library and, where built, the reference's own CUDA kernels.
 
-The cell kernel is opt-in for D in {32, 64} (`set_tuning(bwd_cell=2)`; it measured slower than the query-order kernel);
-`bwd_cell_chunk=n` forces short query chunks so that chunk boundaries, partially filled batches of 32 and cell runs that straddle two
-warps are all exercised on small inputs. Tolerances: fp32 gradients 1e-4 relative (summation order), bf16 1e-2."""
+The sorted backward applies to D in {32, 64}; it is chosen automatically where it measured faster (D = 64, long cell runs) and
+`set_tuning(bwd_sorted=2)` forces it wherever it applies (`=1` switches it off).
+The cases cover ranges that end inside a batch of 32 positions, cell runs that straddle two warps / two CTAs, empty slabs,
+border cells whose clamped key aliases several cells, runtime (L, P) and long runs on hot counters.
+Tolerances: fp32 gradients 1e-4 relative (summation order), bf16 1e-2, fp16 2e-3."""
 import pytest
 import torch
 
@@ -47,18 +49,17 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize('chunk', [0, 7, 33], ids=['chunk-auto', 'chunk-7', 'chunk-33'])
 @pytest.mark.parametrize('cfg', CASES, ids=[c[0] for c in CASES])
-def test_cell_backward_vs_oracle_f32(cfg, chunk):
+def test_sorted_backward_vs_oracle_f32(cfg):
     _, N, M, D, Lq, shapes, P, dist = cfg
     inp = make_inputs(N, M, D, Lq, shapes, P, seed=11, dist=dist)
     wgv, wgl, wga = c_oracle.backward(inp['value'], inp['shapes'], inp['lsi'], inp['loc'], inp['aw'], inp['grad_out'])
-    gv, gl, ga = _bwd(inp, torch.float32, bwd_cell=2, bwd_cell_chunk=chunk)
+    gv, gl, ga = _bwd(inp, torch.float32, bwd_sorted=2)
     torch.testing.assert_close(gv, wgv, rtol=1e-4, atol=1e-4 * _scale(wgv))
     torch.testing.assert_close(gl, wgl, rtol=1e-4, atol=1e-4 * _scale(wgl))
     torch.testing.assert_close(ga, wga, rtol=1e-4, atol=1e-4 * _scale(wga))
     # and against the query-order kernel of this library (same tolerance: only the summation order differs)
-    ogv, ogl, oga = _bwd(inp, torch.float32, bwd_cell=1, bwd_sorted=1)
+    ogv, ogl, oga = _bwd(inp, torch.float32, bwd_sorted=1)
     torch.testing.assert_close(gv, ogv, rtol=1e-4, atol=1e-4 * _scale(ogv))
     torch.testing.assert_close(gl, ogl, rtol=1e-4, atol=1e-4 * _scale(ogl))
     torch.testing.assert_close(ga, oga, rtol=1e-4, atol=1e-4 * _scale(oga))
@@ -66,24 +67,24 @@ def test_cell_backward_vs_oracle_f32(cfg, chunk):
 
 @pytest.mark.parametrize('low', [torch.bfloat16, torch.float16], ids=['bf16', 'f16'])
 @pytest.mark.parametrize('cfg', CASES[:6], ids=[c[0] for c in CASES[:6]])
-def test_cell_backward_vs_oracle_16bit(cfg, low):
+def test_sorted_backward_vs_oracle_16bit(cfg, low):
     _, N, M, D, Lq, shapes, P, dist = cfg
     inp = make_inputs(N, M, D, Lq, shapes, P, seed=12, dist=dist)
     vq, goq = inp['value'].to(low).float(), inp['grad_out'].to(low).float()
     wgv, wgl, wga = c_oracle.backward(vq, inp['shapes'], inp['lsi'], inp['loc'], inp['aw'], goq)
     tol = 1e-2 if low == torch.bfloat16 else 2e-3
-    gv, gl, ga = _bwd(inp, low, bwd_cell=2, bwd_cell_chunk=19)
+    gv, gl, ga = _bwd(inp, low, bwd_sorted=2)
     torch.testing.assert_close(gv, wgv, rtol=tol, atol=tol * _scale(wgv))
     # location / weight gradients are fp32 sums of exactly representable products: fp32-grade agreement
     torch.testing.assert_close(gl, wgl, rtol=1e-4, atol=1e-4 * _scale(wgl))
     torch.testing.assert_close(ga, wga, rtol=1e-4, atol=1e-4 * _scale(wga))
 
 
-def test_cell_backward_out_of_range_points_get_zero_gradients():
+def test_sorted_backward_out_of_range_points_get_zero_gradients():
     inp = make_inputs(1, 2, 32, 40, [(5, 6), (3, 3)], 4, seed=13, dist='uniform')
     inp['loc'][:, ::2] = 7.5          # every other query samples far outside the maps
     inp['loc'][:, 1, :, :, 0] = -3.0
-    gv, gl, ga = _bwd(inp, torch.float32, bwd_cell=2)
+    gv, gl, ga = _bwd(inp, torch.float32, bwd_sorted=2)
     wgv, wgl, wga = c_oracle.backward(inp['value'], inp['shapes'], inp['lsi'], inp['loc'], inp['aw'], inp['grad_out'])
     assert float(gl[:, ::2].abs().max()) == 0.0 and float(ga[:, ::2].abs().max()) == 0.0
     torch.testing.assert_close(gv, wgv, rtol=1e-4, atol=1e-4 * _scale(wgv))
@@ -91,15 +92,15 @@ def test_cell_backward_out_of_range_points_get_zero_gradients():
     torch.testing.assert_close(ga, wga, rtol=1e-4, atol=1e-4 * _scale(wga))
     # nothing in range at all: grad_value stays zero, the other gradients are written (not left uninitialised)
     inp['loc'][:] = 9.0
-    gv, gl, ga = _bwd(inp, torch.float32, bwd_cell=2)
+    gv, gl, ga = _bwd(inp, torch.float32, bwd_sorted=2)
     assert float(gv.abs().max()) == 0.0 and float(gl.abs().max()) == 0.0 and float(ga.abs().max()) == 0.0
 
 
-def test_cell_backward_all_points_in_one_cell():
+def test_sorted_backward_all_points_in_one_cell():
     """Every sample of every query lands in the same bilinear cell: one run per warp range, hot counters."""
     inp = make_inputs(2, 4, 32, 333, [(9, 9)], 4, seed=14, dist='uniform')
     inp['loc'] = (0.5 + 0.02 * (inp['loc'] - 0.5)).contiguous()
-    gv, gl, ga = _bwd(inp, torch.float32, bwd_cell=2)
+    gv, gl, ga = _bwd(inp, torch.float32, bwd_sorted=2)
     wgv, wgl, wga = c_oracle.backward(inp['value'], inp['shapes'], inp['lsi'], inp['loc'], inp['aw'], inp['grad_out'])
     torch.testing.assert_close(gv, wgv, rtol=1e-4, atol=1e-4 * _scale(wgv))
     torch.testing.assert_close(gl, wgl, rtol=1e-4, atol=1e-4 * _scale(wgl))
@@ -108,27 +109,51 @@ def test_cell_backward_all_points_in_one_cell():
 
 @pytest.mark.skipif(not refcuda.available(), reason='oracle/_ref not built')
 @pytest.mark.parametrize('cfg', CASES[:5], ids=[c[0] for c in CASES[:5]])
-def test_cell_backward_vs_reference_cuda(cfg):
+def test_sorted_backward_vs_reference_cuda(cfg):
     _, N, M, D, Lq, shapes, P, dist = cfg
     inp = make_inputs(N, M, D, Lq, shapes, P, seed=15, dist=dist)
     g = {k: v.to(DEV) for k, v in inp.items()}
     rgv, rgl, rga = refcuda.backward(g['value'], g['shapes'], g['lsi'], g['loc'], g['aw'], g['grad_out'])
-    gv, gl, ga = _bwd(inp, torch.float32, bwd_cell=2, bwd_cell_chunk=50)
+    gv, gl, ga = _bwd(inp, torch.float32, bwd_sorted=2)
     torch.testing.assert_close(gv, rgv.cpu(), rtol=1e-4, atol=1e-4 * _scale(rgv))
     torch.testing.assert_close(gl, rgl.cpu(), rtol=1e-4, atol=1e-4 * _scale(rgl))
     torch.testing.assert_close(ga, rga.cpu(), rtol=1e-4, atol=1e-4 * _scale(rga))
 
 
-def test_cell_backward_is_opt_in():
-    """With bwd_cell=2 the cell kernel runs, otherwise it does not (it measured slower than the query-order kernel, DESIGN.md
-    section 3). Both are one launch per call and agree to summation order."""
-    inp = make_inputs(2, 12, 32, 256, [(32, 32), (16, 16), (8, 8)], 4, seed=16, dist='adapter')
+def test_sorted_backward_selection():
+    """Without tuning the sorted backward (4 kernels: histogram, scan, scatter, walk) runs where it measured faster - 64
+    channels per head and >= 16 samples per value token and head - and the one-kernel query-order backward elsewhere;
+    bwd_sorted=2 / 1 force one or the other. They agree to summation order."""
+    dense64 = make_inputs(2, 6, 64, 1344, [(16, 16)], 4, seed=16, dist='adapter')      # 21 samples per token: sorted
     n0 = _cabi.launch_count()
-    gv, gl, ga = _bwd(inp, torch.float32, bwd_sorted=1)
+    gv, gl, ga = _bwd(dense64, torch.float32)
+    assert _cabi.launch_count() - n0 == 4
+    n0 = _cabi.launch_count()
+    ogv, ogl, oga = _bwd(dense64, torch.float32, bwd_sorted=1)
     assert _cabi.launch_count() - n0 == 1
-    dgv, dgl, dga = _bwd(inp, torch.float32, bwd_cell=1, bwd_sorted=1)
-    assert torch.equal(gl, dgl) and torch.equal(ga, dga)   # same kernel: deterministic outputs are bit-identical
-    cgv, cgl, cga = _bwd(inp, torch.float32, bwd_cell=2)
-    torch.testing.assert_close(cgv, gv, rtol=1e-4, atol=1e-4 * _scale(gv))
-    torch.testing.assert_close(cgl, gl, rtol=1e-4, atol=1e-4 * _scale(gl))
-    torch.testing.assert_close(cga, ga, rtol=1e-4, atol=1e-4 * _scale(ga))
+    torch.testing.assert_close(gv, ogv, rtol=1e-4, atol=1e-4 * _scale(ogv))
+    torch.testing.assert_close(gl, ogl, rtol=1e-4, atol=1e-4 * _scale(ogl))
+    torch.testing.assert_close(ga, oga, rtol=1e-4, atol=1e-4 * _scale(oga))
+    for inp in (make_inputs(2, 12, 32, 1344, [(16, 16)], 4, seed=16, dist='adapter'),              # 32 channels
+                make_inputs(2, 6, 64, 256, [(32, 32), (16, 16), (8, 8)], 4, seed=16, dist='adapter')):  # 2 samples per token
+        n0 = _cabi.launch_count()
+        _bwd(inp, torch.float32)
+        assert _cabi.launch_count() - n0 == 1
+        n0 = _cabi.launch_count()
+        _bwd(inp, torch.float32, bwd_sorted=2)
+        assert _cabi.launch_count() - n0 == 4
+    # a head dimension outside {32, 64} has no sorted kernel: one launch whatever the knob says
+    inp = make_inputs(1, 2, 16, 50, [(6, 6)], 4, seed=17, dist='uniform')
+    n0 = _cabi.launch_count()
+    _bwd(inp, torch.float32, bwd_sorted=2)
+    assert _cabi.launch_count() - n0 == 1
+
+
+def test_sorted_backward_many_warps_per_slab():
+    """A slab long enough for several CTAs of the walker (ranges of 32..256 positions per warp, runs cut at every boundary)."""
+    inp = make_inputs(1, 2, 32, 6000, [(12, 12)], 4, seed=18, dist='uniform')
+    wgv, wgl, wga = c_oracle.backward(inp['value'], inp['shapes'], inp['lsi'], inp['loc'], inp['aw'], inp['grad_out'])
+    gv, gl, ga = _bwd(inp, torch.float32, bwd_sorted=2)
+    torch.testing.assert_close(gv, wgv, rtol=1e-4, atol=1e-4 * _scale(wgv))
+    torch.testing.assert_close(gl, wgl, rtol=1e-4, atol=1e-4 * _scale(wgl))
+    torch.testing.assert_close(ga, wga, rtol=1e-4, atol=1e-4 * _scale(wga))

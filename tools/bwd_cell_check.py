@@ -26,7 +26,7 @@ def main():
     ap.add_argument('--chunks', default='0')
     ap.add_argument('--iters', type=int, default=20)
     ap.add_argument('--dist', default='adapter')
-    ap.add_argument('--mode', default='cell', choices=['cell', 'packed16'], help='which opt-in backward to compare with the default')
+    ap.add_argument('--mode', default='cell', choices=['cell', 'packed16', 'sorted'], help='which opt-in backward to compare with the default')
     ap.add_argument('--out', default=os.path.join(ROOT, 'gpurun_out', 'bwd_cell_check.jsonl'))
     args = ap.parse_args()
     peak = 6533.8
@@ -47,7 +47,7 @@ def main():
                     inp['loc'] = torch.rand(inp['loc'].shape, generator=g)
                 g = {k: v.to(DEV) for k, v in inp.items()}
                 call = lambda: _cabi.backward(g['value'], g['shapes'], g['lsi'], g['loc'], g['aw'], g['grad_out'], 64)
-                _cabi.set_tuning(bwd_cell=1)
+                _cabi.set_tuning(bwd_cell=1, bwd_sorted=1)   # baseline: the query-order kernel
                 ref = call()
                 t_old = timeit(call, args.iters, 3, flush)
                 torch.cuda.synchronize()
@@ -57,6 +57,8 @@ def main():
                         if dn == 'f32':
                             continue
                         _cabi.set_tuning(bwd_cell=0, bwd_packed16=2)
+                    elif args.mode == 'sorted':
+                        _cabi.set_tuning(bwd_cell=0, bwd_sorted=2)
                     else:
                         _cabi.set_tuning(bwd_cell=2, bwd_cell_chunk=int(ch))
                     got = call()
@@ -70,7 +72,7 @@ def main():
                                rel_err_gv_gl_ga=['%.2e' % e for e in errs])
                     print(json.dumps(row), flush=True)
                     out.write(json.dumps(row) + '\n')
-                _cabi.set_tuning(bwd_cell=0, bwd_cell_chunk=0, bwd_packed16=0)
+                _cabi.set_tuning(bwd_cell=0, bwd_cell_chunk=0, bwd_packed16=0, bwd_sorted=0)
     out.close()
 
 

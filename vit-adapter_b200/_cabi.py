@@ -502,7 +502,7 @@ def launch_count():
 def set_tuning(**kv):
     """Benchmark knobs, e.g. set_tuning(fwd_chunk=64, fwd_smem=1); value 0 restores the heuristic.
     Keys: fwd_chunk, bwd_chunk, fwd_min_ctas, bwd_min_ctas, fwd_smem, fwd_smem_threads, fwd_smem_chunks, fwd_wide,
-    bwd_cell (2 = the cell-bucketed backward), bwd_cell_chunk, bwd_packed16 (2 = packed 16-bit reductions into grad_value). The knobs are process-wide (see include/msda_b200.h)."""
+    bwd_cell (2 = the cell-bucketed backward), bwd_cell_chunk, bwd_packed16 (2 = packed 16-bit reductions into grad_value), bwd_sorted (slab-sorted backward: 0 = where it measured faster, 1 = never, 2 = wherever it applies). The knobs are process-wide (see include/msda_b200.h)."""
     global _WANT_HOST_SHAPES
     lib = load()
     for k, v in kv.items():

@@ -12,14 +12,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'lib')
 LIBNAME = 'libmsda_b200.so'
-SOURCES = ['msda_fwd.cu', 'msda_fwd_smem.cu', 'msda_bwd.cu', 'msda_bwd_cell.cu', 'adapter_dwconv.cu', 'adapter_layernorm.cu', 'adapter_colsum.cu', 'adapter_residual.cu', 'msda_abi.cu']
+SOURCES = ['msda_fwd.cu', 'msda_fwd_smem.cu', 'msda_bwd.cu', 'msda_bwd_cell.cu', 'msda_bwd_sorted.cu', 'adapter_dwconv.cu', 'adapter_layernorm.cu', 'adapter_colsum.cu', 'adapter_residual.cu', 'msda_abi.cu']
 # (source, extra flags, object name): msda_fwd.cu / msda_bwd.cu are compiled once per value dtype so that the three sets
 # of template instantiations build in parallel (MSDA_TU = 0: f32 + f64 + dispatch, 1: bf16, 2: f16)
 UNITS = [(s, [], s.replace('.cu', '.o')) for s in SOURCES] + [
     ('msda_fwd.cu', ['-DMSDA_TU=1'], 'msda_fwd_bf16.o'), ('msda_fwd.cu', ['-DMSDA_TU=2'], 'msda_fwd_f16.o'),
     ('msda_bwd.cu', ['-DMSDA_TU=1'], 'msda_bwd_bf16.o'), ('msda_bwd.cu', ['-DMSDA_TU=2'], 'msda_bwd_f16.o'),
-    ('msda_bwd_cell.cu', ['-DMSDA_TU=1'], 'msda_bwd_cell_bf16.o'), ('msda_bwd_cell.cu', ['-DMSDA_TU=2'], 'msda_bwd_cell_f16.o')]
-HEADERS = ['msda_common.cuh', os.path.join('..', '..', 'include', 'msda_b200.h')]
+    ('msda_bwd_cell.cu', ['-DMSDA_TU=1'], 'msda_bwd_cell_bf16.o'), ('msda_bwd_cell.cu', ['-DMSDA_TU=2'], 'msda_bwd_cell_f16.o'),
+    ('msda_bwd_sorted.cu', ['-DMSDA_TU=1'], 'msda_bwd_sorted_bf16.o'), ('msda_bwd_sorted.cu', ['-DMSDA_TU=2'], 'msda_bwd_sorted_f16.o')]
+HEADERS = ['msda_common.cuh', 'msda_cell_common.cuh', os.path.join('..', '..', 'include', 'msda_b200.h')]
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
     '-Xcompiler', '-fPIC',
@@ -59,7 +60,7 @@ def build(force=False, verbose=False):
     for s, extra, oname in UNITS:
         o = os.path.join(objdir, oname)
         objs.append(o)
-        cmd = [nvcc] + NVCC_FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + ['-c', '-o', o, os.path.join(CSRC, s)]
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get('MSDA_NVCC_EXTRA', '').split() + extra + (['-Xptxas', '-v'] if verbose else []) + ['-c', '-o', o, os.path.join(CSRC, s)]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, pr in procs:
         out, _ = pr.communicate()

@@ -61,12 +61,14 @@ struct CellPlan {
 int backward_cell_max_points();
 bool plan_backward_cell(int D, int LP, int esize, int qc, int hist_cap, unsigned budget, CellPlan* cp);
 cudaError_t launch_backward_cell(const Params& p, const CellPlan& cp, int dtype, cudaStream_t s);
+size_t backward_sorted_workspace_bytes(int N, int S, int M, int D, int L, int Lq, int P, int sm_count);
+cudaError_t launch_backward_sorted(const Params& p, int dtype, void* ws, int sm_count, int* launches, cudaStream_t s);
 cudaError_t launch_forward_smem(const Params& p, const SmemPlan& plan, int dtype, int G, int nt, cudaStream_t s);
 
 static thread_local char g_err[512] = "";
 constexpr bool kFwdWideDefault = false;  // flipped once measured faster (tuning key "fwd_wide" = 2 forces it)
 static std::atomic<uint64_t> g_launches{0};
-static std::atomic<int> g_qc_fwd{0}, g_qc_bwd{0}, g_minb_fwd{0}, g_minb_bwd{0}, g_smem_mode{0}, g_smem_nt{0}, g_smem_chunks{0}, g_fwd_wide{0}, g_bwd_cell{0}, g_bwd_cell_qc{0}, g_bwd_packed16{0};
+static std::atomic<int> g_qc_fwd{0}, g_qc_bwd{0}, g_minb_fwd{0}, g_minb_bwd{0}, g_smem_mode{0}, g_smem_nt{0}, g_smem_chunks{0}, g_fwd_wide{0}, g_bwd_cell{0}, g_bwd_cell_qc{0}, g_bwd_packed16{0}, g_bwd_sorted{0};
 
 static int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -318,6 +320,7 @@ int msda_set_tuning(const char* key, int32_t value) {
   else if (!strcmp(key, "bwd_cell")) slot = &g_bwd_cell;
   else if (!strcmp(key, "bwd_cell_chunk")) slot = &g_bwd_cell_qc;
   else if (!strcmp(key, "bwd_packed16")) slot = &g_bwd_packed16;
+  else if (!strcmp(key, "bwd_sorted")) slot = &g_bwd_sorted;
   if (!slot) return fail(MSDA_E_NULL, "msda_set_tuning: unknown key '%s'", key);
   slot->store(value);
   return 0;
@@ -393,9 +396,33 @@ int msda_forward_ex(const msda_dims* dims, int dtype, const void* value, const i
   return 0;
 }
 
+// fp32 accumulator of the 16-bit dtypes (first in the workspace), then the sort buffers of the slab-sorted backward
+static size_t accum_workspace_bytes(const msda_dims* d, int dtype) {
+  if (dtype != MSDA_BF16 && dtype != MSDA_F16) return 0;
+  return (size_t)d->batch * d->spatial_size * d->num_heads * d->channels * sizeof(float);
+}
+// Slab-sorted backward (msda_bwd_sorted.cu). Tuning key "bwd_sorted": 0 = where it measured faster, 1 = off, 2 = wherever it
+// applies. MEASURED (profiles/r2_bwd_sorted_vs_query_order.jsonl, B200, L2 flushed): the sort passes cost ~100 us at the bs-16
+// shapes and the walker spends ~25 instructions per sampled point whatever the row length, so it pays where a sample's four
+// row atomics are expensive (256-byte rows, D = 64) and cell runs are long (one level, >= 16 samples per cell): ViT-Adapter-S
+// Extractor 330 -> 282 us fp32 / 337 -> 265 us bf16, L 16x64 Extractor 200 -> 175 us bf16. At D = 32 it ties (B Extractor
+// 323 -> 319 us) or loses (Injectors, ~2 samples per cell: 0.85x), so those keep the query-order kernel.
+static size_t sorted_workspace_bytes(const msda_dims* d, int dtype) {
+  const int mode = g_bwd_sorted.load();
+  if (mode == 1) return 0;
+  if (!(dtype == MSDA_F32 || dtype == MSDA_BF16 || dtype == MSDA_F16)) return 0;
+  if (g_bwd_cell.load() == 2 || g_bwd_packed16.load() == 2) return 0;  // an explicitly requested opt-in kernel wins
+  if (mode != 2) {
+    const long long samples_per_slab = (long long)d->num_query * d->num_levels * d->num_point;
+    if (!(d->channels == 64 && samples_per_slab >= 16ll * d->spatial_size)) return 0;
+  }
+  return backward_sorted_workspace_bytes(d->batch, d->spatial_size, d->num_heads, d->channels, d->num_levels, d->num_query,
+                                         d->num_point, sm_count());
+}
+
 size_t msda_backward_workspace_bytes(const msda_dims* dims, int dtype) {
-  if (!dims || (dtype != MSDA_BF16 && dtype != MSDA_F16)) return 0;
-  return (size_t)dims->batch * dims->spatial_size * dims->num_heads * dims->channels * sizeof(float);
+  if (!dims) return 0;
+  return accum_workspace_bytes(dims, dtype) + sorted_workspace_bytes(dims, dtype);
 }
 
 int msda_backward(const msda_dims* dims, int dtype, const void* value, const int64_t* spatial_shapes,
@@ -451,7 +478,13 @@ int msda_backward(const msda_dims* dims, int dtype, const void* value, const int
   cudaError_t e = cudaMemsetAsync(accum, 0, accum_bytes, s);
   if (e != cudaSuccess) return cuda_fail(e, "msda_backward memset(grad_value)");
   CellPlan cplan;
-  if (vec && plan_cell(dims, dtype, p, &cplan)) {
+  const size_t sorted_bytes = sorted_workspace_bytes(dims, dtype);
+  if (vec && sorted_bytes > 0) {
+    int n = 0;
+    e = launch_backward_sorted(p, dtype, reinterpret_cast<char*>(workspace) + accum_workspace_bytes(dims, dtype), sm_count(), &n, s);
+    if (e != cudaSuccess) return cuda_fail(e, "msda_backward (slab-sorted) launch");
+    g_launches.fetch_add(n - 1);
+  } else if (vec && plan_cell(dims, dtype, p, &cplan)) {
     e = launch_backward_cell(p, cplan, dtype, s);
     if (e != cudaSuccess) return cuda_fail(e, "msda_backward (cell-bucketed) launch");
   } else {
@@ -530,7 +563,7 @@ int msda_backward_fused(const msda_dims* dims, int dtype, const void* value, con
       !((dims->num_levels == 3 || dims->num_levels == 1) && dims->num_point == 4))
     return fail(MSDA_E_UNSUPPORTED, "msda_backward_fused: no fused kernel for dtype=%d D=%d L=%d P=%d", dtype, dims->channels,
                 dims->num_levels, dims->num_point);
-  const size_t need = msda_backward_workspace_bytes(dims, dtype);
+  const size_t need = accum_workspace_bytes(dims, dtype);
   if (need > 0 && (!workspace || workspace_bytes < need || !aligned(workspace, 16)))
     return fail(MSDA_E_WORKSPACE, "msda_backward_fused: workspace of %zu bytes (16-byte aligned) required", need);
   cudaStream_t s = (cudaStream_t)stream;

@@ -1,0 +1,599 @@
+// msda_bwd_sorted.cu — slab-sorted backward of multi-scale deformable attention for sm_100a.
+//
+// Replaces the reference's col2im kernels (detection/ops/src/cuda/ms_deform_im2col_cuda.cuh:301-510, bilinear backward
+// :87-159). The reference - and msda_bwd.cu, the query-order path of this library - issue four row-wide atomics into
+// grad_value per sampled point: 16.5 M 128-byte RED rows for the ViT-Adapter-B Extractor at bs 16, which is exactly what the
+// L2's atomic units serve in 320 us. But grad_value of one (batch, head) SLAB has only S rows (1 024 for
+// that call), so ~84 contributions go to every row: the scatter is a segmented reduction in disguise.
+//
+// Pass 1 (msda_sort_slab_kernel, one CTA per slab): the slab's sampled points are SORTED BY THE BILINEAR CELL they fall in -
+// a counting sort whose histogram lives in shared memory (integer ATOMS only), 20 bytes per point written in cell order.
+// Pass 2 (msda_bwd_sorted_kernel): a group of D/4 lanes walks a contiguous range of the sorted list, 4 channels per lane:
+//   * the four value rows of the current cell and the four partial grad_value rows stay in REGISTERS for the whole run of
+//     points of that cell (4 x 4 + 4 x 4 floats per lane);
+//   * per point: ONE read of the query's grad_out row (the query-order kernel gathers four value rows and scatters four),
+//     16 FMAs for u_k = <grad_out, v_k> and 16 for the grad_value partials; corner weights and the row offset come as one
+//     20-byte broadcast record from the warp's shared-memory scratch, prepared 32 points at a time with one point per lane;
+//   * the partial dot products are reduced with a transposed shuffle network (D/4 values -> 1 per lane) and handed through
+//     shared memory to the lane that owns the point's record, which turns (u_1..u_4) into grad_attn_weight and
+//     grad_sampling_loc (the linear-in-the-corners algebra of msda_bwd.cu);
+//   * when the cell changes, the four partial rows leave with one REDG.E.ADD.F32x4 per lane each: row atomics per point
+//     drop from 4 to 4 / (points per cell run) - ~20 points per cell at the ViT-Adapter-B Extractor.
+// Nothing depends on where the reference points are: the sort is by the actual sampling location, so every input is
+// handled; an adversarial input (all points in one cell) degenerates to long runs, still correct.
+// The summation ORDER differs from the query-order kernel (and is not deterministic: positions inside a cell run come from
+// an atomic cursor), within the same tolerance class as any atomic scatter.
+#include "msda_cell_common.cuh"
+
+namespace msda {
+
+// Workspace carved by the host (launch_backward_sorted below); all pointers are device pointers into it.
+struct SortedPlan {
+  unsigned* cnt;  // [N*M][parts][S] histograms of clamped top-left tokens -> exclusive scan -> the parts' first positions
+  unsigned* nin;  // [N*M]      samples of the slab that pass the bounds test
+  uint4* rec;     // [N*M][cap] sorted: (lh, lw, attention weight, query * L*P + point)
+  unsigned* cw;   // [N*M][cap] sorted: cell word (msda_cell_common.cuh)
+  int cap;        // Lq * L * P: samples per slab
+  int ppw;        // sorted positions per warp of the walker (multiple of 32)
+  int ctas_per_slab;
+  int parts;      // the sort cuts a slab into this many runs of consecutive queries
+  int qpp;        // queries per part
+};
+
+#ifndef MSDA_TU
+#define MSDA_TU 0
+#endif
+
+#if MSDA_TU == 0  // the sort passes do not depend on the value dtype: compiled once
+// ---- pass 1: counting sort of every slab's samples by bilinear cell ---------------------------------------------------------
+// Sort key = clamped top-left token of the cell (< S). Border cells that clamp to the same token share a key; the walker
+// compares cell WORDS, so they only shorten runs.
+// A slab is cut into sp.parts PARTS of consecutive queries so that the grid covers every SM several times over (192 slabs on
+// 148 SMs would otherwise run as two waves). Three kernels:
+//   hist    CTA (slab, part): histogram of the part's samples in shared memory (integer ATOMS), stored to cnt[slab][part][S]
+//   scan    CTA (slab): exclusive scan of cnt in (key, part) order, in place; nin[slab] = samples in range
+//   scatter CTA (slab, part): its row of cnt becomes the cursors in shared memory; every sample takes its position with one
+//           ATOMS and writes its 20-byte record there
+constexpr int kSortThreads = 256;
+constexpr int kSortUnroll = 4;
+constexpr int kScanThreads = 1024;
+
+template <int LT, int PT, bool SCATTER>
+__global__ void __launch_bounds__(kSortThreads) msda_sort_part_kernel(const Params p, const SortedPlan sp) {
+  constexpr bool kStatic = (LT > 0);
+  const int L = kStatic ? LT : p.L;
+  const int P = kStatic ? PT : p.P;
+  const int LP = L * P;
+  extern __shared__ unsigned s_cnt[];
+  __shared__ int s_H[kMaxLevels], s_W[kMaxLevels], s_start[kMaxLevels];
+  const int tid = threadIdx.x;
+  const int slab = blockIdx.x / sp.parts, part = blockIdx.x - slab * sp.parts;
+  const int b = slab / p.M, m = slab - b * p.M;
+  const int S = p.S;
+  unsigned* __restrict__ gcnt = sp.cnt + ((size_t)slab * sp.parts + part) * S;
+  if constexpr (SCATTER) {
+    for (int i = tid; i < S; i += kSortThreads) s_cnt[i] = gcnt[i];
+  } else {
+    for (int i = tid; i < S; i += kSortThreads) s_cnt[i] = 0u;
+  }
+  if (tid < L) {
+    s_H[tid] = (int)p.shapes[2 * tid];
+    s_W[tid] = (int)p.shapes[2 * tid + 1];
+    s_start[tid] = (int)p.lsi[tid];
+  }
+  __syncthreads();
+  const size_t pair0 = ((size_t)b * p.Lq * p.M + (size_t)m) * LP;  // (b, query 0, m, point 0)
+  const unsigned qstride = (unsigned)p.M * (unsigned)LP;
+  const float2* __restrict__ loc = reinterpret_cast<const float2*>(p.loc) + pair0;
+  const float* __restrict__ aw = reinterpret_cast<const float*>(p.aw) + pair0;
+  const unsigned s_base = (unsigned)__cvta_generic_to_shared(s_cnt);
+  const unsigned i_begin = (unsigned)part * (unsigned)sp.qpp * (unsigned)LP;
+  const unsigned i_end = min((unsigned)sp.cap, i_begin + (unsigned)sp.qpp * (unsigned)LP);
+  uint4* __restrict__ rec = sp.rec + (size_t)slab * sp.cap;
+  unsigned* __restrict__ cwv = sp.cw + (size_t)slab * sp.cap;
+
+  for (unsigned i0 = i_begin + tid; i0 < i_end; i0 += kSortThreads * kSortUnroll) {
+    float2 xy[kSortUnroll];
+    float a[kSortUnroll];
+    unsigned o[kSortUnroll];
+#pragma unroll
+    for (int k = 0; k < kSortUnroll; ++k) {
+      const unsigned i = i0 + k * kSortThreads;
+      const unsigned q = i / (unsigned)LP;
+      o[k] = q * qstride + (i - q * (unsigned)LP);
+      xy[k] = i < i_end ? __ldg(loc + o[k]) : make_float2(0.f, 0.f);
+      if constexpr (SCATTER) a[k] = i < i_end ? __ldg(aw + o[k]) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < kSortUnroll; ++k) {
+      const unsigned i = i0 + k * kSortThreads;
+      if (i >= i_end) break;
+      const int l = (int)(i % (unsigned)LP) / P;
+      const int W = s_W[l];
+      const PointGeom<float> g = point_geom<float>(xy[k].x, xy[k].y, s_H[l], W);
+      if (g.mask != 0u) {
+        const unsigned ka = s_base + 4u * (unsigned)(s_start[l] + max(g.h_low, 0) * W + max(g.w_low, 0));
+        if constexpr (SCATTER) {
+          const unsigned pos = atoms_add(ka, 1u);
+          rec[pos] = make_uint4(__float_as_uint(g.lh), __float_as_uint(g.lw), __float_as_uint(a[k]), i);
+          cwv[pos] = (unsigned)(s_start[l] + (g.h_low + 1) * W + (g.w_low + 1)) | (g.mask << 20) | ((unsigned)l << 24);
+        } else {
+          reds_add(ka, 1u);
+        }
+      } else if constexpr (!SCATTER) {
+        // the reference skips the sample (ms_deform_im2col_cuda.cuh:365): its gradients are the zeros of the memset there
+        (reinterpret_cast<float*>(p.grad_aw) + pair0)[o[k]] = 0.f;
+        (reinterpret_cast<float2*>(p.grad_loc) + pair0)[o[k]] = make_float2(0.f, 0.f);
+      }
+    }
+  }
+  if constexpr (!SCATTER) {
+    __syncthreads();
+    for (int i = tid; i < S; i += kSortThreads) gcnt[i] = s_cnt[i];
+  }
+}
+
+// exclusive scan of cnt[slab][part][key] in (key, part) order. Every access is coalesced over the key: per-key totals over
+// the parts go to shared memory (S counters, dynamic), are scanned there in chunks of the CTA size, and a last sweep hands
+// every (part, key) its first position.
+__global__ void __launch_bounds__(kScanThreads) msda_sort_scan_kernel(const SortedPlan sp, int S) {
+  extern __shared__ unsigned s_tot[];
+  __shared__ unsigned s_warp[kScanThreads / 32];
+  __shared__ unsigned s_carry;
+  const int slab = blockIdx.x, parts = sp.parts;
+  unsigned* __restrict__ c = sp.cnt + (size_t)slab * parts * S;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < S; i += kScanThreads) {
+    unsigned sum = 0;
+    for (int r = 0; r < parts; ++r) sum += c[(size_t)r * S + i];
+    s_tot[i] = sum;
+  }
+  if (tid == 0) s_carry = 0u;
+  __syncthreads();
+  for (int base = 0; base < S; base += kScanThreads) {
+    const int i = base + tid;
+    const unsigned v = i < S ? s_tot[i] : 0u;
+    unsigned incl = v;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, incl, s);
+      if (lane >= s) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    const unsigned carry = s_carry;
+    if (warp == 0) {
+      const unsigned w = s_warp[lane];
+      unsigned wi = w;
+#pragma unroll
+      for (int s = 1; s < 32; s <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, wi, s);
+        if (lane >= s) wi += t;
+      }
+      s_warp[lane] = wi - w;  // exclusive prefix of the warp totals
+      if (lane == 31) s_carry = carry + wi;
+    }
+    __syncthreads();
+    if (i < S) s_tot[i] = carry + s_warp[warp] + incl - v;
+    __syncthreads();
+  }
+  if (tid == 0) sp.nin[slab] = s_carry;
+  for (int i = tid; i < S; i += kScanThreads) {
+    unsigned run = s_tot[i];
+    for (int r = 0; r < parts; ++r) {
+      const unsigned v = c[(size_t)r * S + i];
+      c[(size_t)r * S + i] = run;
+      run += v;
+    }
+  }
+}
+#endif  // MSDA_TU == 0
+
+// ---- pass 2: walk the sorted list ---------------------------------------------------------------------------------------------
+// T = value dtype, G = lanes per group (D = 4 * G), LT/PT = compile-time levels / points (0,0 = runtime).
+//
+// A warp owns sp.ppw consecutive sorted positions, split into 32 / G contiguous group ranges. A batch is G steps; in step t
+// every group works on position t of its batch. Lane (group, j) PREPARES position j of its group's batch (one point per
+// lane: record load, corner weights, row offsets, start-of-cell flag) into the warp's scratch, and FINISHES it after the
+// dot products of the batch are reduced. The grad_out rows of a batch are copied into shared memory with cp.async one batch
+// ahead (a first version read them from global memory at the point of use: 45 % of all stall samples sat on that load).
+// Scratch per warp (32 points; group rows padded so that the groups' broadcasts hit different banks):
+//   wq  2 x float4  corner weight * attention weight, each weight twice (the operand pairs of the packed FMAs); 0 for a
+//                   corner the reference does not read
+//   xq  uint4       byte offset of each corner's row inside the (b, m) value slab, + 2;  1 = the reference does not read it
+//   uq  float4      the reduced (u_1..u_4) of the point, written by the consumer for the finishing lane
+//   hq  uint        1 when the point STARTS a cell
+//   gbuf            the grad_out rows of the batch (kBufs batches deep), [point][D] as in global memory
+
+// Packed fp32 pairs (FFMA2 / FMUL2 on 64-bit register pairs; the sm_100 intrinsics __ffma2_rn / __fmul2_rn): per lane and
+// point the walker needs 16 FMAs for the four dot products and 16 for the four partial rows; as pairs these are 8 + 8
+// instructions plus 4 adds. A row of 4 channels is two pairs.
+struct Row4 {
+  float2 lo, hi;
+};
+template <typename T>
+__device__ __forceinline__ Row4 row_from_global(const char* p) {
+  Row4 r;
+  if constexpr (sizeof(T) == 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    r.lo = make_float2(t.x, t.y);
+    r.hi = make_float2(t.z, t.w);
+  } else {
+    const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+    unpack2<T>(t.x, r.lo.x, r.lo.y);
+    unpack2<T>(t.y, r.hi.x, r.hi.y);
+  }
+  return r;
+}
+template <typename T>
+__device__ __forceinline__ Row4 row_from_shared(unsigned a) {
+  Row4 r;
+  if constexpr (sizeof(T) == 4) {
+    const uint4 t = lds128(a);
+    r.lo = make_float2(__uint_as_float(t.x), __uint_as_float(t.y));
+    r.hi = make_float2(__uint_as_float(t.z), __uint_as_float(t.w));
+  } else {
+    const uint2 t = lds64(a);
+    unpack2<T>(t.x, r.lo.x, r.lo.y);
+    unpack2<T>(t.y, r.hi.x, r.hi.y);
+  }
+  return r;
+}
+
+template <typename T, int G>
+struct WalkScratch {
+  static constexpr int kGroups = 32 / G;
+  static constexpr int kStride = G + 1;                           // records per group row (one pad)
+  static constexpr unsigned kRowB = 4u * G * sizeof(T);           // one grad_out row
+#ifndef WALK_BUFS
+#define WALK_BUFS 1
+#endif
+#ifndef WALK_MINB
+#define WALK_MINB 3
+#endif
+  static constexpr int kBufs = kRowB <= 128 ? WALK_BUFS : 1;      // batches of grad_out rows in flight
+  static constexpr unsigned kW = 0;                                // 2 x float4 [kGroups][kStride]
+  static constexpr unsigned kX = kW + kGroups * kStride * 32u;    // uint4
+  static constexpr unsigned kU = kX + kGroups * kStride * 16u;    // float4
+  static constexpr unsigned kH = kU + kGroups * kStride * 16u;    // uint
+  static constexpr unsigned kG = (kH + kGroups * kStride * 4u + 15u) & ~15u;  // grad_out rows: [kBufs][32][kRowB]
+  static constexpr unsigned kBytes = kG + kBufs * 32u * kRowB;
+};
+
+template <typename T, int G, int LT, int PT, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) msda_bwd_sorted_kernel(const Params p, const SortedPlan sp) {
+  constexpr bool kStatic = (LT > 0);
+  constexpr int D = 4 * G;
+  constexpr int NG = 32 / G;                         // groups per warp
+  constexpr unsigned kRowB = D * sizeof(T);          // bytes of one head row of value / grad_out
+  constexpr int kAccShift = sizeof(T) == 2 ? 1 : 0;  // fp32 accumulator rows are 4 / sizeof(T) times as long
+  using SC = WalkScratch<T, G>;
+  constexpr int kBufs = SC::kBufs;
+
+  const int L = kStatic ? LT : p.L;
+  const int P = kStatic ? PT : p.P;
+  const int LP = L * P;
+  const unsigned MDb = (unsigned)p.M * kRowB;  // bytes between neighbouring tokens of value / neighbouring queries of grad_out
+
+  __shared__ int s_lvH[kMaxLevels], s_lvW[kMaxLevels];
+  extern __shared__ __align__(16) char s_scr[];  // kWarps * SC::kBytes
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int slab = blockIdx.x / sp.ctas_per_slab, chunk = blockIdx.x - slab * sp.ctas_per_slab;
+  const int b = slab / p.M, m = slab - b * p.M;
+  if (tid < L) {
+    s_lvH[tid] = (int)p.shapes[2 * tid];
+    s_lvW[tid] = (int)p.shapes[2 * tid + 1];
+  }
+  __syncthreads();  // the only block-wide barrier
+  const int n_in = (int)sp.nin[slab];
+  const int r0 = (chunk * kWarps + warp) * sp.ppw;
+  if (r0 >= n_in) return;
+  const int rend = min(n_in, r0 + sp.ppw);
+  const int gi = lane / G, j = lane % G;
+  const int glen = (rend - r0 + NG - 1) / NG;          // positions per group (the last group may get fewer, even none)
+  const int g0 = r0 + gi * glen, gend = min(rend, g0 + glen);
+  const int nb = (glen + G - 1) / G;                    // batches: the same count for every group of the warp
+
+  const uint4* __restrict__ rec = sp.rec + (size_t)slab * sp.cap;
+  const unsigned* __restrict__ cwv = sp.cw + (size_t)slab * sp.cap;
+
+  const unsigned scr = (unsigned)__cvta_generic_to_shared(s_scr) + warp * SC::kBytes;
+  const unsigned my = (unsigned)(gi * SC::kStride + j);     // this lane's prepared point
+  const unsigned grp = (unsigned)(gi * SC::kStride);        // step 0 of this lane's group
+  const size_t slab_v = ((size_t)b * p.S * p.M + (size_t)m) * D;
+  const size_t pair0 = ((size_t)b * p.Lq * p.M + (size_t)m);  // (b, query 0, m)
+  const unsigned qstride = (unsigned)p.M * (unsigned)LP;      // points between consecutive queries of this head
+  // value / accumulator bases are biased by the "+ 2" of the offset words
+  const char* __restrict__ vb2 = reinterpret_cast<const char*>(p.value) + slab_v * sizeof(T) + j * (4 * sizeof(T)) - 2;
+  char* __restrict__ gvb2 = reinterpret_cast<char*>(p.grad_value) + slab_v * 4u + j * 16 - (2 << kAccShift);  // fp32 accumulator
+  const char* __restrict__ gob_row = reinterpret_cast<const char*>(p.grad_out) + pair0 * kRowB;
+  const char* __restrict__ vb_row = reinterpret_cast<const char*>(p.value) + slab_v * sizeof(T) - 2;
+  float* __restrict__ gaw = reinterpret_cast<float*>(p.grad_aw) + pair0 * LP;
+  float2* __restrict__ gloc = reinterpret_cast<float2*>(p.grad_loc) + pair0 * LP;
+
+  unsigned cur[4] = {1u, 1u, 1u, 1u};  // offset words of the current cell's rows (1 = not read)
+  Row4 v[4], acc[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    v[k].lo = v[k].hi = make_float2(0.f, 0.f);
+    acc[k].lo = acc[k].hi = make_float2(0.f, 0.f);
+  }
+  unsigned lastcw = 0xFFFFFFFEu;  // cell word of the group's previous position
+
+  // The grad_out rows of a batch go to shared memory: the lanes of a group copy row after row, 16 bytes per lane
+  // (consecutive lanes -> consecutive addresses on both sides); `pidx` is the point index of THIS lane's point, whose row
+  // offset the other lanes receive by shuffle.
+  auto stage_rows = [&](unsigned pidx, int buf) {
+    constexpr int kLanesPerRow = kRowB / 16;          // 8 (fp32, D = 32), 4 (16-bit, D = 32), 16 / 8 (D = 64)
+    constexpr int kRowsPerIter = G / kLanesPerRow;    // 1 (fp32) or 2 (16-bit)
+    const unsigned my_off = (pidx / (unsigned)LP) * MDb;
+    const unsigned dst0 = scr + SC::kG + (unsigned)(buf * 32 + gi * G) * kRowB + (unsigned)(j % kLanesPerRow) * 16u;
+    const char* src0 = gob_row + (j % kLanesPerRow) * 16;
+#pragma unroll
+    for (int t = 0; t < G; t += kRowsPerIter) {
+      const int row = t + j / kLanesPerRow;
+      const unsigned off = __shfl_sync(0xffffffffu, my_off, row, G);
+      cp_async16(dst0 + (unsigned)row * kRowB, ptr_add(src0, off));
+    }
+  };
+
+  // the records of the next batch are requested while the current batch is worked on
+  uint4 recC = make_uint4(0u, 0u, 0u, 0u), recN = make_uint4(0u, 0u, 0u, 0u);
+  unsigned cwC = kNoCell, cwN = kNoCell;
+  if (g0 + j < gend) { recC = __ldg(rec + g0 + j); cwC = __ldg(cwv + g0 + j); }
+  if (g0 + G + j < gend) { recN = __ldg(rec + g0 + G + j); cwN = __ldg(cwv + g0 + G + j); }
+  if constexpr (kBufs == 2) {
+    stage_rows(recC.w, 0);  // (a lane without a point names the row of query 0: finite data, weight 0)
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+
+  for (int bi = 0; bi < nb; ++bi) {
+    const int pos = g0 + bi * G + j;
+    const bool valid = pos < gend;
+    uint4 recNN = make_uint4(0u, 0u, 0u, 0u);
+    unsigned cwNN = kNoCell;
+    if (pos + 2 * G < gend) { recNN = __ldg(rec + pos + 2 * G); cwNN = __ldg(cwv + pos + 2 * G); }
+    if constexpr (kBufs == 2) {
+      stage_rows(recN.w, (bi + 1) & 1);  // rows of the NEXT batch (when there is none: a harmless copy nobody reads)
+    } else {
+      __syncwarp();                     // the previous batch's readers are done with the only buffer
+      stage_rows(recC.w, 0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    // ---- prepare: one point per lane ----------------------------------------------------------------------------------------------
+    {
+      unsigned prev = __shfl_up_sync(0xffffffffu, cwC, 1, G);
+      if (j == 0) prev = lastcw;
+      lastcw = __shfl_sync(0xffffffffu, cwC, G - 1, G);
+      const bool head = valid && cwC != prev;
+      unsigned xw[4] = {1u, 1u, 1u, 1u};
+      float cf[4] = {0.f, 0.f, 0.f, 0.f};
+      if (valid) {
+        const unsigned W = (unsigned)s_lvW[(cwC >> 24) & 15u];
+        const unsigned br = cwC & 0xFFFFFu;
+        xw[0] = (cwC & (1u << 20)) ? (br - W - 1u) * MDb + 2u : 1u;
+        xw[1] = (cwC & (2u << 20)) ? (br - W) * MDb + 2u : 1u;
+        xw[2] = (cwC & (4u << 20)) ? (br - 1u) * MDb + 2u : 1u;
+        xw[3] = (cwC & (8u << 20)) ? br * MDb + 2u : 1u;
+        const float lh = __uint_as_float(recC.x), lw = __uint_as_float(recC.y), a = __uint_as_float(recC.z);
+        const float hh = 1.f - lh, hw = 1.f - lw;
+        cf[0] = xw[0] > 1u ? (hh * hw) * a : 0.f;
+        cf[1] = xw[1] > 1u ? (hh * lw) * a : 0.f;
+        cf[2] = xw[2] > 1u ? (lh * hw) * a : 0.f;
+        cf[3] = xw[3] > 1u ? (lh * lw) * a : 0.f;
+        if (head) {  // the four value rows this cell needs within the next G steps: request the lines now
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (xw[k] > 1u) prefetch_l2(vb_row + xw[k]);
+        }
+      }
+      if constexpr (kBufs == 2) __syncwarp();  // the previous batch's readers are done with the scratch
+      sts128(scr + SC::kW + my * 32u, __float_as_uint(cf[0]), __float_as_uint(cf[0]), __float_as_uint(cf[1]), __float_as_uint(cf[1]));
+      sts128(scr + SC::kW + my * 32u + 16u, __float_as_uint(cf[2]), __float_as_uint(cf[2]), __float_as_uint(cf[3]), __float_as_uint(cf[3]));
+      sts128(scr + SC::kX + my * 16u, xw[0], xw[1], xw[2], xw[3]);
+      sts32(scr + SC::kH + my * 4u, head ? 1u : 0u);
+      if constexpr (kBufs == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");  // this batch's rows have landed
+      else asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+    }
+    // ---- consume: G steps; in step t every group works on point t of its batch ---------------------------------------------------
+    const unsigned gbuf = scr + SC::kG + (unsigned)((kBufs == 2 ? (bi & 1) : 0) * 32 + gi * G) * kRowB + j * (4u * (unsigned)sizeof(T));
+#pragma unroll 2
+    for (int t = 0; t < G; ++t) {
+      const unsigned st = grp + (unsigned)t;
+      const unsigned hd = lds32(scr + SC::kH + st * 4u);
+      const Row4 g = row_from_shared<T>(gbuf + (unsigned)t * kRowB);
+      if (hd) {  // group-uniform: a new cell starts here - flush the partial rows, fetch the new cell's rows
+        const uint4 X = lds128(scr + SC::kX + st * 16u);
+        const unsigned nx[4] = {X.x, X.y, X.z, X.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (cur[k] > 1u)
+            red_add_v4(reinterpret_cast<float*>(gvb2 + ((size_t)cur[k] << kAccShift)), acc[k].lo.x, acc[k].lo.y, acc[k].hi.x, acc[k].hi.y);
+          acc[k].lo = acc[k].hi = make_float2(0.f, 0.f);
+          cur[k] = nx[k];
+          if (cur[k] > 1u) v[k] = row_from_global<T>(vb2 + cur[k]);
+        }
+      }
+      const uint4 W01 = lds128(scr + SC::kW + st * 32u), W23 = lds128(scr + SC::kW + st * 32u + 16u);
+      const float2 cfp[4] = {make_float2(__uint_as_float(W01.x), __uint_as_float(W01.y)), make_float2(__uint_as_float(W01.z), __uint_as_float(W01.w)),
+                             make_float2(__uint_as_float(W23.x), __uint_as_float(W23.y)), make_float2(__uint_as_float(W23.z), __uint_as_float(W23.w))};
+      float d[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 dd = __ffma2_rn(g.hi, v[k].hi, __fmul2_rn(g.lo, v[k].lo));
+        d[k] = dd.x + dd.y;
+        acc[k].lo = __ffma2_rn(cfp[k], g.lo, acc[k].lo);
+        acc[k].hi = __ffma2_rn(cfp[k], g.hi, acc[k].hi);
+      }
+      // (u_1..u_4) over the G lanes of the group: two transposing steps (4 -> 2 -> 1 value per lane), then plain butterflies.
+      // Lane j ends up with the total of u_(2 * bit(G/2) + bit(G/4) + 1); the lanes with no lower bit set hand it over.
+      {
+        const bool up1 = (j & (G / 2)) != 0;
+        const float s0 = up1 ? d[0] : d[2], k0 = up1 ? d[2] : d[0];
+        const float s1 = up1 ? d[1] : d[3], k1 = up1 ? d[3] : d[1];
+        d[0] = k0 + __shfl_xor_sync(0xffffffffu, s0, G / 2, G);
+        d[1] = k1 + __shfl_xor_sync(0xffffffffu, s1, G / 2, G);
+        const bool up2 = (j & (G / 4)) != 0;
+        const float s2 = up2 ? d[0] : d[1], k2 = up2 ? d[1] : d[0];
+        float r = k2 + __shfl_xor_sync(0xffffffffu, s2, G / 4, G);
+#pragma unroll
+        for (int s = G / 8; s > 0; s >>= 1) r += __shfl_xor_sync(0xffffffffu, r, s, G);
+        if ((j & (G / 4 - 1)) == 0) sts32(scr + SC::kU + st * 16u + 4u * (unsigned)(j / (G / 4)), __float_as_uint(r));
+      }
+    }
+    __syncwarp();
+    // ---- finish: the lane that holds the record turns (u_1..u_4) into the gradients of its point -------------------------------------
+    if (valid) {
+      const unsigned cw = cwC;
+      const unsigned l = (cw >> 24) & 15u;
+      const float lh = __uint_as_float(recC.x), lw = __uint_as_float(recC.y), a = __uint_as_float(recC.z);
+      const float fW = (float)s_lvW[l], fH = (float)s_lvH[l];
+      const unsigned ql = recC.w / (unsigned)LP;
+      const unsigned o32 = ql * qstride + (recC.w - ql * (unsigned)LP);
+      const uint4 uu = lds128(scr + SC::kU + my * 16u);
+      // corners the reference does not read count as zero rows (their registers held whatever row was loaded last)
+      const float u1 = (cw & (1u << 20)) ? __uint_as_float(uu.x) : 0.f, u2 = (cw & (2u << 20)) ? __uint_as_float(uu.y) : 0.f;
+      const float u3 = (cw & (4u << 20)) ? __uint_as_float(uu.z) : 0.f, u4 = (cw & (8u << 20)) ? __uint_as_float(uu.w) : 0.f;
+      const float hh = 1.f - lh, hw = 1.f - lw;
+      const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
+      const float s_a = w1 * u1 + w2 * u2 + w3 * u3 + w4 * u4;
+      const float s_w = hh * (u2 - u1) + lh * (u4 - u3);
+      const float s_h = hw * (u3 - u1) + lw * (u4 - u2);
+      gaw[o32] = s_a;
+      gloc[o32] = make_float2(fW * s_w * a, fH * s_h * a);
+    }
+    recC = recN; cwC = cwN;
+    recN = recNN; cwN = cwNN;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");  // (the last iteration's look-ahead copy)
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (cur[k] > 1u)
+      red_add_v4(reinterpret_cast<float*>(gvb2 + ((size_t)cur[k] << kAccShift)), acc[k].lo.x, acc[k].lo.y, acc[k].hi.x, acc[k].hi.y);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Launchers
+// ---------------------------------------------------------------------------------------------
+template <typename T, int G, int LT, int PT>
+static cudaError_t launch_sorted_k(const Params& p, const SortedPlan& sp, dim3 grid, cudaStream_t s) {
+  auto kern = msda_bwd_sorted_kernel<T, G, LT, PT, WALK_MINB>;
+  constexpr unsigned smem = kWarps * WalkScratch<T, G>::kBytes;
+  if (smem > 40u * 1024u) {
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  kern<<<grid, kThreads, smem, s>>>(p, sp);
+  return cudaGetLastError();
+}
+
+template <typename T, int G>
+static cudaError_t launch_sorted_c(const Params& p, const SortedPlan& sp, dim3 grid, cudaStream_t s) {
+  if (p.L == 3 && p.P == 4) return launch_sorted_k<T, G, 3, 4>(p, sp, grid, s);
+  if (p.L == 1 && p.P == 4) return launch_sorted_k<T, G, 1, 4>(p, sp, grid, s);
+  return launch_sorted_k<T, G, 0, 0>(p, sp, grid, s);
+}
+
+template <typename T>
+static cudaError_t launch_sorted_t(const Params& p, const SortedPlan& sp, cudaStream_t s) {
+  const dim3 grid((unsigned)((size_t)p.N * p.M * sp.ctas_per_slab));
+  if (p.D == 32) return launch_sorted_c<T, 8>(p, sp, grid, s);
+  if (p.D == 64) return launch_sorted_c<T, 16>(p, sp, grid, s);
+  return cudaErrorNotSupported;
+}
+
+cudaError_t bwd_sorted_bf16(const Params& p, const SortedPlan& sp, cudaStream_t s);
+cudaError_t bwd_sorted_f16(const Params& p, const SortedPlan& sp, cudaStream_t s);
+
+#if MSDA_TU == 1
+cudaError_t bwd_sorted_bf16(const Params& p, const SortedPlan& sp, cudaStream_t s) { return launch_sorted_t<__nv_bfloat16>(p, sp, s); }
+#elif MSDA_TU == 2
+cudaError_t bwd_sorted_f16(const Params& p, const SortedPlan& sp, cudaStream_t s) { return launch_sorted_t<__half>(p, sp, s); }
+#else
+static size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+// Parts per slab of the sort: enough CTAs for ~4 per SM, at most 64, at least 64 queries each.
+static int sort_parts(size_t slabs, int Lq, int sm_count) {
+  long long parts = (4ll * sm_count + (long long)slabs - 1) / (long long)slabs;
+  if (parts > 64) parts = 64;
+  while (parts > 1 && Lq / parts < 64) --parts;
+  return (int)(parts < 1 ? 1 : parts);
+}
+
+// Bytes of workspace the sorted backward needs for these dimensions (0 = the shape is outside its domain).
+size_t backward_sorted_workspace_bytes(int N, int S, int M, int D, int L, int Lq, int P, int sm_count) {
+  if (!(D == 32 || D == 64)) return 0;
+  if (S >= (1 << 19)) return 0;                        // cell words keep the corner token in 20 bits
+  if ((size_t)S * 4 > kSmemBudget - 1024u) return 0;   // the sort's histograms live in shared memory
+  const long long cap = (long long)Lq * L * P;
+  if (cap * M >= (1ll << 31) || (long long)Lq * M * D * 4 >= (1ll << 31)) return 0;  // 32-bit in-image point / row offsets
+  const size_t slabs = (size_t)N * M;
+  const int parts = sort_parts(slabs, Lq, sm_count);
+  return align16(slabs * parts * S * 4) + align16(slabs * 4) + slabs * (size_t)cap * 16 + align16(slabs * (size_t)cap * 4);
+}
+
+template <int LT, int PT>
+static cudaError_t launch_sort(const Params& p, const SortedPlan& sp, cudaStream_t s) {
+  const unsigned smem = (unsigned)p.S * 4u;
+  if (smem > 40u * 1024u) {
+    cudaError_t e = cudaFuncSetAttribute(msda_sort_part_kernel<LT, PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(msda_sort_part_kernel<LT, PT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  const unsigned grid = (unsigned)((size_t)p.N * p.M * sp.parts);
+  msda_sort_part_kernel<LT, PT, false><<<grid, kSortThreads, smem, s>>>(p, sp);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (smem > 40u * 1024u) {
+    e = cudaFuncSetAttribute(msda_sort_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  msda_sort_scan_kernel<<<(unsigned)((size_t)p.N * p.M), kScanThreads, smem, s>>>(sp, p.S);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  msda_sort_part_kernel<LT, PT, true><<<grid, kSortThreads, smem, s>>>(p, sp);
+  return cudaGetLastError();
+}
+
+// Counting sort + walk. `p.grad_value` must point at the zero-filled fp32 ACCUMULATOR (grad_value itself for f32, the scratch
+// for bf16 / f16); `ws` at backward_sorted_workspace_bytes() bytes, 16-byte aligned. `launches` counts kernel launches.
+cudaError_t launch_backward_sorted(const Params& p, int dtype, void* ws, int sm_count, int* launches, cudaStream_t s) {
+  const size_t slabs = (size_t)p.N * p.M;
+  const long long cap = (long long)p.Lq * p.L * p.P;
+  SortedPlan sp;
+  sp.parts = sort_parts(slabs, p.Lq, sm_count);
+  sp.qpp = (p.Lq + sp.parts - 1) / sp.parts;
+  char* w = reinterpret_cast<char*>(ws);
+  sp.cnt = reinterpret_cast<unsigned*>(w);
+  w += align16(slabs * sp.parts * p.S * 4);
+  sp.nin = reinterpret_cast<unsigned*>(w);
+  w += align16(slabs * 4);
+  sp.rec = reinterpret_cast<uint4*>(w);
+  w += slabs * (size_t)cap * 16;
+  sp.cw = reinterpret_cast<unsigned*>(w);
+  sp.cap = (int)cap;
+  // positions per warp: as long as possible (every group flushes its last run when its range ends) while the grid still
+  // covers every SM several times over
+  sp.ppw = 32;
+  for (int ppw = 256; ppw >= 32; ppw >>= 1) {
+    const long long ctas = (long long)slabs * ((cap + (long long)kWarps * ppw - 1) / ((long long)kWarps * ppw));
+    if (ctas >= 6ll * sm_count || ppw == 32) { sp.ppw = ppw; break; }
+  }
+  sp.ctas_per_slab = (int)((cap + (long long)kWarps * sp.ppw - 1) / ((long long)kWarps * sp.ppw));
+
+  cudaError_t e;
+  if (p.L == 3 && p.P == 4) e = launch_sort<3, 4>(p, sp, s);
+  else if (p.L == 1 && p.P == 4) e = launch_sort<1, 4>(p, sp, s);
+  else e = launch_sort<0, 0>(p, sp, s);
+  if (e != cudaSuccess) return e;
+  if (dtype == MSDA_F32) e = launch_sorted_t<float>(p, sp, s);
+  else if (dtype == MSDA_BF16) e = bwd_sorted_bf16(p, sp, s);
+  else if (dtype == MSDA_F16) e = bwd_sorted_f16(p, sp, s);
+  else e = cudaErrorNotSupported;
+  if (e == cudaSuccess && launches) *launches = 4;
+  return e;
+}
+#endif  // MSDA_TU
+
+}  // namespace msda
