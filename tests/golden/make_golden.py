@@ -202,6 +202,52 @@ def adapter_cls_case(ref_seg_adapter, name, dim, heads, ratio, H, W, N, seed):
     print(name)
 
 
+def load_reference_wsdm_adapter():
+    """wsdm2023/mmdet_custom/models/backbones/adapter_modules.py: the copy whose InteractionBlock threads text tokens."""
+    sys.path.insert(0, os.path.join(REF, 'wsdm2023'))
+    spec = importlib.util.spec_from_file_location(
+        'ref_wsdm_adapter_modules', os.path.join(REF, 'wsdm2023/mmdet_custom/models/backbones/adapter_modules.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def text_block_stand_in(x, q, q_mask, H, W):
+    """Parameter-free stand-in for the wsdm2023 ViT blocks, which take and return (image tokens, text tokens): the two
+    streams exchange their masked means so that the order of the calls and the returned q both matter."""
+    m = q_mask.to(q.dtype).unsqueeze(-1)
+    qm = (q * m).sum(1, keepdim=True) / m.sum(1, keepdim=True).clamp_min(1)
+    return x * 1.125 + 0.25 * qm + 0.01 * (H - W), q * 0.75 + 0.5 * x.mean(1, keepdim=True)
+
+
+def adapter_text_case(ref_wsdm_adapter, name, dim, heads, ratio, H, W, N, T, seed):
+    """InteractionBlock.forward of the wsdm2023 copy (:183-198): injector -> blocks(x, q, q_mask) -> extractors."""
+    torch.manual_seed(seed)
+    blk = ref_wsdm_adapter.InteractionBlock(dim=dim, num_heads=heads, n_points=4, init_values=0., deform_ratio=ratio,
+                                            extra_extractor=True, with_cffn=True, cffn_ratio=0.25).double()
+    with torch.no_grad():
+        for p in blk.parameters():
+            p.add_(torch.randn_like(p) * 0.05)
+    img = torch.zeros(N, 3, H, W)
+    di1, di2 = ref_wsdm_adapter.deform_inputs(img)
+    h, w = H // 16, W // 16
+    x = torch.randn(N, h * w, dim, dtype=torch.double)
+    c = torch.randn(N, (2 * h) * (2 * w) + h * w + (h // 2) * (w // 2), dim, dtype=torch.double)
+    q = torch.randn(N, T, dim, dtype=torch.double)
+    q_mask = torch.ones(N, T, dtype=torch.bool)
+    q_mask[0, T // 2:] = False
+    di1d = [di1[0].double(), di1[1], di1[2]]
+    di2d = [di2[0].double(), di2[1], di2[2]]
+    xo, co, qo = blk(x, c, q, q_mask, [text_block_stand_in, text_block_stand_in], di1d, di2d, h, w)
+    arrays = {('sd.' + k): v.numpy() for k, v in blk.state_dict().items()}
+    arrays.update(x=x.numpy(), c=c.numpy(), q=q.numpy(), q_mask=q_mask.numpy(), x_out=xo.detach().numpy(),
+                  c_out=co.detach().numpy(), q_out=qo.detach().numpy(), ref1=di1[0].numpy(), shapes1=di1[1].numpy(),
+                  lsi1=di1[2].numpy(), ref2=di2[0].numpy(), shapes2=di2[1].numpy(), lsi2=di2[2].numpy(),
+                  cfg=np.array([dim, heads, H, W, N], dtype=np.int64), ratio=np.array(ratio))
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), **arrays)
+    print(name)
+
+
 def init_case(ref_mod, name):
     """The reference's deterministic init of sampling_offsets.bias for the adapter head counts."""
     arrays = {}
@@ -283,6 +329,9 @@ def main():
                          shapes=[(4, 4)], seed=62, ref_levels=1)
         adapter_cls_case(load_reference_seg_adapter(), 'adapter_block_cls', dim=32, heads=4, ratio=0.5, H=64, W=96, N=2, seed=63)
         return
+    if 'text' in sys.argv[1:]:        # only the wsdm2023 text-token interaction block (added late in round 2)
+        adapter_text_case(load_reference_wsdm_adapter(), 'adapter_block_text', dim=32, heads=4, ratio=0.5, H=64, W=96, N=2, T=5, seed=64)
+        return
     if 'layernorm' in sys.argv[1:]:   # only the N2 fixtures (the others are unchanged)
         layernorm_case(ref_adapter, 'layernorm_c96', C=96, shape=(2, 21), seed=51)
         layernorm_case(ref_adapter, 'layernorm_c768', C=768, shape=(1, 5), seed=52, heads=12)
@@ -318,6 +367,8 @@ def main():
     module_grad_case(ref_mod, 'module_l1_grads', d_model=128, n_levels=1, n_heads=4, n_points=4, ratio=1.0, N=2, Lq=84,
                      shapes=[(4, 4)], seed=62, ref_levels=1)
     adapter_cls_case(load_reference_seg_adapter(), 'adapter_block_cls', dim=32, heads=4, ratio=0.5, H=64, W=96, N=2, seed=63)
+    # 10. the wsdm2023 interaction block (text tokens threaded through the ViT blocks)
+    adapter_text_case(load_reference_wsdm_adapter(), 'adapter_block_text', dim=32, heads=4, ratio=0.5, H=64, W=96, N=2, T=5, seed=64)
 
 
 if __name__ == '__main__':

@@ -4,7 +4,7 @@ import torch
 
 from conftest import load_golden
 
-from vit_adapter_b200.adapter import (InteractionBlock, InteractionBlockWithCls, SpatialPriorModule, deform_inputs,
+from vit_adapter_b200.adapter import (InteractionBlock, InteractionBlockWithCls, InteractionBlockWithText, SpatialPriorModule, deform_inputs,
                                       get_reference_points)
 
 
@@ -43,6 +43,10 @@ def test_interaction_block_state_dict_matches_reference():
     blk2 = InteractionBlockWithCls(dim=dim, num_heads=heads, deform_ratio=float(g['ratio']), extra_extractor=True)
     assert sorted(blk2.state_dict().keys()) == sorted(ref.keys())
     assert float(blk2.injector.gamma.abs().max()) == 0.0  # init_values = 0 => injector is the identity at init
+    # the wsdm2023 copy (text tokens through the blocks) has the same parameters: its golden's keys load strictly
+    gt = load_golden('adapter_block_text')
+    blk3 = InteractionBlockWithText(dim=dim, num_heads=heads, deform_ratio=float(gt['ratio']), extra_extractor=True).double()
+    blk3.load_state_dict({k[3:]: v for k, v in gt.items() if k.startswith('sd.')}, strict=True)
 
 
 def test_spatial_prior_module_shapes_and_keys():

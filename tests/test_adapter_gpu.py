@@ -6,7 +6,7 @@ import torch
 from conftest import load_golden
 
 from vit_adapter_b200 import MSDeformAttn
-from vit_adapter_b200.adapter import InteractionBlock, InteractionBlockWithCls, deform_inputs
+from vit_adapter_b200.adapter import InteractionBlock, InteractionBlockWithCls, InteractionBlockWithText, deform_inputs
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
@@ -120,3 +120,28 @@ def test_interaction_block_with_cls_matches_reference_f64():
                       [_vit_block_stand_in, _vit_block_stand_in], d1f, d2f, H // 16, W // 16)
     torch.testing.assert_close(x.cpu().double(), g['x_out'], rtol=1e-4, atol=1e-4 * float(g['x_out'].abs().max()))
     torch.testing.assert_close(c.cpu().double(), g['c_out'], rtol=1e-4, atol=1e-4 * float(g['c_out'].abs().max()))
+
+
+def _text_block_stand_in(x, q, q_mask, H, W):
+    """Same parameter-free stand-in for the wsdm2023 ViT blocks as tests/golden/make_golden.py::text_block_stand_in."""
+    m = q_mask.to(q.dtype).unsqueeze(-1)
+    qm = (q * m).sum(1, keepdim=True) / m.sum(1, keepdim=True).clamp_min(1)
+    return x * 1.125 + 0.25 * qm + 0.01 * (H - W), q * 0.75 + 0.5 * x.mean(1, keepdim=True)
+
+
+def test_interaction_block_with_text_matches_reference_f64():
+    """Forward parity of the wsdm2023 interaction block (text tokens q and their mask go through the ViT blocks with the image
+    tokens; wsdm2023/mmdet_custom/models/backbones/adapter_modules.py:161-198) against a golden of the reference class."""
+    g = load_golden('adapter_block_text')
+    dim, heads, H, W, N = [int(v) for v in g['cfg']]
+    blk = InteractionBlockWithText(dim=dim, num_heads=heads, n_points=4, init_values=0., deform_ratio=float(g['ratio']),
+                                   extra_extractor=True, with_cffn=True, cffn_ratio=0.25).double()
+    blk.load_state_dict({k[3:]: v for k, v in g.items() if k.startswith('sd.')}, strict=True)
+    blk = blk.to(DEV)
+    d1 = [g['ref1'].double().to(DEV), g['shapes1'].to(DEV), g['lsi1'].to(DEV)]
+    d2 = [g['ref2'].double().to(DEV), g['shapes2'].to(DEV), g['lsi2'].to(DEV)]
+    x, c, q = blk(g['x'].to(DEV), g['c'].to(DEV), g['q'].to(DEV), g['q_mask'].to(DEV), [_text_block_stand_in, _text_block_stand_in],
+                  d1, d2, H // 16, W // 16)
+    torch.testing.assert_close(x.cpu(), g['x_out'], rtol=1e-8, atol=1e-9)
+    torch.testing.assert_close(c.cpu(), g['c_out'], rtol=1e-8, atol=1e-9)
+    torch.testing.assert_close(q.cpu(), g['q_out'], rtol=1e-8, atol=1e-9)

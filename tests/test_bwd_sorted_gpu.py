@@ -121,9 +121,9 @@ def test_sorted_backward_vs_reference_cuda(cfg):
 
 
 def test_sorted_backward_selection():
-    """Without tuning the sorted backward (4 kernels: histogram, scan, scatter, walk) runs where it measured faster - 64
-    channels per head and >= 16 samples per value token and head - and the one-kernel query-order backward elsewhere;
-    bwd_sorted=2 / 1 force one or the other. They agree to summation order."""
+    """Without tuning the sorted backward (4 kernels: histogram, scan, scatter, walk) runs where it measured faster - >= 16
+    samples per value token and head, and 64 channels per head or >= 2 M samples - and the one-kernel query-order backward
+    elsewhere; bwd_sorted=2 / 1 force one or the other. They agree to summation order."""
     dense64 = make_inputs(2, 6, 64, 1344, [(16, 16)], 4, seed=16, dist='adapter')      # 21 samples per token: sorted
     n0 = _cabi.launch_count()
     gv, gl, ga = _bwd(dense64, torch.float32)

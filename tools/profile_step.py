@@ -25,6 +25,7 @@ def main():
     ap.add_argument('--smem', type=int, default=0, help='fwd_smem tuning mode (0 auto, 1 off, 2 forced)')
     ap.add_argument('--smem-threads', type=int, default=0)
     ap.add_argument('--fwd-only', action='store_true')
+    ap.add_argument('--bwd-sorted', type=int, default=0, help='bwd_sorted tuning mode (0 auto, 1 off, 2 forced)')
     args = ap.parse_args()
     dev = torch.device('cuda', 0)
     batch = args.batch or VARIANTS[args.variant][3]
@@ -35,7 +36,7 @@ def main():
         calls.append({k: v.to(dev) for k, v in h.items()})
     if args.ref:
         from oracle import refcuda
-    _cabi.set_tuning(fwd_smem=args.smem, fwd_smem_threads=args.smem_threads)
+    _cabi.set_tuning(fwd_smem=args.smem, fwd_smem_threads=args.smem_threads, bwd_sorted=args.bwd_sorted)
     for _ in range(args.warm + args.steps):
         for d in calls:
             if args.ref:

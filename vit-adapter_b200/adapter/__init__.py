@@ -1,3 +1,3 @@
 from .adapter_modules import (ConvFFN, DropPath, DWConv, Extractor, Injector, InteractionBlock,  # noqa: F401
-                              InteractionBlockWithCls, SpatialPriorModule, deform_inputs, get_reference_points)
+                              InteractionBlockWithCls, InteractionBlockWithText, SpatialPriorModule, deform_inputs, get_reference_points)
 from .sync_batchnorm import SyncBatchNormNoHostSync  # noqa: F401

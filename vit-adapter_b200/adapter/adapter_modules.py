@@ -353,6 +353,18 @@ class InteractionBlockWithCls(_InteractionBase):
         return x, self._extract(x, c, deform_inputs2, H, W), cls
 
 
+class InteractionBlockWithText(_InteractionBase):
+    """The wsdm2023 grounding variant: the ViT blocks also carry text tokens `q` (with their mask) next to the image tokens
+    (wsdm2023/mmdet_custom/models/backbones/adapter_modules.py:161-198, where the class is again called InteractionBlock).
+    Same sub-modules and state-dict keys; returns (x, c, q)."""
+
+    def forward(self, x, c, q, q_mask, blocks, deform_inputs1, deform_inputs2, H, W):
+        x, c = self._inject(x, c, deform_inputs1)
+        for blk in blocks:
+            x, q = blk(x, q, q_mask, H, W)
+        return x, self._extract(x, c, deform_inputs2, H, W), q
+
+
 class SpatialPriorModule(nn.Module):
     """Convolutional stem producing the 1/4 map and the 1/8, 1/16, 1/32 token sequences the Injector
     reads (reference :194-246). `norm_layer` defaults to nn.SyncBatchNorm as in the reference."""

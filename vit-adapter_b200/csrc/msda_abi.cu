@@ -402,11 +402,14 @@ static size_t accum_workspace_bytes(const msda_dims* d, int dtype) {
   return (size_t)d->batch * d->spatial_size * d->num_heads * d->channels * sizeof(float);
 }
 // Slab-sorted backward (msda_bwd_sorted.cu). Tuning key "bwd_sorted": 0 = where it measured faster, 1 = off, 2 = wherever it
-// applies. MEASURED (profiles/r2_bwd_sorted_vs_query_order.jsonl, B200, L2 flushed): the sort passes cost ~100 us at the bs-16
-// shapes and the walker spends ~25 instructions per sampled point whatever the row length, so it pays where a sample's four
-// row atomics are expensive (256-byte rows, D = 64) and cell runs are long (one level, >= 16 samples per cell): ViT-Adapter-S
-// Extractor 330 -> 282 us fp32 / 337 -> 265 us bf16, L 16x64 Extractor 200 -> 175 us bf16. At D = 32 it ties (B Extractor
-// 323 -> 319 us) or loses (Injectors, ~2 samples per cell: 0.85x), so those keep the query-order kernel.
+// applies. MEASURED (profiles/r2_bwd_sorted_vs_query_order.jsonl, B200, L2 flushed, sorted vs query order): the sort costs
+// ~45 us per 4 M samples and the walker ~25 instructions per sample whatever the row length, so it pays where cell runs are
+// long (one level, >= 16 samples per value token and head: Extractor calls) and either the row atomics are expensive
+// (256-byte rows, D = 64) or the call is large enough to amortise the four launches:
+//   ViT-Adapter-B Extractor bs 16  322.6 -> 267.3 us fp32 (1.21x), 336.8 -> 301.9 us bf16     S Extractor 330.6 -> 244.3 (1.35x),
+//   336.9 -> 242.7 bf16 (1.39x)     L 16x64 Extractor bs 1  197.3 -> 168.9 (1.17x), bf16 201.2 -> 168.9 (1.19x)     T Extractor 1.09x.
+// It loses on the Injectors (3 levels, ~2 samples per cell: 0.76-0.93x) and on small 128-byte-row calls (L 16x32 Extractor
+// bs 1, 1 M samples: 0.85x), which keep the query-order kernel.
 static size_t sorted_workspace_bytes(const msda_dims* d, int dtype) {
   const int mode = g_bwd_sorted.load();
   if (mode == 1) return 0;
@@ -414,7 +417,9 @@ static size_t sorted_workspace_bytes(const msda_dims* d, int dtype) {
   if (g_bwd_cell.load() == 2 || g_bwd_packed16.load() == 2) return 0;  // an explicitly requested opt-in kernel wins
   if (mode != 2) {
     const long long samples_per_slab = (long long)d->num_query * d->num_levels * d->num_point;
-    if (!(d->channels == 64 && samples_per_slab >= 16ll * d->spatial_size)) return 0;
+    const long long samples = samples_per_slab * d->batch * d->num_heads;
+    if (samples_per_slab < 16ll * d->spatial_size) return 0;
+    if (!(d->channels == 64 || samples >= 2000000ll)) return 0;
   }
   return backward_sorted_workspace_bytes(d->batch, d->spatial_size, d->num_heads, d->channels, d->num_levels, d->num_query,
                                          d->num_point, sm_count());
