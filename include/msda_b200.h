@@ -120,7 +120,9 @@ int msda_forward_ex(const msda_dims* dims, int dtype,
                     void* stream);
 
 /* Bytes of scratch the backward needs for (dims, dtype); 0 when none is needed.
- * (bf16 / f16 accumulate grad_value in an fp32 scratch of N*S*M*D floats.) */
+ * (bf16 / f16 accumulate grad_value in an fp32 scratch of N*S*M*D floats; calls that take the slab-sorted backward -
+ * single-level calls with many samples per value token, see msda_set_tuning "bwd_sorted" - add the sort buffers: one
+ * 4-byte index per sample plus the histograms. Ask again after changing a tuning key.) */
 size_t msda_backward_workspace_bytes(const msda_dims* dims, int dtype);
 
 /* Backward: replaces ms_deform_attn_cuda_backward (ms_deform_attn_cuda.cu:83-153) and the col2im
@@ -275,6 +277,9 @@ uint64_t msda_launch_count(void);
  *   "bwd_cell_chunk"                queries per chunk of the cell-bucketed backward
  *   "bwd_packed16"                  2 = bf16 / f16 backward with packed 16-bit reductions straight into grad_value (no fp32
  *                                   scratch, no convert kernel; every contribution rounded to 16 bits - looser numerics)
+ *   "bwd_sorted"                    slab-sorted backward (msda_bwd_sorted.cu; D in {32, 64}): 0 = where it measured faster (one
+ *                                   level, >= 16 samples per value token and head, and D = 64 or >= 2 M samples), 1 = never,
+ *                                   2 = wherever it applies. Changes msda_backward_workspace_bytes().
  * Returns 0, or MSDA_E_NULL for an unknown key. */
 int msda_set_tuning(const char* key, int32_t value);
 

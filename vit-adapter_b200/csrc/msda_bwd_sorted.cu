@@ -236,6 +236,13 @@ __device__ __forceinline__ Row4 row_from_shared(unsigned a) {
   return r;
 }
 
+// one predicated vector reduction (a branch around it costs 4 more instructions on the start-of-cell path, four times)
+__device__ __forceinline__ void red_add_v4_if(unsigned on, float* p, float a, float b, float c, float d) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n\t}" ::"l"(p), "f"(a), "f"(b),
+               "f"(c), "f"(d), "r"(on)
+               : "memory");
+}
+
 template <typename T, int G>
 struct WalkScratch {
   static constexpr int kGroups = 32 / G;
@@ -427,8 +434,8 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_bwd_sorted_kernel(const P
         const unsigned nx[4] = {X.x, X.y, X.z, X.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          if (cur[k] > 1u)
-            red_add_v4(reinterpret_cast<float*>(gvb2 + ((size_t)cur[k] << kAccShift)), acc[k].lo.x, acc[k].lo.y, acc[k].hi.x, acc[k].hi.y);
+          red_add_v4_if(cur[k] > 1u, reinterpret_cast<float*>(gvb2 + ((size_t)cur[k] << kAccShift)), acc[k].lo.x, acc[k].lo.y, acc[k].hi.x,
+                        acc[k].hi.y);
           acc[k].lo = acc[k].hi = make_float2(0.f, 0.f);
           cur[k] = nx[k];
           if (cur[k] > 1u) v[k] = row_from_global<T>(vb2 + cur[k]);
