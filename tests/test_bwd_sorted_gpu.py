@@ -157,3 +157,44 @@ def test_sorted_backward_many_warps_per_slab():
     torch.testing.assert_close(gv, wgv, rtol=1e-4, atol=1e-4 * _scale(wgv))
     torch.testing.assert_close(gl, wgl, rtol=1e-4, atol=1e-4 * _scale(wgl))
     torch.testing.assert_close(ga, wga, rtol=1e-4, atol=1e-4 * _scale(wga))
+
+
+@pytest.mark.parametrize('seed', range(12))
+def test_sorted_backward_random_shapes(seed):
+    """Seeded random shapes (levels 1-4 with ragged maps, points 1-8, heads 1-7, D in {32, 64}, ragged query counts), forced
+    through the sorted backward, against the C oracle."""
+    import random
+    rnd = random.Random(1000 + seed)
+    L = rnd.randint(1, 4)
+    shapes = [(rnd.randint(1, 12), rnd.randint(1, 12)) for _ in range(L)]
+    N, M, D = rnd.randint(1, 3), rnd.randint(1, 7), rnd.choice([32, 64])
+    Lq, P = rnd.choice([1, 5, 33, 97, 260]), rnd.randint(1, 8)
+    inp = make_inputs(N, M, D, Lq, shapes, P, seed=2000 + seed, dist=rnd.choice(['uniform', 'edges']))
+    wgv, wgl, wga = c_oracle.backward(inp['value'], inp['shapes'], inp['lsi'], inp['loc'], inp['aw'], inp['grad_out'])
+    gv, gl, ga = _bwd(inp, torch.float32, bwd_sorted=2)
+    torch.testing.assert_close(gv, wgv, rtol=1e-4, atol=1e-4 * _scale(wgv))
+    torch.testing.assert_close(gl, wgl, rtol=1e-4, atol=1e-4 * _scale(wgl))
+    torch.testing.assert_close(ga, wga, rtol=1e-4, atol=1e-4 * _scale(wga))
+
+
+def test_sorted_backward_in_a_cuda_graph():
+    """The four kernels of the sorted backward and its workspace allocation capture into a CUDA graph (nothing in the call
+    synchronises); replays give the eager result to summation order."""
+    inp = make_inputs(2, 6, 64, 1344, [(16, 16)], 4, seed=21, dist='adapter')
+    g = {k: v.to(DEV) for k, v in inp.items()}
+    eager = _cabi.backward(g['value'], g['shapes'], g['lsi'], g['loc'], g['aw'], g['grad_out'], 64)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        _cabi.backward(g['value'], g['shapes'], g['lsi'], g['loc'], g['aw'], g['grad_out'], 64)
+        torch.cuda.synchronize()
+        n0 = _cabi.launch_count()
+        with torch.cuda.graph(graph, stream=s):
+            out = _cabi.backward(g['value'], g['shapes'], g['lsi'], g['loc'], g['aw'], g['grad_out'], 64)
+        assert _cabi.launch_count() - n0 == 4   # the sorted path was the one captured
+    for _ in range(2):
+        graph.replay()
+    torch.cuda.synchronize()
+    for a, b in zip(out, eager):
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-4 * _scale(b))
