@@ -311,7 +311,6 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_bwd_sorted_kernel(const P
   const char* __restrict__ vb2 = reinterpret_cast<const char*>(p.value) + slab_v * sizeof(T) + j * (4 * sizeof(T)) - 2;
   char* __restrict__ gvb2 = reinterpret_cast<char*>(p.grad_value) + slab_v * 4u + j * 16 - (2 << kAccShift);  // fp32 accumulator
   const char* __restrict__ gob_row = reinterpret_cast<const char*>(p.grad_out) + pair0 * kRowB;
-  const char* __restrict__ vb_row = reinterpret_cast<const char*>(p.value) + slab_v * sizeof(T) - 2;
   float* __restrict__ gaw = reinterpret_cast<float*>(p.grad_aw) + pair0 * LP;
   float2* __restrict__ gloc = reinterpret_cast<float2*>(p.grad_loc) + pair0 * LP;
   const float* __restrict__ aw = reinterpret_cast<const float*>(p.aw) + pair0 * LP;
@@ -386,6 +385,7 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_bwd_sorted_kernel(const P
       lw = gm.lw;
       cwC = (unsigned)(s_lvStart[lvl] + (gm.h_low + 1) * W + (gm.w_low + 1)) | (gm.mask << 20) | (lvl << 24);
     }
+    unsigned heads = 0u;
     // ---- prepare: one point per lane ----------------------------------------------------------------------------------------------
     {
       unsigned prev = __shfl_up_sync(0xffffffffu, cwC, 1, G);
@@ -407,17 +407,13 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_bwd_sorted_kernel(const P
         cf[1] = xw[1] > 1u ? (hh * lw) * a : 0.f;
         cf[2] = xw[2] > 1u ? (lh * hw) * a : 0.f;
         cf[3] = xw[3] > 1u ? (lh * lw) * a : 0.f;
-        if (head) {  // the four value rows this cell needs within the next G steps: request the lines now
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (xw[k] > 1u) prefetch_l2(vb_row + xw[k]);
-        }
       }
       if constexpr (kBufs == 2) __syncwarp();  // the previous batch's readers are done with the scratch
       sts128(scr + SC::kW + my * 32u, __float_as_uint(cf[0]), __float_as_uint(cf[0]), __float_as_uint(cf[1]), __float_as_uint(cf[1]));
       sts128(scr + SC::kW + my * 32u + 16u, __float_as_uint(cf[2]), __float_as_uint(cf[2]), __float_as_uint(cf[3]), __float_as_uint(cf[3]));
       sts128(scr + SC::kX + my * 16u, xw[0], xw[1], xw[2], xw[3]);
-      sts32(scr + SC::kH + my * 4u, head ? 1u : 0u);
+      // start-of-cell flags of the whole batch as one register: bit (lane) = that lane's sample starts a cell
+      heads = __ballot_sync(0xffffffffu, head);
       if constexpr (kBufs == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");  // this batch's rows have landed
       else asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncwarp();
@@ -427,7 +423,7 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_bwd_sorted_kernel(const P
 #pragma unroll 2
     for (int t = 0; t < G; ++t) {
       const unsigned st = grp + (unsigned)t;
-      const unsigned hd = lds32(scr + SC::kH + st * 4u);
+      const unsigned hd = (heads >> (gi * G + t)) & 1u;
       const Row4 g = row_from_shared<T>(gbuf + (unsigned)t * kRowB);
       if (hd) {  // group-uniform: a new cell starts here - flush the partial rows, fetch the new cell's rows
         const uint4 X = lds128(scr + SC::kX + st * 16u);
