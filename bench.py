@@ -238,9 +238,10 @@ def run_reference_arm(args):
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': workload_config(variant, batch, 'f32'),
         'cpu_baseline': {'value': value, 'unit': 'Gsamples/s', 'cores': threads, 'kind': 'port',
-                         'sample': '%d of %d images per step (BASELINE cfg 1 shape), Injector+Extractor fwd+bwd via '
+                         'sample': '%d of %d images per step at this workload\'s own shape (ViT-Adapter-%s: %d heads x %d ch, '
+                                   '%dx%d; BASELINE cfg 1 is the same call sequence at variant S), Injector+Extractor fwd+bwd via '
                                    'oracle/core_pytorch.py (restatement of ms_deform_attn_core_pytorch, F.grid_sample '
-                                   '+ autograd), torch %d threads' % (sample_batch, batch, threads)},
+                                   '+ autograd), torch %d threads' % (sample_batch, batch, variant, M, D, side, side, threads)},
         'e2e': {'value': value, 'unit': 'Gsamples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
