@@ -121,27 +121,28 @@ def test_sorted_backward_vs_reference_cuda(cfg):
 
 
 def test_sorted_backward_selection():
-    """Without tuning the sorted backward (4 kernels: histogram, scan, scatter, walk) runs where it measured faster - >= 16
-    samples per value token and head, and 64 channels per head or >= 2 M samples - and the one-kernel query-order backward
-    elsewhere; bwd_sorted=2 / 1 force one or the other. They agree to summation order."""
-    dense64 = make_inputs(2, 6, 64, 1344, [(16, 16)], 4, seed=16, dist='adapter')      # 21 samples per token: sorted
+    """Without tuning the sorted backward (5 kernels: histogram, 2 x scan, scatter, walk) runs where it measured faster - one
+    level with >= 16 samples per value token and head, and >= 0.5 M samples at 64 channels per head / >= 1 M at 32 - and the
+    one-kernel query-order backward elsewhere; bwd_sorted=2 / 1 force one or the other. They agree to summation order."""
+    big64 = make_inputs(4, 6, 64, 5376, [(32, 32)], 4, seed=16, dist='adapter')      # ViT-Adapter-S Extractor, 4 images: 516 k samples
     n0 = _cabi.launch_count()
-    gv, gl, ga = _bwd(dense64, torch.float32)
-    assert _cabi.launch_count() - n0 == 4
+    gv, gl, ga = _bwd(big64, torch.float32)
+    assert _cabi.launch_count() - n0 == 5
     n0 = _cabi.launch_count()
-    ogv, ogl, oga = _bwd(dense64, torch.float32, bwd_sorted=1)
+    ogv, ogl, oga = _bwd(big64, torch.float32, bwd_sorted=1)
     assert _cabi.launch_count() - n0 == 1
     torch.testing.assert_close(gv, ogv, rtol=1e-4, atol=1e-4 * _scale(ogv))
     torch.testing.assert_close(gl, ogl, rtol=1e-4, atol=1e-4 * _scale(ogl))
     torch.testing.assert_close(ga, oga, rtol=1e-4, atol=1e-4 * _scale(oga))
-    for inp in (make_inputs(2, 12, 32, 1344, [(16, 16)], 4, seed=16, dist='adapter'),              # 32 channels
+    for inp in (make_inputs(2, 6, 64, 1344, [(16, 16)], 4, seed=16, dist='adapter'),                # dense, but a small call
+                make_inputs(4, 6, 32, 5376, [(32, 32)], 4, seed=16, dist='adapter'),                # 516 k samples at 32 channels
                 make_inputs(2, 6, 64, 256, [(32, 32), (16, 16), (8, 8)], 4, seed=16, dist='adapter')):  # 2 samples per token
         n0 = _cabi.launch_count()
         _bwd(inp, torch.float32)
         assert _cabi.launch_count() - n0 == 1
         n0 = _cabi.launch_count()
         _bwd(inp, torch.float32, bwd_sorted=2)
-        assert _cabi.launch_count() - n0 == 4
+        assert _cabi.launch_count() - n0 == 5
     # a head dimension outside {32, 64} has no sorted kernel: one launch whatever the knob says
     inp = make_inputs(1, 2, 16, 50, [(6, 6)], 4, seed=17, dist='uniform')
     n0 = _cabi.launch_count()
@@ -182,6 +183,14 @@ def test_sorted_backward_in_a_cuda_graph():
     synchronises); replays give the eager result to summation order."""
     inp = make_inputs(2, 6, 64, 1344, [(16, 16)], 4, seed=21, dist='adapter')
     g = {k: v.to(DEV) for k, v in inp.items()}
+    _cabi.set_tuning(bwd_sorted=2)
+    try:
+        _sorted_in_a_graph(g)
+    finally:
+        _cabi.set_tuning(bwd_sorted=0)
+
+
+def _sorted_in_a_graph(g):
     eager = _cabi.backward(g['value'], g['shapes'], g['lsi'], g['loc'], g['aw'], g['grad_out'], 64)
     torch.cuda.synchronize()
     graph = torch.cuda.CUDAGraph()
@@ -192,7 +201,7 @@ def test_sorted_backward_in_a_cuda_graph():
         n0 = _cabi.launch_count()
         with torch.cuda.graph(graph, stream=s):
             out = _cabi.backward(g['value'], g['shapes'], g['lsi'], g['loc'], g['aw'], g['grad_out'], 64)
-        assert _cabi.launch_count() - n0 == 4   # the sorted path was the one captured
+        assert _cabi.launch_count() - n0 == 5   # the sorted path was the one captured
     for _ in range(2):
         graph.replay()
     torch.cuda.synchronize()

@@ -25,6 +25,7 @@ def main():
     ap.add_argument('--dtypes', default='f32,bf16')
     ap.add_argument('--chunks', default='0')
     ap.add_argument('--iters', type=int, default=20)
+    ap.add_argument('--batch', type=int, default=0, help='images per call (default: the variant\'s BASELINE batch)')
     ap.add_argument('--dist', default='adapter')
     ap.add_argument('--mode', default='cell', choices=['cell', 'packed16', 'sorted'], help='which opt-in backward to compare with the default')
     ap.add_argument('--out', default=os.path.join(ROOT, 'gpurun_out', 'bwd_cell_check.jsonl'))
@@ -37,7 +38,7 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
     out = open(args.out, 'w')
     for variant in args.variants.split(','):
-        batch = VARIANTS[variant][3]
+        batch = args.batch or VARIANTS[variant][3]
         for (name, N, M, D, Lq, shapes) in call_shapes(variant, batch):
             for dn in args.dtypes.split(','):
                 dtype = {'f32': torch.float32, 'bf16': torch.bfloat16, 'f16': torch.float16}[dn]
@@ -65,7 +66,7 @@ def main():
                     torch.cuda.synchronize()
                     errs = [float((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-30)) for a, b in zip(got, ref)]
                     t_new = timeit(call, args.iters, 3, flush)
-                    row = dict(mode=args.mode, variant=variant, call=name, dtype=dn, chunk=int(ch), dist=args.dist, old_us=round(t_old['med'] * 1e3, 1),
+                    row = dict(mode=args.mode, variant=variant, batch=batch, call=name, dtype=dn, chunk=int(ch), dist=args.dist, old_us=round(t_old['med'] * 1e3, 1),
                                cell_us=round(t_new['med'] * 1e3, 1), cell_min_us=round(t_new['min'] * 1e3, 1),
                                speedup=round(t_old['med'] / t_new['med'], 2), hbm_frac=round(nbytes / (t_new['med'] * 1e-3) / 1e9 / peak, 3),
                                gsamples=round(n_points(N, M, Lq, len(shapes)) / (t_new['med'] * 1e-3) / 1e9, 2),

@@ -30,6 +30,8 @@ namespace msda {
 // Workspace carved by the host (launch_backward_sorted below); all pointers are device pointers into it.
 struct SortedPlan {
   unsigned* cnt;  // [N*M][parts][S] histograms of clamped top-left tokens -> exclusive scan -> the parts' first positions
+  unsigned* tot;  // [N*M][S]   per key, the samples of all parts
+  unsigned* chunk_sum;  // [N*M][ceil(S / 256)] per chunk of 256 keys, its samples
   unsigned* nin;  // [N*M]      samples of the slab that pass the bounds test
   unsigned* idx;  // [N*M][cap] the slab's samples in cell order: query * L*P + point
   int cap;        // Lq * L * P: samples per slab
@@ -50,14 +52,13 @@ struct SortedPlan {
 // A slab is cut into sp.parts PARTS of consecutive queries so that the grid covers every SM several times over (192 slabs on
 // 148 SMs would otherwise run as two waves). Three kernels:
 //   hist    CTA (slab, part): histogram of the part's samples in shared memory (integer ATOMS), stored to cnt[slab][part][S]
-//   scan    CTA (slab): exclusive scan of cnt in (key, part) order, in place; nin[slab] = samples in range
+//   scan    two kernels over (slab, 256 keys): exclusive scan of cnt in (key, part) order, in place; nin[slab] = samples in range
 //   scatter CTA (slab, part): its row of cnt becomes the cursors in shared memory; every sample takes its position with one
 //           ATOMS and writes its 4-byte index there (a first version wrote 20-byte records - fractions, weight, cell word -
 //           to those random positions: 75 us instead of 23 us at ViT-Adapter-B bs 16; the walker now gathers location and
 //           weight by index and redoes the geometry)
 constexpr int kSortThreads = 256;
 constexpr int kSortUnroll = 4;
-constexpr int kScanThreads = 1024;
 
 template <int LT, int PT, bool SCATTER>
 __global__ void __launch_bounds__(kSortThreads) msda_sort_part_kernel(const Params p, const SortedPlan sp) {
@@ -129,57 +130,85 @@ __global__ void __launch_bounds__(kSortThreads) msda_sort_part_kernel(const Para
   }
 }
 
-// exclusive scan of cnt[slab][part][key] in (key, part) order. Every access is coalesced over the key: per-key totals over
-// the parts go to shared memory (S counters, dynamic), are scanned there in chunks of the CTA size, and a last sweep hands
-// every (part, key) its first position.
-__global__ void __launch_bounds__(kScanThreads) msda_sort_scan_kernel(const SortedPlan sp, int S) {
-  extern __shared__ unsigned s_tot[];
-  __shared__ unsigned s_warp[kScanThreads / 32];
-  __shared__ unsigned s_carry;
-  const int slab = blockIdx.x, parts = sp.parts;
-  unsigned* __restrict__ c = sp.cnt + (size_t)slab * parts * S;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < S; i += kScanThreads) {
-    unsigned sum = 0;
-    for (int r = 0; r < parts; ++r) sum += c[(size_t)r * S + i];
-    s_tot[i] = sum;
-  }
-  if (tid == 0) s_carry = 0u;
+// exclusive scan of cnt[slab][part][key] in (key, part) order, two kernels over (slab, chunk of kScanKeys keys) so that calls
+// with few slabs still fill the GPU (one CTA per slab took 31-40 us at ViT-Adapter-L bs 1: 16 CTAs reading 7 MB):
+//   totals  per key, the sum over the parts -> tot[slab][key]; per chunk, the sum of its keys -> chunk_sum[slab][chunk]
+//   bases   the chunk's first position (sum of the chunk sums before it), a block scan of its totals, and a sweep that
+//           hands every (part, key) its first position; the last chunk also writes nin[slab]
+// Every access is coalesced over the key; loads go out in batches of 8 parts.
+constexpr int kScanKeys = 256;
+
+__device__ __forceinline__ unsigned block_sum_256(unsigned v, unsigned* s_w) {  // all 256 threads; returns the total
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
   __syncthreads();
-  for (int base = 0; base < S; base += kScanThreads) {
-    const int i = base + tid;
-    const unsigned v = i < S ? s_tot[i] : 0u;
-    unsigned incl = v;
+  if (lane == 0) s_w[warp] = v;
+  __syncthreads();
+  unsigned t = 0;
 #pragma unroll
-    for (int s = 1; s < 32; s <<= 1) {
-      const unsigned t = __shfl_up_sync(0xffffffffu, incl, s);
-      if (lane >= s) incl += t;
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    const unsigned carry = s_carry;
-    if (warp == 0) {
-      const unsigned w = s_warp[lane];
-      unsigned wi = w;
+  for (int w = 0; w < kScanKeys / 32; ++w) t += s_w[w];
+  return t;
+}
+
+__global__ void __launch_bounds__(kScanKeys) msda_sort_totals_kernel(const SortedPlan sp, int S) {
+  __shared__ unsigned s_w[kScanKeys / 32];
+  const int slab = blockIdx.y, chunk = blockIdx.x, parts = sp.parts;
+  const unsigned* __restrict__ c = sp.cnt + (size_t)slab * parts * S;
+  const int i = chunk * kScanKeys + threadIdx.x;
+  unsigned sum = 0;
+  if (i < S) {
+    for (int r0 = 0; r0 < parts; r0 += 8) {
+      unsigned v[8];
 #pragma unroll
-      for (int s = 1; s < 32; s <<= 1) {
-        const unsigned t = __shfl_up_sync(0xffffffffu, wi, s);
-        if (lane >= s) wi += t;
-      }
-      s_warp[lane] = wi - w;  // exclusive prefix of the warp totals
-      if (lane == 31) s_carry = carry + wi;
+      for (int k = 0; k < 8; ++k) v[k] = r0 + k < parts ? c[(size_t)(r0 + k) * S + i] : 0u;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sum += v[k];
     }
-    __syncthreads();
-    if (i < S) s_tot[i] = carry + s_warp[warp] + incl - v;
-    __syncthreads();
+    sp.tot[(size_t)slab * S + i] = sum;
   }
-  if (tid == 0) sp.nin[slab] = s_carry;
-  for (int i = tid; i < S; i += kScanThreads) {
-    unsigned run = s_tot[i];
-    for (int r = 0; r < parts; ++r) {
-      const unsigned v = c[(size_t)r * S + i];
-      c[(size_t)r * S + i] = run;
-      run += v;
+  const unsigned total = block_sum_256(sum, s_w);
+  if (threadIdx.x == 0) sp.chunk_sum[(size_t)slab * gridDim.x + chunk] = total;
+}
+
+__global__ void __launch_bounds__(kScanKeys) msda_sort_bases_kernel(const SortedPlan sp, int S) {
+  __shared__ unsigned s_w[kScanKeys / 32];
+  const int slab = blockIdx.y, chunk = blockIdx.x, parts = sp.parts, nchunks = gridDim.x;
+  unsigned* __restrict__ c = sp.cnt + (size_t)slab * parts * S;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // first position of this chunk
+  unsigned before = 0;
+  for (int k = threadIdx.x; k < chunk; k += kScanKeys) before += sp.chunk_sum[(size_t)slab * nchunks + k];
+  const unsigned offset = block_sum_256(before, s_w);
+  const int i = chunk * kScanKeys + threadIdx.x;
+  const unsigned v = i < S ? sp.tot[(size_t)slab * S + i] : 0u;
+  unsigned incl = v;
+#pragma unroll
+  for (int s = 1; s < 32; s <<= 1) {
+    const unsigned t = __shfl_up_sync(0xffffffffu, incl, s);
+    if (lane >= s) incl += t;
+  }
+  __syncthreads();
+  if (lane == 31) s_w[warp] = incl;
+  __syncthreads();
+  unsigned wbefore = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < kScanKeys / 32; ++w) {
+    if (w < warp) wbefore += s_w[w];
+    total += s_w[w];
+  }
+  if (chunk == nchunks - 1 && threadIdx.x == 0) sp.nin[slab] = offset + total;
+  if (i < S) {
+    unsigned run = offset + wbefore + incl - v;
+    for (int r0 = 0; r0 < parts; r0 += 8) {
+      unsigned x[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) x[k] = r0 + k < parts ? c[(size_t)(r0 + k) * S + i] : 0u;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (r0 + k < parts) c[(size_t)(r0 + k) * S + i] = run;
+        run += x[k];
+      }
     }
   }
 }
@@ -549,8 +578,10 @@ size_t backward_sorted_workspace_bytes(int N, int S, int M, int D, int L, int Lq
   const long long cap = (long long)Lq * L * P;
   if (cap * M >= (1ll << 31) || (long long)Lq * M * D * 4 >= (1ll << 31)) return 0;  // 32-bit in-image point / row offsets
   const size_t slabs = (size_t)N * M;
+  if (slabs > 65535) return 0;                         // the scan kernels put the slab in gridDim.y
   const int parts = sort_parts(slabs, Lq, sm_count);
-  return align16(slabs * parts * S * 4) + align16(slabs * 4) + align16(slabs * (size_t)cap * 4);
+  return align16(slabs * parts * S * 4) + align16(slabs * S * 4) + align16(slabs * ((S + 255) / 256) * 4) + align16(slabs * 4) +
+         align16(slabs * (size_t)cap * 4);
 }
 
 template <int LT, int PT>
@@ -565,11 +596,10 @@ static cudaError_t launch_sort(const Params& p, const SortedPlan& sp, cudaStream
   msda_sort_part_kernel<LT, PT, false><<<grid, kSortThreads, smem, s>>>(p, sp);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  if (smem > 40u * 1024u) {
-    e = cudaFuncSetAttribute(msda_sort_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-  }
-  msda_sort_scan_kernel<<<(unsigned)((size_t)p.N * p.M), kScanThreads, smem, s>>>(sp, p.S);
+  const dim3 gscan((unsigned)((p.S + kScanKeys - 1) / kScanKeys), (unsigned)((size_t)p.N * p.M));
+  msda_sort_totals_kernel<<<gscan, kScanKeys, 0, s>>>(sp, p.S);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  msda_sort_bases_kernel<<<gscan, kScanKeys, 0, s>>>(sp, p.S);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   msda_sort_part_kernel<LT, PT, true><<<grid, kSortThreads, smem, s>>>(p, sp);
   return cudaGetLastError();
@@ -586,6 +616,10 @@ cudaError_t launch_backward_sorted(const Params& p, int dtype, void* ws, int sm_
   char* w = reinterpret_cast<char*>(ws);
   sp.cnt = reinterpret_cast<unsigned*>(w);
   w += align16(slabs * sp.parts * p.S * 4);
+  sp.tot = reinterpret_cast<unsigned*>(w);
+  w += align16(slabs * p.S * 4);
+  sp.chunk_sum = reinterpret_cast<unsigned*>(w);
+  w += align16(slabs * ((p.S + 255) / 256) * 4);
   sp.nin = reinterpret_cast<unsigned*>(w);
   w += align16(slabs * 4);
   sp.idx = reinterpret_cast<unsigned*>(w);
@@ -608,7 +642,7 @@ cudaError_t launch_backward_sorted(const Params& p, int dtype, void* ws, int sm_
   else if (dtype == MSDA_BF16) e = bwd_sorted_bf16(p, sp, s);
   else if (dtype == MSDA_F16) e = bwd_sorted_f16(p, sp, s);
   else e = cudaErrorNotSupported;
-  if (e == cudaSuccess && launches) *launches = 4;
+  if (e == cudaSuccess && launches) *launches = 5;
   return e;
 }
 #endif  // MSDA_TU
