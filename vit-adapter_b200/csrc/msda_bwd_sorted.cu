@@ -6,19 +6,24 @@
 // L2's atomic units serve in 320 us. But grad_value of one (batch, head) SLAB has only S rows (1 024 for
 // that call), so ~84 contributions go to every row: the scatter is a segmented reduction in disguise.
 //
-// Pass 1 (msda_sort_slab_kernel, one CTA per slab): the slab's sampled points are SORTED BY THE BILINEAR CELL they fall in -
-// a counting sort whose histogram lives in shared memory (integer ATOMS only), 20 bytes per point written in cell order.
-// Pass 2 (msda_bwd_sorted_kernel): a group of D/4 lanes walks a contiguous range of the sorted list, 4 channels per lane:
-//   * the four value rows of the current cell and the four partial grad_value rows stay in REGISTERS for the whole run of
-//     points of that cell (4 x 4 + 4 x 4 floats per lane);
-//   * per point: ONE read of the query's grad_out row (the query-order kernel gathers four value rows and scatters four),
-//     16 FMAs for u_k = <grad_out, v_k> and 16 for the grad_value partials; corner weights and the row offset come as one
-//     20-byte broadcast record from the warp's shared-memory scratch, prepared 32 points at a time with one point per lane;
-//   * the partial dot products are reduced with a transposed shuffle network (D/4 values -> 1 per lane) and handed through
-//     shared memory to the lane that owns the point's record, which turns (u_1..u_4) into grad_attn_weight and
-//     grad_sampling_loc (the linear-in-the-corners algebra of msda_bwd.cu);
-//   * when the cell changes, the four partial rows leave with one REDG.E.ADD.F32x4 per lane each: row atomics per point
-//     drop from 4 to 4 / (points per cell run) - ~20 points per cell at the ViT-Adapter-B Extractor.
+// Pass 1 (msda_sort_*_kernel): every slab's sampled points are SORTED BY THE BILINEAR CELL they fall in - a counting sort whose
+// histograms live in shared memory (integer ATOMS only); one 4-byte sample index per point is written in cell order.
+// Pass 2 (msda_bwd_sorted_kernel): a group of D/4 lanes walks a contiguous range of the sorted list. A lane owns ONE corner
+// of the bilinear cell and 16 channels (four 4-channel vectors, interleaved with the other lanes of the corner so that every
+// vector access of a corner covers whole 32-byte sectors):
+//   * the lane's 16 channels of the current cell's value row and of the partial grad_value row stay in REGISTERS for the
+//     whole run of samples of that cell (16 + 16 floats);
+//   * per sample: ONE read of the query's grad_out row (the query-order kernel gathers four value rows and scatters four),
+//     staged through shared memory with cp.async one batch of 32 samples ahead; 8 packed FMAs (FFMA2) for the lane's share
+//     of u_k = <grad_out, v_k> and 8 for the partial row; the corner weight comes as one 8-byte broadcast from the warp's
+//     scratch, prepared with one sample per lane (index load, gather of location / weight, geometry, corner weights);
+//   * u_k needs one add across the 2 (D = 32) or 4 (D = 64) lanes of the corner; the lane that prepared the sample turns
+//     (u_1..u_4) into grad_attn_weight and grad_sampling_loc (the linear-in-the-corners algebra of msda_bwd.cu);
+//   * when the cell changes, the partial row leaves with four REDG.E.ADD.F32x4 per lane: row atomics per sample drop
+//     from 4 to 4 / (samples per cell run) - ~20 samples per cell at the ViT-Adapter-B Extractor.
+// (An earlier lane layout - every lane 4 channels of all four corners - needed a transposing shuffle reduction of four
+// values over the whole group per sample, 19 of its 47 instructions per step, and four predicated row flushes / loads where a
+// cell starts: 108 M instead of 83 M instructions at ViT-Adapter-B bs 16. Same time in fp32, 5-10 % slower in bf16 / D = 64.)
 // Nothing depends on where the reference points are: the sort is by the actual sampling location, so every input is
 // handled; an adversarial input (all points in one cell) degenerates to long runs, still correct.
 // The summation ORDER differs from the query-order kernel (and is not deterministic: positions inside a cell run come from
@@ -288,8 +293,11 @@ struct WalkScratch {
   static constexpr unsigned kX = kW + kGroups * kStride * 32u;    // uint4
   static constexpr unsigned kU = kX + kGroups * kStride * 16u;    // float4
   static constexpr unsigned kH = kU + kGroups * kStride * 16u;    // uint
-  static constexpr unsigned kG = (kH + kGroups * kStride * 4u + 15u) & ~15u;  // grad_out rows: [kBufs][32][kRowB]
-  static constexpr unsigned kBytes = kG + kBufs * 32u * kRowB;
+  static constexpr unsigned kG = (kH + kGroups * kStride * 4u + 15u) & ~15u;  // grad_out rows: [kBufs][group][G rows + skew]
+  static constexpr unsigned kSkew = (G / 4) * 4u * sizeof(T);  // bytes one vector covers across the lanes of a corner: shifts each
+                                                               // group's rows so that the groups' reads hit different banks
+  static constexpr unsigned kGroupB = G * kRowB + kSkew;  // group g's rows start at g * kGroupB, i.e. skewed by g * kSkew
+  static constexpr unsigned kBytes = kG + kBufs * kGroups * kGroupB;
 };
 
 template <typename T, int G, int LT, int PT, int MINB>
@@ -336,22 +344,38 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_bwd_sorted_kernel(const P
   const size_t slab_v = ((size_t)b * p.S * p.M + (size_t)m) * D;
   const size_t pair0 = ((size_t)b * p.Lq * p.M + (size_t)m);  // (b, query 0, m)
   const unsigned qstride = (unsigned)p.M * (unsigned)LP;      // points between consecutive queries of this head
+  // Consumer lane mapping: lane j of a group owns ONE corner (kc) and a quarter / half of the channels as four 4-channel
+  // vectors: vector c covers channels 4 * (c * NH + hq) ..+4, so that the NH lanes of a corner cover whole 32-byte sectors
+  // with every vector access. The dot product <grad_out, v_kc> then needs one add across NH lanes (NH = 2 / 4) instead of a
+  // transposing reduction of four values over all G lanes, and the start-of-cell path handles one row per lane with
+  // immediate offsets instead of four rows with four predicates and addresses.
+  constexpr int NH = G / 4;
+  const int kc = j / NH, hq = j % NH;
+  constexpr unsigned kVecT = 4u * sizeof(T);          // one vector of value / grad_out
+  constexpr unsigned kVecStepT = NH * kVecT;          // between a lane's consecutive vectors
   // value / accumulator bases are biased by the "+ 2" of the offset words
-  const char* __restrict__ vb2 = reinterpret_cast<const char*>(p.value) + slab_v * sizeof(T) + j * (4 * sizeof(T)) - 2;
-  char* __restrict__ gvb2 = reinterpret_cast<char*>(p.grad_value) + slab_v * 4u + j * 16 - (2 << kAccShift);  // fp32 accumulator
+  const char* __restrict__ vb2 = reinterpret_cast<const char*>(p.value) + slab_v * sizeof(T) + hq * kVecT - 2;
+  char* __restrict__ gvb2 = reinterpret_cast<char*>(p.grad_value) + slab_v * 4u + hq * 16 - (2 << kAccShift);  // fp32 accumulator
   const char* __restrict__ gob_row = reinterpret_cast<const char*>(p.grad_out) + pair0 * kRowB;
   float* __restrict__ gaw = reinterpret_cast<float*>(p.grad_aw) + pair0 * LP;
   float2* __restrict__ gloc = reinterpret_cast<float2*>(p.grad_loc) + pair0 * LP;
   const float* __restrict__ aw = reinterpret_cast<const float*>(p.aw) + pair0 * LP;
   const float2* __restrict__ loc = reinterpret_cast<const float2*>(p.loc) + pair0 * LP;
 
-  unsigned cur[4] = {1u, 1u, 1u, 1u};  // offset words of the current cell's rows (1 = not read)
-  Row4 v[4], acc[4];
+  unsigned cur = 1u;  // offset word of the current cell's row of this lane's corner (1 = the reference does not read it)
+  Row4 v[4], acc[4];  // this lane's four vectors of that value row and of the partial grad_value row
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    v[k].lo = v[k].hi = make_float2(0.f, 0.f);
-    acc[k].lo = acc[k].hi = make_float2(0.f, 0.f);
+  for (int c = 0; c < 4; ++c) {
+    v[c].lo = v[c].hi = make_float2(0.f, 0.f);
+    acc[c].lo = acc[c].hi = make_float2(0.f, 0.f);
   }
+  auto flush_row = [&]() {
+    if (cur > 1u) {
+      float* dst = reinterpret_cast<float*>(gvb2 + ((size_t)cur << kAccShift));
+#pragma unroll
+      for (int c = 0; c < 4; ++c) red_add_v4(dst + c * (NH * 4), acc[c].lo.x, acc[c].lo.y, acc[c].hi.x, acc[c].hi.y);
+    }
+  };
   unsigned lastcw = 0xFFFFFFFEu;  // cell word of the group's previous position
 
   // The grad_out rows of a batch go to shared memory: the lanes of a group copy row after row, 16 bytes per lane
@@ -361,7 +385,7 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_bwd_sorted_kernel(const P
     constexpr int kLanesPerRow = kRowB / 16;          // 8 (fp32, D = 32), 4 (16-bit, D = 32), 16 / 8 (D = 64)
     constexpr int kRowsPerIter = G / kLanesPerRow;    // 1 (fp32) or 2 (16-bit)
     const unsigned my_off = (pidx / (unsigned)LP) * MDb;
-    const unsigned dst0 = scr + SC::kG + (unsigned)(buf * 32 + gi * G) * kRowB + (unsigned)(j % kLanesPerRow) * 16u;
+    const unsigned dst0 = scr + SC::kG + (unsigned)(buf * NG + gi) * SC::kGroupB + (unsigned)(j % kLanesPerRow) * 16u;
     const char* src0 = gob_row + (j % kLanesPerRow) * 16;
 #pragma unroll
     for (int t = 0; t < G; t += kRowsPerIter) {
@@ -448,50 +472,35 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_bwd_sorted_kernel(const P
       __syncwarp();
     }
     // ---- consume: G steps; in step t every group works on point t of its batch ---------------------------------------------------
-    const unsigned gbuf = scr + SC::kG + (unsigned)((kBufs == 2 ? (bi & 1) : 0) * 32 + gi * G) * kRowB + j * (4u * (unsigned)sizeof(T));
+    const unsigned gbuf = scr + SC::kG + (unsigned)((kBufs == 2 ? (bi & 1) : 0) * NG + gi) * SC::kGroupB + hq * kVecT;
 #pragma unroll 2
     for (int t = 0; t < G; ++t) {
       const unsigned st = grp + (unsigned)t;
-      const unsigned hd = (heads >> (gi * G + t)) & 1u;
-      const Row4 g = row_from_shared<T>(gbuf + (unsigned)t * kRowB);
-      if (hd) {  // group-uniform: a new cell starts here - flush the partial rows, fetch the new cell's rows
-        const uint4 X = lds128(scr + SC::kX + st * 16u);
-        const unsigned nx[4] = {X.x, X.y, X.z, X.w};
+      if ((heads >> (gi * G + t)) & 1u) {  // group-uniform: a new cell starts here - flush the partial row, fetch the new cell's row
+        flush_row();
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          red_add_v4_if(cur[k] > 1u, reinterpret_cast<float*>(gvb2 + ((size_t)cur[k] << kAccShift)), acc[k].lo.x, acc[k].lo.y, acc[k].hi.x,
-                        acc[k].hi.y);
-          acc[k].lo = acc[k].hi = make_float2(0.f, 0.f);
-          cur[k] = nx[k];
-          if (cur[k] > 1u) v[k] = row_from_global<T>(vb2 + cur[k]);
+        for (int c = 0; c < 4; ++c) acc[c].lo = acc[c].hi = make_float2(0.f, 0.f);
+        cur = lds32(scr + SC::kX + st * 16u + 4u * kc);
+        if (cur > 1u) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) v[c] = row_from_global<T>(vb2 + cur + c * kVecStepT);
         }
       }
-      const uint4 W01 = lds128(scr + SC::kW + st * 32u), W23 = lds128(scr + SC::kW + st * 32u + 16u);
-      const float2 cfp[4] = {make_float2(__uint_as_float(W01.x), __uint_as_float(W01.y)), make_float2(__uint_as_float(W01.z), __uint_as_float(W01.w)),
-                             make_float2(__uint_as_float(W23.x), __uint_as_float(W23.y)), make_float2(__uint_as_float(W23.z), __uint_as_float(W23.w))};
-      float d[4];
+      const uint2 Wk = lds64(scr + SC::kW + st * 32u + 8u * kc);  // (weight, weight) of this lane's corner
+      const float2 cfk = make_float2(__uint_as_float(Wk.x), __uint_as_float(Wk.y));
+      float2 dd = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 dd = __ffma2_rn(g.hi, v[k].hi, __fmul2_rn(g.lo, v[k].lo));
-        d[k] = dd.x + dd.y;
-        acc[k].lo = __ffma2_rn(cfp[k], g.lo, acc[k].lo);
-        acc[k].hi = __ffma2_rn(cfp[k], g.hi, acc[k].hi);
+      for (int c = 0; c < 4; ++c) {
+        const Row4 g = row_from_shared<T>(gbuf + (unsigned)t * kRowB + c * kVecStepT);
+        dd = __ffma2_rn(g.lo, v[c].lo, dd);
+        dd = __ffma2_rn(g.hi, v[c].hi, dd);
+        acc[c].lo = __ffma2_rn(cfk, g.lo, acc[c].lo);
+        acc[c].hi = __ffma2_rn(cfk, g.hi, acc[c].hi);
       }
-      // (u_1..u_4) over the G lanes of the group: two transposing steps (4 -> 2 -> 1 value per lane), then plain butterflies.
-      // Lane j ends up with the total of u_(2 * bit(G/2) + bit(G/4) + 1); the lanes with no lower bit set hand it over.
-      {
-        const bool up1 = (j & (G / 2)) != 0;
-        const float s0 = up1 ? d[0] : d[2], k0 = up1 ? d[2] : d[0];
-        const float s1 = up1 ? d[1] : d[3], k1 = up1 ? d[3] : d[1];
-        d[0] = k0 + __shfl_xor_sync(0xffffffffu, s0, G / 2, G);
-        d[1] = k1 + __shfl_xor_sync(0xffffffffu, s1, G / 2, G);
-        const bool up2 = (j & (G / 4)) != 0;
-        const float s2 = up2 ? d[0] : d[1], k2 = up2 ? d[1] : d[0];
-        float r = k2 + __shfl_xor_sync(0xffffffffu, s2, G / 4, G);
+      float r = dd.x + dd.y;  // <grad_out, v_kc> over this lane's 16 channels; the other NH - 1 lanes of the corner hold the rest
 #pragma unroll
-        for (int s = G / 8; s > 0; s >>= 1) r += __shfl_xor_sync(0xffffffffu, r, s, G);
-        if ((j & (G / 4 - 1)) == 0) sts32(scr + SC::kU + st * 16u + 4u * (unsigned)(j / (G / 4)), __float_as_uint(r));
-      }
+      for (int s = NH / 2; s > 0; s >>= 1) r += __shfl_xor_sync(0xffffffffu, r, s, NH);
+      if (hq == 0) sts32(scr + SC::kU + st * 16u + 4u * kc, __float_as_uint(r));
     }
     __syncwarp();
     // ---- finish: the lane that holds the record turns (u_1..u_4) into the gradients of its point -------------------------------------
@@ -516,10 +525,7 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_bwd_sorted_kernel(const P
     idxN = idxNN;
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");  // (the last iteration's look-ahead copy)
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-    if (cur[k] > 1u)
-      red_add_v4(reinterpret_cast<float*>(gvb2 + ((size_t)cur[k] << kAccShift)), acc[k].lo.x, acc[k].lo.y, acc[k].hi.x, acc[k].hi.y);
+  flush_row();
 }
 
 // ---------------------------------------------------------------------------------------------
