@@ -232,12 +232,12 @@ __global__ void __launch_bounds__(kScanKeys) msda_sort_bases_kernel(const Sorted
 //                   corner the reference does not read
 //   xq  uint4       byte offset of each corner's row inside the (b, m) value slab, + 2;  1 = the reference does not read it
 //   uq  float4      the reduced (u_1..u_4) of the point, written by the consumer for the finishing lane
-//   hq  uint        1 when the point STARTS a cell
-//   gbuf            the grad_out rows of the batch (kBufs batches deep), [point][D] as in global memory
+//   gbuf            the grad_out rows of the batch (kBufs batches deep), [group][point][D], each group's rows skewed by kSkew
+// (the start-of-cell flags of a batch travel as one ballot register, not through the scratch)
 
-// Packed fp32 pairs (FFMA2 / FMUL2 on 64-bit register pairs; the sm_100 intrinsics __ffma2_rn / __fmul2_rn): per lane and
-// point the walker needs 16 FMAs for the four dot products and 16 for the four partial rows; as pairs these are 8 + 8
-// instructions plus 4 adds. A row of 4 channels is two pairs.
+// Packed fp32 pairs (FFMA2 on 64-bit register pairs; the sm_100 intrinsic __ffma2_rn): per lane and sample the walker needs
+// 16 FMAs for its share of the dot product and 16 for its share of the partial row; as pairs these are 8 + 8 instructions.
+// A vector of 4 channels is two pairs.
 struct Row4 {
   float2 lo, hi;
 };
@@ -292,8 +292,7 @@ struct WalkScratch {
   static constexpr unsigned kW = 0;                                // 2 x float4 [kGroups][kStride]
   static constexpr unsigned kX = kW + kGroups * kStride * 32u;    // uint4
   static constexpr unsigned kU = kX + kGroups * kStride * 16u;    // float4
-  static constexpr unsigned kH = kU + kGroups * kStride * 16u;    // uint
-  static constexpr unsigned kG = (kH + kGroups * kStride * 4u + 15u) & ~15u;  // grad_out rows: [kBufs][group][G rows + skew]
+  static constexpr unsigned kG = kU + kGroups * kStride * 16u;    // grad_out rows: [kBufs][group][G rows + skew]
   static constexpr unsigned kSkew = (G / 4) * 4u * sizeof(T);  // bytes one vector covers across the lanes of a corner: shifts each
                                                                // group's rows so that the groups' reads hit different banks
   static constexpr unsigned kGroupB = G * kRowB + kSkew;  // group g's rows start at g * kGroupB, i.e. skewed by g * kSkew
