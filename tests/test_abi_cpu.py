@@ -105,3 +105,36 @@ def test_pybind_compat_module_has_reference_surface():
         m.ms_deform_attn_forward(torch.rand(1, 4, 1, 4), torch.as_tensor([(2, 2)]), torch.zeros(1, dtype=torch.long),
                                  torch.rand(1, 1, 1, 1, 1, 2), torch.rand(1, 1, 1, 1, 1), 64)
     sys.modules.pop('MultiScaleDeformableAttention', None)
+
+
+def test_backward_workspace_sizes_follow_the_kernel_selection():
+    """msda_backward_workspace_bytes() needs no GPU: 16-bit dtypes ask for the fp32 accumulator, calls that take the slab-sorted
+    backward (one level, >= 16 samples per value token and head, large enough) add its sort buffers, and the tuning key
+    changes the answer."""
+    import ctypes
+    from vit_adapter_b200 import _cabi
+    lib = _cabi.load()
+    F32, BF16 = 0, 1
+    assert (_cabi._DTYPES[__import__('torch').float32], _cabi._DTYPES[__import__('torch').bfloat16]) == (F32, BF16)
+
+    def ws(N, S, M, D, L, Lq, P, dtype):
+        d = _cabi.MsdaDims(N, S, M, D, L, Lq, P)
+        return lib.msda_backward_workspace_bytes(ctypes.byref(d), dtype)
+
+    extractor_b = (16, 1024, 12, 32, 1, 5376, 4)      # ViT-Adapter-B Extractor, 16 images: 4.1 M samples, 21 per token and head
+    injector_b = (16, 5376, 12, 32, 3, 1024, 4)       # 2.3 samples per token and head
+    small64 = (1, 256, 6, 64, 1, 1344, 4)             # dense but tiny
+    accum = lambda N, S, M, D, *_: N * S * M * D * 4
+    try:
+        sorted_bytes = ws(*extractor_b, F32)
+        assert sorted_bytes >= 16 * 12 * 5376 * 4 * 4                  # at least one 4-byte index per sample
+        assert ws(*extractor_b, BF16) == accum(*extractor_b) + sorted_bytes
+        assert ws(*injector_b, F32) == 0 and ws(*injector_b, BF16) == accum(*injector_b)
+        assert ws(*small64, F32) == 0
+        _cabi.set_tuning(bwd_sorted=1)
+        assert ws(*extractor_b, F32) == 0 and ws(*extractor_b, BF16) == accum(*extractor_b)
+        _cabi.set_tuning(bwd_sorted=2)
+        assert ws(*small64, F32) > 0 and ws(*injector_b, F32) > 0
+        assert ws(1, 256, 6, 48, 1, 1344, 4, F32) == 0                 # no sorted kernel for this head width
+    finally:
+        _cabi.set_tuning(bwd_sorted=0)

@@ -277,6 +277,12 @@ __device__ __forceinline__ void red_add_v4_if(unsigned on, float* p, float a, fl
                : "memory");
 }
 
+#ifndef WALK_THREADS
+#define WALK_THREADS 256
+#endif
+constexpr int kWalkThreads = WALK_THREADS;  // threads per walker CTA
+constexpr int kWalkWarps = kWalkThreads / 32;
+
 template <typename T, int G>
 struct WalkScratch {
   static constexpr int kGroups = 32 / G;
@@ -300,7 +306,7 @@ struct WalkScratch {
 };
 
 template <typename T, int G, int LT, int PT, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) msda_bwd_sorted_kernel(const Params p, const SortedPlan sp) {
+__global__ void __launch_bounds__(kWalkThreads, MINB) msda_bwd_sorted_kernel(const Params p, const SortedPlan sp) {
   constexpr bool kStatic = (LT > 0);
   constexpr int D = 4 * G;
   constexpr int NG = 32 / G;                         // groups per warp
@@ -315,7 +321,7 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_bwd_sorted_kernel(const P
   const unsigned MDb = (unsigned)p.M * kRowB;  // bytes between neighbouring tokens of value / neighbouring queries of grad_out
 
   __shared__ int s_lvH[kMaxLevels], s_lvW[kMaxLevels], s_lvStart[kMaxLevels];
-  extern __shared__ __align__(16) char s_scr[];  // kWarps * SC::kBytes
+  extern __shared__ __align__(16) char s_scr[];  // kWalkWarps * SC::kBytes
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int slab = blockIdx.x / sp.ctas_per_slab, chunk = blockIdx.x - slab * sp.ctas_per_slab;
@@ -327,7 +333,7 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_bwd_sorted_kernel(const P
   }
   __syncthreads();  // the only block-wide barrier
   const int n_in = (int)sp.nin[slab];
-  const int r0 = (chunk * kWarps + warp) * sp.ppw;
+  const int r0 = (chunk * kWalkWarps + warp) * sp.ppw;
   if (r0 >= n_in) return;
   const int rend = min(n_in, r0 + sp.ppw);
   const int gi = lane / G, j = lane % G;
@@ -533,12 +539,12 @@ __global__ void __launch_bounds__(kThreads, MINB) msda_bwd_sorted_kernel(const P
 template <typename T, int G, int LT, int PT>
 static cudaError_t launch_sorted_k(const Params& p, const SortedPlan& sp, dim3 grid, cudaStream_t s) {
   auto kern = msda_bwd_sorted_kernel<T, G, LT, PT, WALK_MINB>;
-  constexpr unsigned smem = kWarps * WalkScratch<T, G>::kBytes;
+  constexpr unsigned smem = kWalkWarps * WalkScratch<T, G>::kBytes;
   if (smem > 40u * 1024u) {
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  kern<<<grid, kThreads, smem, s>>>(p, sp);
+  kern<<<grid, kWalkThreads, smem, s>>>(p, sp);
   return cudaGetLastError();
 }
 
@@ -633,10 +639,10 @@ cudaError_t launch_backward_sorted(const Params& p, int dtype, void* ws, int sm_
   // covers every SM several times over
   sp.ppw = 32;
   for (int ppw = 256; ppw >= 32; ppw >>= 1) {
-    const long long ctas = (long long)slabs * ((cap + (long long)kWarps * ppw - 1) / ((long long)kWarps * ppw));
+    const long long ctas = (long long)slabs * ((cap + (long long)kWalkWarps * ppw - 1) / ((long long)kWalkWarps * ppw));
     if (ctas >= 6ll * sm_count || ppw == 32) { sp.ppw = ppw; break; }
   }
-  sp.ctas_per_slab = (int)((cap + (long long)kWarps * sp.ppw - 1) / ((long long)kWarps * sp.ppw));
+  sp.ctas_per_slab = (int)((cap + (long long)kWalkWarps * sp.ppw - 1) / ((long long)kWalkWarps * sp.ppw));
 
   cudaError_t e;
   if (p.L == 3 && p.P == 4) e = launch_sort<3, 4>(p, sp, s);
