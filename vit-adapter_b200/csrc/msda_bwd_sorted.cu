@@ -575,7 +575,10 @@ static size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 // Parts per slab of the sort: enough CTAs for ~4 per SM, at most 64, at least 64 queries each.
 static int sort_parts(size_t slabs, int Lq, int sm_count) {
-  long long parts = (4ll * sm_count + (long long)slabs - 1) / (long long)slabs;
+#ifndef SORT_PARTS_PER_SM
+#define SORT_PARTS_PER_SM 4
+#endif
+  long long parts = ((long long)SORT_PARTS_PER_SM * sm_count + (long long)slabs - 1) / (long long)slabs;
   if (parts > 64) parts = 64;
   while (parts > 1 && Lq / parts < 64) --parts;
   return (int)(parts < 1 ? 1 : parts);
