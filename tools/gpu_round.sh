@@ -11,6 +11,14 @@ python tools/profile_step.py > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python tools/profile_step.py > gpurun_out/ncu_launches.log 2>&1
 python tools/profile_step.py > gpurun_out/plain.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:msda_ -s 8 -c 4 -o gpurun_out/prof python tools/profile_step.py > gpurun_out/ncu_full.log 2>&1
+# round 2: the slab-sorted backward against the query-order one at every BASELINE shape (and at 1 / 2 / 4 images), the
+# walker / sort kernels under ncu, the north-star configuration's Extractor call under ncu
+python tools/bwd_cell_check.py --mode sorted --variants B,S,T,L,L64 --dtypes f32,bf16 --out gpurun_out/bwd_sorted_vs_query_order.jsonl > gpurun_out/bwd_sorted.log 2>&1
+for b in 1 2 4; do python tools/bwd_cell_check.py --mode sorted --variants B,S --dtypes f32,bf16 --batch $b --out gpurun_out/bwd_sorted_b$b.jsonl >> gpurun_out/bwd_sorted.log 2>&1; done
+python tools/profile_step.py > gpurun_out/plain.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:sort -s 5 -c 5 -o gpurun_out/prof_sorted python tools/profile_step.py --warm 1 > gpurun_out/ncu_full.log 2>&1
+for v in L L64; do python tools/profile_step.py --variant $v --dtype bf16 > gpurun_out/plain.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:msda_ -s 13 -c 13 -o gpurun_out/prof_${v}_bf16 python tools/profile_step.py --variant $v --dtype bf16 --warm 1 > gpurun_out/ncu_full.log 2>&1; done
 ls -la gpurun_out
 python tools/profile_adapter_kernels.py > gpurun_out/plain_adapter.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:adapter_ -s 20 -c 10 -o gpurun_out/prof_adapter python tools/profile_adapter_kernels.py > gpurun_out/ncu_adapter.log 2>&1
