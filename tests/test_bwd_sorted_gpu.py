@@ -207,3 +207,45 @@ def _sorted_in_a_graph(g):
     torch.cuda.synchronize()
     for a, b in zip(out, eager):
         torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-4 * _scale(b))
+
+
+@pytest.mark.parametrize('cfg', [CASES[0], CASES[1], CASES[5], CASES[8]], ids=[CASES[i][0] for i in (0, 1, 5, 8)])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['f32', 'bf16'])
+def test_sorted_backward_stays_inside_its_buffers(cfg, dtype):
+    """Every buffer the sorted backward writes - grad_value, grad_sampling_loc, grad_attn_weight and the workspace (fp32
+    accumulator, histograms, scan totals, sorted indices) - sits between two guard bands filled with a pattern; the call must
+    leave the bands untouched (compute-sanitizer is not available on the GPU pool, so the ABI is called with guarded memory)."""
+    import ctypes
+    _, N, M, D, Lq, shapes, P, dist = cfg
+    inp = make_inputs(N, M, D, Lq, shapes, P, seed=31, dist=dist)
+    g = {k: v.to(DEV) for k, v in inp.items()}
+    value, go = g['value'].to(dtype).contiguous(), g['grad_out'].to(dtype).contiguous()
+    lib = _cabi.load()
+    dims = _cabi._dims(value, g['shapes'], g['loc'])
+    code = _cabi._DTYPES[dtype]
+    GUARD = 4096
+
+    def guarded(nbytes):
+        buf = torch.full((nbytes + 2 * GUARD,), 0xA5, dtype=torch.uint8, device=DEV)
+        return buf, buf.data_ptr() + GUARD
+
+    _cabi.set_tuning(bwd_sorted=2)
+    try:
+        ws_bytes = lib.msda_backward_workspace_bytes(ctypes.byref(dims), code)
+        assert ws_bytes > 0
+        bufs = {name: guarded(n) for name, n in (('gv', value.numel() * value.element_size()), ('gl', g['loc'].numel() * 4),
+                                                 ('ga', g['aw'].numel() * 4), ('ws', ws_bytes))}
+        rc = lib.msda_backward(ctypes.byref(dims), code, value.data_ptr(), g['shapes'].data_ptr(), g['lsi'].data_ptr(),
+                               g['loc'].data_ptr(), g['aw'].data_ptr(), go.data_ptr(), bufs['gv'][1], bufs['gl'][1], bufs['ga'][1],
+                               bufs['ws'][1], ws_bytes, torch.cuda.current_stream().cuda_stream)
+        assert rc == 0, lib.msda_last_error()
+        torch.cuda.synchronize()
+    finally:
+        _cabi.set_tuning(bwd_sorted=0)
+    for name, (buf, _) in bufs.items():
+        assert bool((buf[:GUARD] == 0xA5).all()) and bool((buf[-GUARD:] == 0xA5).all()), 'guard band of %s was written' % name
+    # and the guarded outputs are the right answer
+    gv = bufs['gv'][0][GUARD:-GUARD].view(dtype).view_as(value).float().cpu()
+    wgv, _, _ = c_oracle.backward(value.float().cpu(), inp['shapes'], inp['lsi'], inp['loc'], inp['aw'], go.float().cpu())
+    tol = 1e-4 if dtype == torch.float32 else 1e-2
+    torch.testing.assert_close(gv, wgv, rtol=tol, atol=tol * _scale(wgv))
