@@ -121,13 +121,13 @@ def test_sorted_backward_vs_reference_cuda(cfg):
 
 
 def test_sorted_backward_selection():
-    """Without tuning the sorted backward (5 kernels: histogram, 2 x scan, scatter, walk) runs where it measured faster - one
+    """Without tuning the sorted backward (4 kernels: histogram, prefix, scatter, walk) runs where it measured faster - one
     level with >= 16 samples per value token and head, and >= 0.5 M samples at 64 channels per head / >= 1 M at 32 - and the
     one-kernel query-order backward elsewhere; bwd_sorted=2 / 1 force one or the other. They agree to summation order."""
     big64 = make_inputs(4, 6, 64, 5376, [(32, 32)], 4, seed=16, dist='adapter')      # ViT-Adapter-S Extractor, 4 images: 516 k samples
     n0 = _cabi.launch_count()
     gv, gl, ga = _bwd(big64, torch.float32)
-    assert _cabi.launch_count() - n0 == 5
+    assert _cabi.launch_count() - n0 == 4
     n0 = _cabi.launch_count()
     ogv, ogl, oga = _bwd(big64, torch.float32, bwd_sorted=1)
     assert _cabi.launch_count() - n0 == 1
@@ -142,7 +142,7 @@ def test_sorted_backward_selection():
         assert _cabi.launch_count() - n0 == 1
         n0 = _cabi.launch_count()
         _bwd(inp, torch.float32, bwd_sorted=2)
-        assert _cabi.launch_count() - n0 == 5
+        assert _cabi.launch_count() - n0 == 4
     # a head dimension outside {32, 64} has no sorted kernel: one launch whatever the knob says
     inp = make_inputs(1, 2, 16, 50, [(6, 6)], 4, seed=17, dist='uniform')
     n0 = _cabi.launch_count()
@@ -201,7 +201,7 @@ def _sorted_in_a_graph(g):
         n0 = _cabi.launch_count()
         with torch.cuda.graph(graph, stream=s):
             out = _cabi.backward(g['value'], g['shapes'], g['lsi'], g['loc'], g['aw'], g['grad_out'], 64)
-        assert _cabi.launch_count() - n0 == 5   # the sorted path was the one captured
+        assert _cabi.launch_count() - n0 == 4   # the sorted path was the one captured
     for _ in range(2):
         graph.replay()
     torch.cuda.synchronize()

@@ -13,7 +13,8 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libmsda_b200.so')
+# (MSDA_B200_LIB names another build of the same library: A/B timing of kernel variants, tools/walker_variants.sh)
+LIB_PATH = os.environ.get('MSDA_B200_LIB') or os.path.join(_HERE, 'lib', 'libmsda_b200.so')
 
 MSDA_F32, MSDA_BF16, MSDA_F64 = 0, 1, 2
 MSDA_F16 = 3

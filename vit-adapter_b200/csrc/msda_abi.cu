@@ -403,7 +403,7 @@ static size_t accum_workspace_bytes(const msda_dims* d, int dtype) {
 }
 // Slab-sorted backward (msda_bwd_sorted.cu). Tuning key "bwd_sorted": 0 = where it measured faster, 1 = off, 2 = wherever it
 // applies. MEASURED (profiles/r2_bwd_sorted_vs_query_order.jsonl and r2_bwd_sorted_small_batches.jsonl, B200, L2 flushed,
-// query order -> sorted): the sort costs ~45 us per 4 M samples plus five launches, the walker ~26 instructions per sample
+// query order -> sorted): the sort costs ~45 us per 4 M samples plus four launches, the walker ~26 instructions per sample
 // whatever the row length, so it pays where cell runs are long (one level, >= 16 samples per value token and head: the
 // Extractor calls) and the call is large enough for the launches: from ~1 M samples at 128-byte rows (D = 32), ~0.5 M at
 // 256-byte rows (D = 64), whose row atomics cost twice as much in query order:

@@ -34,9 +34,8 @@ namespace msda {
 
 // Workspace carved by the host (launch_backward_sorted below); all pointers are device pointers into it.
 struct SortedPlan {
-  unsigned* cnt;  // [N*M][parts][S] histograms of clamped top-left tokens -> exclusive scan -> the parts' first positions
+  unsigned* cnt;  // [N*M][parts][S] histograms of clamped top-left tokens -> per key, the exclusive prefix over the parts
   unsigned* tot;  // [N*M][S]   per key, the samples of all parts
-  unsigned* chunk_sum;  // [N*M][ceil(S / 256)] per chunk of 256 keys, its samples
   unsigned* nin;  // [N*M]      samples of the slab that pass the bounds test
   unsigned* idx;  // [N*M][cap] the slab's samples in cell order: query * L*P + point
   int cap;        // Lq * L * P: samples per slab
@@ -57,11 +56,12 @@ struct SortedPlan {
 // A slab is cut into sp.parts PARTS of consecutive queries so that the grid covers every SM several times over (192 slabs on
 // 148 SMs would otherwise run as two waves). Three kernels:
 //   hist    CTA (slab, part): histogram of the part's samples in shared memory (integer ATOMS), stored to cnt[slab][part][S]
-//   scan    two kernels over (slab, 256 keys): exclusive scan of cnt in (key, part) order, in place; nin[slab] = samples in range
-//   scatter CTA (slab, part): its row of cnt becomes the cursors in shared memory; every sample takes its position with one
-//           ATOMS and writes its 4-byte index there (a first version wrote 20-byte records - fractions, weight, cell word -
-//           to those random positions: 75 us instead of 23 us at ViT-Adapter-B bs 16; the walker now gathers location and
-//           weight by index and redoes the geometry)
+//   prefix  CTA (slab, 32 keys): per key, the exclusive prefix of cnt over the parts (in place) and the total -> tot[slab][S]
+//   scatter CTA (slab, part): scans tot[slab] over the keys in shared memory (12.5 KB at ViT-Adapter-L; every CTA of the slab
+//           repeats it - cheaper than a kernel of its own) and adds its row of cnt: the cursors of (part, key); every sample
+//           takes its position with one ATOMS and writes its 4-byte index there (a first version wrote 20-byte records -
+//           fractions, weight, cell word - to those random positions: 75 us instead of 23 us at ViT-Adapter-B bs 16; the
+//           walker now gathers location and weight by index and redoes the geometry)
 constexpr int kSortThreads = 256;
 constexpr int kSortUnroll = 4;
 
@@ -78,15 +78,39 @@ __global__ void __launch_bounds__(kSortThreads) msda_sort_part_kernel(const Para
   const int b = slab / p.M, m = slab - b * p.M;
   const int S = p.S;
   unsigned* __restrict__ gcnt = sp.cnt + ((size_t)slab * sp.parts + part) * S;
-  if constexpr (SCATTER) {
-    for (int i = tid; i < S; i += kSortThreads) s_cnt[i] = gcnt[i];
-  } else {
-    for (int i = tid; i < S; i += kSortThreads) s_cnt[i] = 0u;
-  }
   if (tid < L) {
     s_H[tid] = (int)p.shapes[2 * tid];
     s_W[tid] = (int)p.shapes[2 * tid + 1];
     s_start[tid] = (int)p.lsi[tid];
+  }
+  if constexpr (SCATTER) {
+    // cursors: first position of (key, this part) = samples of the slab's smaller keys + samples of this key in earlier parts.
+    // Thread t scans keys [t * run, (t + 1) * run) of tot[slab] straight from global memory (the second read hits L1).
+    __shared__ unsigned s_warp[kSortThreads / 32];
+    const unsigned* __restrict__ tot = sp.tot + (size_t)slab * S;
+    const int run = (S + kSortThreads - 1) / kSortThreads;
+    const int k0 = min(S, tid * run), k1 = min(S, k0 + run);
+    unsigned sum = 0;
+    for (int i = k0; i < k1; ++i) sum += tot[i];
+    unsigned incl = sum;
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    unsigned before = incl - sum;
+#pragma unroll
+    for (int w = 0; w < kSortThreads / 32; ++w) before += w < warp ? s_warp[w] : 0u;
+    if (part == 0 && tid == kSortThreads - 1) sp.nin[slab] = before + sum;
+    for (int i = k0; i < k1; ++i) {
+      s_cnt[i] = before + gcnt[i];
+      before += tot[i];
+    }
+  } else {
+    for (int i = tid; i < S; i += kSortThreads) s_cnt[i] = 0u;
   }
   __syncthreads();
   const size_t pair0 = ((size_t)b * p.Lq * p.M + (size_t)m) * LP;  // (b, query 0, m, point 0)
@@ -135,86 +159,45 @@ __global__ void __launch_bounds__(kSortThreads) msda_sort_part_kernel(const Para
   }
 }
 
-// exclusive scan of cnt[slab][part][key] in (key, part) order, two kernels over (slab, chunk of kScanKeys keys) so that calls
-// with few slabs still fill the GPU (one CTA per slab took 31-40 us at ViT-Adapter-L bs 1: 16 CTAs reading 7 MB):
-//   totals  per key, the sum over the parts -> tot[slab][key]; per chunk, the sum of its keys -> chunk_sum[slab][chunk]
-//   bases   the chunk's first position (sum of the chunk sums before it), a block scan of its totals, and a sweep that
-//           hands every (part, key) its first position; the last chunk also writes nin[slab]
-// Every access is coalesced over the key; loads go out in batches of 8 parts.
-constexpr int kScanKeys = 256;
+// Per key, the exclusive prefix of cnt[slab][part][key] over the parts (in place) and the total of the key -> tot[slab][key].
+// CTA (slab, 32 keys): lane = key, warp = a group of up to 8 consecutive parts, so that a warp access covers 32 consecutive
+// keys of one part and a thread's loads all go out at once. (The first version scanned in (key, part) order with two
+// kernels over (slab, 256 keys) whose threads walked the parts eight at a time: 9 + 17 us at ViT-Adapter-L bs 1 - 37 parts of
+// 3 136 keys per slab -, against 8.6 us for the histogram itself.)
+constexpr int kPrefixKeys = 32, kPrefixGroups = 8, kMaxParts = 64;
 
-__device__ __forceinline__ unsigned block_sum_256(unsigned v, unsigned* s_w) {  // all 256 threads; returns the total
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+__global__ void __launch_bounds__(kPrefixKeys * kPrefixGroups) msda_sort_prefix_kernel(const SortedPlan sp, int S) {
+  __shared__ unsigned s_g[kPrefixGroups][kPrefixKeys];
+  const int slab = blockIdx.y, lane = threadIdx.x & 31, grp = threadIdx.x >> 5, parts = sp.parts;
+  const int groups = (int)(blockDim.x >> 5);                     // min(kPrefixGroups, parts)
+  const int key = blockIdx.x * kPrefixKeys + lane;
+  const int per = (parts + groups - 1) / groups;                 // parts per group, <= 8
+  const int p0 = grp * per;
+  unsigned* __restrict__ c = sp.cnt + ((size_t)slab * parts + p0) * S + key;
+  unsigned x[kMaxParts / kPrefixGroups];
 #pragma unroll
-  for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-  __syncthreads();
-  if (lane == 0) s_w[warp] = v;
-  __syncthreads();
-  unsigned t = 0;
-#pragma unroll
-  for (int w = 0; w < kScanKeys / 32; ++w) t += s_w[w];
-  return t;
-}
-
-__global__ void __launch_bounds__(kScanKeys) msda_sort_totals_kernel(const SortedPlan sp, int S) {
-  __shared__ unsigned s_w[kScanKeys / 32];
-  const int slab = blockIdx.y, chunk = blockIdx.x, parts = sp.parts;
-  const unsigned* __restrict__ c = sp.cnt + (size_t)slab * parts * S;
-  const int i = chunk * kScanKeys + threadIdx.x;
+  for (int k = 0; k < kMaxParts / kPrefixGroups; ++k) x[k] = (key < S && k < per && p0 + k < parts) ? c[(size_t)k * S] : 0u;
   unsigned sum = 0;
-  if (i < S) {
-    for (int r0 = 0; r0 < parts; r0 += 8) {
-      unsigned v[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = r0 + k < parts ? c[(size_t)(r0 + k) * S + i] : 0u;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) sum += v[k];
-    }
-    sp.tot[(size_t)slab * S + i] = sum;
+  for (int k = 0; k < kMaxParts / kPrefixGroups; ++k) {
+    const unsigned t = x[k];
+    x[k] = sum;
+    sum += t;
   }
-  const unsigned total = block_sum_256(sum, s_w);
-  if (threadIdx.x == 0) sp.chunk_sum[(size_t)slab * gridDim.x + chunk] = total;
-}
-
-__global__ void __launch_bounds__(kScanKeys) msda_sort_bases_kernel(const SortedPlan sp, int S) {
-  __shared__ unsigned s_w[kScanKeys / 32];
-  const int slab = blockIdx.y, chunk = blockIdx.x, parts = sp.parts, nchunks = gridDim.x;
-  unsigned* __restrict__ c = sp.cnt + (size_t)slab * parts * S;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // first position of this chunk
-  unsigned before = 0;
-  for (int k = threadIdx.x; k < chunk; k += kScanKeys) before += sp.chunk_sum[(size_t)slab * nchunks + k];
-  const unsigned offset = block_sum_256(before, s_w);
-  const int i = chunk * kScanKeys + threadIdx.x;
-  const unsigned v = i < S ? sp.tot[(size_t)slab * S + i] : 0u;
-  unsigned incl = v;
-#pragma unroll
-  for (int s = 1; s < 32; s <<= 1) {
-    const unsigned t = __shfl_up_sync(0xffffffffu, incl, s);
-    if (lane >= s) incl += t;
-  }
+  s_g[grp][lane] = sum;
   __syncthreads();
-  if (lane == 31) s_w[warp] = incl;
-  __syncthreads();
-  unsigned wbefore = 0, total = 0;
+  unsigned before = 0, total = 0;
 #pragma unroll
-  for (int w = 0; w < kScanKeys / 32; ++w) {
-    if (w < warp) wbefore += s_w[w];
-    total += s_w[w];
+  for (int g = 0; g < kPrefixGroups; ++g) {
+    const unsigned t = g < groups ? s_g[g][lane] : 0u;
+    before += g < grp ? t : 0u;
+    total += t;
   }
-  if (chunk == nchunks - 1 && threadIdx.x == 0) sp.nin[slab] = offset + total;
-  if (i < S) {
-    unsigned run = offset + wbefore + incl - v;
-    for (int r0 = 0; r0 < parts; r0 += 8) {
-      unsigned x[8];
+  if (key < S) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) x[k] = r0 + k < parts ? c[(size_t)(r0 + k) * S + i] : 0u;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        if (r0 + k < parts) c[(size_t)(r0 + k) * S + i] = run;
-        run += x[k];
-      }
-    }
+    for (int k = 0; k < kMaxParts / kPrefixGroups; ++k)
+      if (k < per && p0 + k < parts) c[(size_t)k * S] = before + x[k];
+    if (grp == 0) sp.tot[(size_t)slab * S + key] = total;
   }
 }
 #endif  // MSDA_TU == 0
@@ -579,7 +562,7 @@ static int sort_parts(size_t slabs, int Lq, int sm_count) {
 #define SORT_PARTS_PER_SM 4
 #endif
   long long parts = ((long long)SORT_PARTS_PER_SM * sm_count + (long long)slabs - 1) / (long long)slabs;
-  if (parts > 64) parts = 64;
+  if (parts > kMaxParts) parts = kMaxParts;
   while (parts > 1 && Lq / parts < 64) --parts;
   return (int)(parts < 1 ? 1 : parts);
 }
@@ -592,10 +575,9 @@ size_t backward_sorted_workspace_bytes(int N, int S, int M, int D, int L, int Lq
   const long long cap = (long long)Lq * L * P;
   if (cap * M >= (1ll << 31) || (long long)Lq * M * D * 4 >= (1ll << 31)) return 0;  // 32-bit in-image point / row offsets
   const size_t slabs = (size_t)N * M;
-  if (slabs > 65535) return 0;                         // the scan kernels put the slab in gridDim.y
+  if (slabs > 65535) return 0;                         // the prefix kernel puts the slab in gridDim.y
   const int parts = sort_parts(slabs, Lq, sm_count);
-  return align16(slabs * parts * S * 4) + align16(slabs * S * 4) + align16(slabs * ((S + 255) / 256) * 4) + align16(slabs * 4) +
-         align16(slabs * (size_t)cap * 4);
+  return align16(slabs * parts * S * 4) + align16(slabs * S * 4) + align16(slabs * 4) + align16(slabs * (size_t)cap * 4);
 }
 
 template <int LT, int PT>
@@ -610,10 +592,8 @@ static cudaError_t launch_sort(const Params& p, const SortedPlan& sp, cudaStream
   msda_sort_part_kernel<LT, PT, false><<<grid, kSortThreads, smem, s>>>(p, sp);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  const dim3 gscan((unsigned)((p.S + kScanKeys - 1) / kScanKeys), (unsigned)((size_t)p.N * p.M));
-  msda_sort_totals_kernel<<<gscan, kScanKeys, 0, s>>>(sp, p.S);
-  if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  msda_sort_bases_kernel<<<gscan, kScanKeys, 0, s>>>(sp, p.S);
+  const dim3 gprefix((unsigned)((p.S + kPrefixKeys - 1) / kPrefixKeys), (unsigned)((size_t)p.N * p.M));
+  msda_sort_prefix_kernel<<<gprefix, kPrefixKeys * (sp.parts < kPrefixGroups ? sp.parts : kPrefixGroups), 0, s>>>(sp, p.S);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   msda_sort_part_kernel<LT, PT, true><<<grid, kSortThreads, smem, s>>>(p, sp);
   return cudaGetLastError();
@@ -632,8 +612,6 @@ cudaError_t launch_backward_sorted(const Params& p, int dtype, void* ws, int sm_
   w += align16(slabs * sp.parts * p.S * 4);
   sp.tot = reinterpret_cast<unsigned*>(w);
   w += align16(slabs * p.S * 4);
-  sp.chunk_sum = reinterpret_cast<unsigned*>(w);
-  w += align16(slabs * ((p.S + 255) / 256) * 4);
   sp.nin = reinterpret_cast<unsigned*>(w);
   w += align16(slabs * 4);
   sp.idx = reinterpret_cast<unsigned*>(w);
@@ -656,7 +634,7 @@ cudaError_t launch_backward_sorted(const Params& p, int dtype, void* ws, int sm_
   else if (dtype == MSDA_BF16) e = bwd_sorted_bf16(p, sp, s);
   else if (dtype == MSDA_F16) e = bwd_sorted_f16(p, sp, s);
   else e = cudaErrorNotSupported;
-  if (e == cudaSuccess && launches) *launches = 5;
+  if (e == cudaSuccess && launches) *launches = 4;
   return e;
 }
 #endif  // MSDA_TU
