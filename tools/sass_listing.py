@@ -34,7 +34,8 @@ KERNELS = [
     ('bwd_sorted_walk_f32_L1', 'msda_bwd_sorted.o', r'msda_bwd_sorted_kernelIfLi8ELi1ELi4ELi3E', 'slab-sorted backward, walker fp32 D=32, Extractor (main loop = one batch of 32 samples)'),
     ('bwd_sorted_walk_bf16_d64_L1', 'msda_bwd_sorted_bf16.o', r'msda_bwd_sorted_kernelI13__nv_bfloat16Li16ELi1ELi4ELi3E', 'slab-sorted backward, walker bf16 D=64, Extractor (north-star 16 x 64)'),
     ('bwd_sorted_hist_L1', 'msda_bwd_sorted.o', r'msda_sort_part_kernelILi1ELi4ELb0E', 'slab-sorted backward, histogram pass of the counting sort'),
-    ('bwd_sorted_scatter_L1', 'msda_bwd_sorted.o', r'msda_sort_part_kernelILi1ELi4ELb1E', 'slab-sorted backward, scatter pass of the counting sort'),
+    ('bwd_sorted_prefix', 'msda_bwd_sorted.o', r'msda_sort_prefix_kernel', 'slab-sorted backward, per-key prefix over the parts of the counting sort'),
+    ('bwd_sorted_scatter_L1', 'msda_bwd_sorted.o', r'msda_sort_part_kernelILi1ELi4ELb1E', 'slab-sorted backward, scatter pass of the counting sort (key scan + cursors, then one ATOMS per sample)'),
 ]
 MNEMONICS = ['LDG.E.128', 'LDG.E.64', 'LDG.E ', 'LDGSTS', 'LDS', 'STS', 'REDG.E.ADD.F32x4', 'ATOMS', 'SHFL', 'FFMA2', 'FMUL2', 'FFMA ', 'FMUL ', 'FADD', 'IMAD.WIDE',
              'BAR.SYNC', 'STG']
