@@ -46,6 +46,8 @@ CASES = [
     ('p8-one-level', 2, 3, 64, 45, [(12, 10)], 8, 'edges'),
     ('tiny-map-many-points', 1, 2, 32, 700, [(2, 3)], 4, 'uniform'),   # ~470 points per cell: long runs, hot ATOMS keys
     ('wide-row', 1, 2, 32, 90, [(1, 40), (40, 1)], 4, 'edges'),
+    ('many-parts', 1, 2, 32, 4200, [(6, 7)], 4, 'uniform'),   # 2 slabs: the sort cuts each into 64 parts (8 per prefix group)
+    ('parts-not-multiple-of-groups', 1, 3, 64, 1300, [(9, 5), (4, 4)], 2, 'uniform'),   # 20 parts: groups of 3, the last two short
 ]
 
 
