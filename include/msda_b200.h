@@ -278,7 +278,7 @@ uint64_t msda_launch_count(void);
  *   "bwd_packed16"                  2 = bf16 / f16 backward with packed 16-bit reductions straight into grad_value (no fp32
  *                                   scratch, no convert kernel; every contribution rounded to 16 bits - looser numerics)
  *   "bwd_sorted"                    slab-sorted backward (msda_bwd_sorted.cu; D in {32, 64}): 0 = where it measured faster (one
- *                                   level, >= 16 samples per value token and head, and D = 64 or >= 2 M samples), 1 = never,
+ *                                   level, >= 16 samples per value token and head, and >= 1 M samples at D = 32 / >= 0.25 M at D = 64), 1 = never,
  *                                   2 = wherever it applies. Changes msda_backward_workspace_bytes().
  * Returns 0, or MSDA_E_NULL for an unknown key. */
 int msda_set_tuning(const char* key, int32_t value);

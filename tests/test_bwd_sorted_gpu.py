@@ -124,7 +124,7 @@ def test_sorted_backward_vs_reference_cuda(cfg):
 
 def test_sorted_backward_selection():
     """Without tuning the sorted backward (4 kernels: histogram, prefix, scatter, walk) runs where it measured faster - one
-    level with >= 16 samples per value token and head, and >= 0.5 M samples at 64 channels per head / >= 1 M at 32 - and the
+    level with >= 16 samples per value token and head, and >= 0.25 M samples at 64 channels per head / >= 1 M at 32 - and the
     one-kernel query-order backward elsewhere; bwd_sorted=2 / 1 force one or the other. They agree to summation order."""
     big64 = make_inputs(4, 6, 64, 5376, [(32, 32)], 4, seed=16, dist='adapter')      # ViT-Adapter-S Extractor, 4 images: 516 k samples
     n0 = _cabi.launch_count()

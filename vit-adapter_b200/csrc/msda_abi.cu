@@ -405,11 +405,12 @@ static size_t accum_workspace_bytes(const msda_dims* d, int dtype) {
 // applies. MEASURED (profiles/r2_bwd_sorted_vs_query_order.jsonl and r2_bwd_sorted_small_batches.jsonl, B200, L2 flushed,
 // query order -> sorted): the sort costs ~45 us per 4 M samples plus four launches, the walker ~26 instructions per sample
 // whatever the row length, so it pays where cell runs are long (one level, >= 16 samples per value token and head: the
-// Extractor calls) and the call is large enough for the launches: from ~1 M samples at 128-byte rows (D = 32), ~0.5 M at
+// Extractor calls) and the call is large enough for the launches: from ~1 M samples at 128-byte rows (D = 32), ~0.25 M at
 // 256-byte rows (D = 64), whose row atomics cost twice as much in query order:
 //   ViT-Adapter-B Extractor bs 16  322 -> 267 us fp32 (1.21x), 337 -> 277 bf16     S bs 16  331 -> 241 (1.37x), 337 -> 230 bf16 (1.46x)
 //   L 16x64 bs 1  196 -> 144 (1.35x), bf16 202 -> 136 (1.48x)     L 16x32 bs 1  105 -> 101, bf16 112 -> 105     T bs 16  1.09-1.11x
-//   B bs 4 (1.0 M samples) 1.04x, bs 2 0.97-1.0x, bs 1 0.71x       S bs 4 (0.5 M) 1.07-1.17x, bs 2 0.91-0.97x, bs 1 0.70x
+//   B bs 4 (1.0 M samples) 1.04-1.09x, bs 2 1.0-1.03x, bs 1 0.81-0.87x       S bs 4 (0.5 M) 1.19-1.32x, bs 2 (0.26 M) 1.11-1.19x, bs 1 0.90x
+//   (small batches re-measured after the sort's scan became one kernel: profiles/r2_bwd_sorted_small_batches.jsonl)
 // It loses on the Injectors (3 levels, ~2 samples per cell: 0.76-0.93x), which keep the query-order kernel.
 static size_t sorted_workspace_bytes(const msda_dims* d, int dtype) {
   const int mode = g_bwd_sorted.load();
@@ -420,7 +421,7 @@ static size_t sorted_workspace_bytes(const msda_dims* d, int dtype) {
     const long long samples_per_slab = (long long)d->num_query * d->num_levels * d->num_point;
     const long long samples = samples_per_slab * d->batch * d->num_heads;
     if (samples_per_slab < 16ll * d->spatial_size) return 0;
-    if (samples < (d->channels == 64 ? 500000ll : 1000000ll)) return 0;
+    if (samples < (d->channels == 64 ? 250000ll : 1000000ll)) return 0;
   }
   return backward_sorted_workspace_bytes(d->batch, d->spatial_size, d->num_heads, d->channels, d->num_levels, d->num_query,
                                          d->num_point, sm_count());
