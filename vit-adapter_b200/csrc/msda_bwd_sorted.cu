@@ -599,6 +599,14 @@ static cudaError_t launch_sort(const Params& p, const SortedPlan& sp, cudaStream
   return cudaGetLastError();
 }
 
+// Walker CTAs one SM holds: the launch bound, or fewer where the scratch of a CTA is large (fp32 rows of 64 channels: 2).
+static int walker_resident_ctas(int dtype, int D) {
+  const unsigned per_warp = dtype == MSDA_F32 ? (D == 64 ? WalkScratch<float, 16>::kBytes : WalkScratch<float, 8>::kBytes)
+                                              : (D == 64 ? WalkScratch<__half, 16>::kBytes : WalkScratch<__half, 8>::kBytes);
+  const int by_smem = (int)(228u * 1024u / (kWalkWarps * per_warp + 1024u + 256u));
+  return by_smem < 1 ? 1 : (by_smem < WALK_MINB ? by_smem : WALK_MINB);
+}
+
 // Counting sort + walk. `p.grad_value` must point at the zero-filled fp32 ACCUMULATOR (grad_value itself for f32, the scratch
 // for bf16 / f16); `ws` at backward_sorted_workspace_bytes() bytes, 16-byte aligned. `launches` counts kernel launches.
 cudaError_t launch_backward_sorted(const Params& p, int dtype, void* ws, int sm_count, int* launches, cudaStream_t s) {
@@ -616,12 +624,24 @@ cudaError_t launch_backward_sorted(const Params& p, int dtype, void* ws, int sm_
   w += align16(slabs * 4);
   sp.idx = reinterpret_cast<unsigned*>(w);
   sp.cap = (int)cap;
-  // positions per warp: as long as possible (every group flushes its last run when its range ends) while the grid still
-  // covers every SM several times over
-  sp.ppw = 32;
-  for (int ppw = 256; ppw >= 32; ppw >>= 1) {
-    const long long ctas = (long long)slabs * ((cap + (long long)kWalkWarps * ppw - 1) / ((long long)kWalkWarps * ppw));
-    if (ctas >= 6ll * sm_count || ppw == 32) { sp.ppw = ppw; break; }
+  // positions per warp: as long as possible (every group flushes its last run when its range ends) while the grid is at least
+  // two full rounds of resident CTAs and fills its last round: the largest multiple of 32 whose CTA count is >= 90 % (else
+  // >= 80 %) of a whole number of rounds; if none, the first of 256 / 128 / 64 / 32 with six CTAs per SM.
+  // (ViT-Adapter-S bs 16: 1 056 CTAs at 256 positions per warp are 2.4 rounds of 3 x 148, 1 632 at 160 are 3.7: 235 -> 224 us
+  // fp32, 208 -> 198 bf16; T 155 -> 149; B - 2 112 CTAs, 4.8 rounds - and L are unchanged: profiles/r2_walker_ppw_{old,new}.jsonl)
+  const long long round_ctas = (long long)walker_resident_ctas(dtype, p.D) * sm_count;
+  auto ctas_at = [&](int ppw) { return (long long)slabs * ((cap + (long long)kWalkWarps * ppw - 1) / ((long long)kWalkWarps * ppw)); };
+  sp.ppw = 0;
+  for (int pass = 0; pass < 2 && sp.ppw == 0; ++pass) {
+    for (int ppw = 256; ppw >= 32; ppw -= 32) {
+      const long long ctas = ctas_at(ppw), rounds = (ctas + round_ctas - 1) / round_ctas;
+      if (rounds >= 2 && ctas * 10 >= rounds * round_ctas * (pass == 0 ? 9 : 8)) { sp.ppw = ppw; break; }
+    }
+  }
+  if (sp.ppw == 0) {
+    sp.ppw = 32;
+    for (int ppw = 256; ppw >= 32; ppw >>= 1)
+      if (ctas_at(ppw) >= 6ll * sm_count) { sp.ppw = ppw; break; }
   }
   sp.ctas_per_slab = (int)((cap + (long long)kWalkWarps * sp.ppw - 1) / ((long long)kWalkWarps * sp.ppw));
 
