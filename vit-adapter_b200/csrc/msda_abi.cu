@@ -121,12 +121,21 @@ static int sm_count() {
   return n;
 }
 
-// queries per CTA chunk: enough CTAs to fill 148 SMs x ~8 resident CTAs, chunks as long as possible
-// otherwise (longer chunk = more L1 reuse of the value rows around neighbouring queries).
+// Queries per CTA chunk of the query-order kernels (a multiple of the queries one pass of the CTA serves). Two regimes,
+// MEASURED at every chunk size (tools/chunk_sweep.py, profiles/r2_chunk_sweep.jsonl; B / S / L, fp32 and bf16):
+//   dense calls (>= 8 samples per value token and head: the Extractors, 21): consecutive queries gather the same value rows,
+//     so long chunks keep them in L1 - ViT-Adapter-B Extractor forward 124 us at 256 queries per CTA, 140 at 64, 166 at 32:
+//     enough CTAs to fill the SMs ~8 times over, chunks as long as possible otherwise (<= 256);
+//   sparse calls (the Injectors, 2.3): nothing to reuse, and a CTA's time is proportional to its queries, so the shortest
+//     chunk gives the evenest last round - ViT-Adapter-B Injector, 1 024 queries x 192 slabs: 7 chunks of 160 (the last one 64
+//     long) were 1 344 CTAs = 3.03 rounds of 3 x 148 -> backward 239 us, 32 chunks of 32 are 13.8 rounds -> 226 us; S
+//     226 -> 216 us, forward 86 -> 80; L bs 1 forward 37.7 -> 32.8 us.
 static int pick_chunk(const msda_dims* d, int per_iter, int override_qc) {
   int qc;
   if (override_qc > 0) {
     qc = override_qc;
+  } else if ((int64_t)d->num_query * d->num_levels * d->num_point < 8 * (int64_t)d->spatial_size) {
+    qc = per_iter > 32 ? per_iter : 32;
   } else {
     const int64_t bm = (int64_t)d->batch * d->num_heads;
     const int64_t target_ctas = (int64_t)sm_count() * 8;
