@@ -240,7 +240,10 @@ static cudaError_t launch_vec_g(const Params& p, int minb, dim3 grid, cudaStream
   switch (minb) {
     case 3: return launch_vec_gm<T, G, 3>(p, grid, s);
     case 6: return launch_vec_gm<T, G, 6>(p, grid, s);
-    default: return launch_vec_gm<T, G, 4>(p, grid, s);
+    // measured (tools/minctas_sweep.py, profiles/r2_minctas_sweep.jsonl): fp32 is fastest compiled for 4 resident CTAs
+    // (64 registers), the 16-bit kernels - which also hold the unpacked rows - for 3 (80): Extractor forward bf16 B
+    // 101 -> 96 us, S 88 -> 85, L bs 1 35.6 -> 33.6; 6 CTAs (40 registers) lose 20 % at fp32
+    default: return launch_vec_gm<T, G, (sizeof(T) == 2 ? 3 : 4)>(p, grid, s);
   }
 }
 
