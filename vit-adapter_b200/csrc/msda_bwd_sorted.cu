@@ -39,7 +39,7 @@ struct SortedPlan {
   unsigned* nin;  // [N*M]      samples of the slab that pass the bounds test
   unsigned* idx;  // [N*M][cap] the slab's samples in cell order: query * L*P + point
   int cap;        // Lq * L * P: samples per slab
-  int ppw;        // sorted positions per warp of the walker (multiple of 32)
+  int ppw;        // sorted positions per warp of the walker (a multiple of 32)
   int ctas_per_slab;
   int parts;      // the sort cuts a slab into this many runs of consecutive queries
   int qpp;        // queries per part
@@ -57,7 +57,7 @@ struct SortedPlan {
 // 148 SMs would otherwise run as two waves). Three kernels:
 //   hist    CTA (slab, part): histogram of the part's samples in shared memory (integer ATOMS), stored to cnt[slab][part][S]
 //   prefix  CTA (slab, 32 keys): per key, the exclusive prefix of cnt over the parts (in place) and the total -> tot[slab][S]
-//   scatter CTA (slab, part): scans tot[slab] over the keys in shared memory (12.5 KB at ViT-Adapter-L; every CTA of the slab
+//   scatter CTA (slab, part): scans tot[slab] over the keys (12.5 KB at ViT-Adapter-L, read from L2; every CTA of the slab
 //           repeats it - cheaper than a kernel of its own) and adds its row of cnt: the cursors of (part, key); every sample
 //           takes its position with one ATOMS and writes its 4-byte index there (a first version wrote 20-byte records -
 //           fractions, weight, cell word - to those random positions: 75 us instead of 23 us at ViT-Adapter-B bs 16; the
@@ -556,7 +556,8 @@ cudaError_t bwd_sorted_f16(const Params& p, const SortedPlan& sp, cudaStream_t s
 #else
 static size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-// Parts per slab of the sort: enough CTAs for ~4 per SM, at most 64, at least 64 queries each.
+// Parts per slab of the sort: enough CTAs for ~4 per SM, at most 64, at least 64 queries each. (2 / 3 per SM measured slower;
+// picking the count that spreads the CTAs most evenly over the SMs - 6 parts instead of 4 at ViT-Adapter-B - measured the same.)
 static int sort_parts(size_t slabs, int Lq, int sm_count) {
 #ifndef SORT_PARTS_PER_SM
 #define SORT_PARTS_PER_SM 4
