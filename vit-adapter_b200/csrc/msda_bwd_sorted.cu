@@ -160,42 +160,48 @@ __global__ void __launch_bounds__(kSortThreads) msda_sort_part_kernel(const Para
 }
 
 // Per key, the exclusive prefix of cnt[slab][part][key] over the parts (in place) and the total of the key -> tot[slab][key].
-// CTA (slab, 32 keys): lane = key, warp = a group of up to 8 consecutive parts, so that a warp access covers 32 consecutive
-// keys of one part and a thread's loads all go out at once. (The first version scanned in (key, part) order with two
-// kernels over (slab, 256 keys) whose threads walked the parts eight at a time: 9 + 17 us at ViT-Adapter-L bs 1 - 37 parts of
-// 3 136 keys per slab -, against 8.6 us for the histogram itself.)
-constexpr int kPrefixKeys = 32, kPrefixGroups = 8, kMaxParts = 64;
+// A CTA of 256 threads serves (slab, 256 / groups consecutive keys); a thread owns one key and a group of up to 8 consecutive
+// parts, so that a warp access covers 32 consecutive keys of one part and a thread's loads all go out at once; groups =
+// 1 / 2 / 4 / 8 for up to 8 / 16 / 32 / 64 parts (ViT-Adapter-B bs 16: 4 parts, 256 keys per CTA, 768 CTAs; L bs 1: 37 parts,
+// 32 keys per CTA). (The first version scanned in (key, part) order with two kernels over (slab, 256 keys) whose threads
+// walked the parts eight at a time: 9 + 17 us at ViT-Adapter-L bs 1 - 37 parts of 3 136 keys per slab -, against 8.6 us for
+// the histogram itself.)
+constexpr int kPrefixThreads = 256, kPrefixPer = 8, kMaxParts = 64;
+static int prefix_groups(int parts) { return parts <= 8 ? 1 : parts <= 16 ? 2 : parts <= 32 ? 4 : 8; }
 
-__global__ void __launch_bounds__(kPrefixKeys * kPrefixGroups) msda_sort_prefix_kernel(const SortedPlan sp, int S) {
-  __shared__ unsigned s_g[kPrefixGroups][kPrefixKeys];
-  const int slab = blockIdx.y, lane = threadIdx.x & 31, grp = threadIdx.x >> 5, parts = sp.parts;
-  const int groups = (int)(blockDim.x >> 5);                     // min(kPrefixGroups, parts)
-  const int key = blockIdx.x * kPrefixKeys + lane;
-  const int per = (parts + groups - 1) / groups;                 // parts per group, <= 8
+__global__ void __launch_bounds__(kPrefixThreads) msda_sort_prefix_kernel(const SortedPlan sp, int S, int groups) {
+  __shared__ unsigned s_g[kPrefixThreads];          // [groups][keys per CTA]
+  const int slab = blockIdx.y, parts = sp.parts;
+  const int kpc = kPrefixThreads / groups;          // keys per CTA: a multiple of 32, so a warp has one group
+  const int grp = (int)threadIdx.x / kpc, kl = (int)threadIdx.x - grp * kpc;
+  const int key = blockIdx.x * kpc + kl;
+  const int per = (parts + groups - 1) / groups;    // parts per group, <= 8
   const int p0 = grp * per;
   unsigned* __restrict__ c = sp.cnt + ((size_t)slab * parts + p0) * S + key;
-  unsigned x[kMaxParts / kPrefixGroups];
+  unsigned x[kPrefixPer];
 #pragma unroll
-  for (int k = 0; k < kMaxParts / kPrefixGroups; ++k) x[k] = (key < S && k < per && p0 + k < parts) ? c[(size_t)k * S] : 0u;
+  for (int k = 0; k < kPrefixPer; ++k) x[k] = (key < S && k < per && p0 + k < parts) ? c[(size_t)k * S] : 0u;
   unsigned sum = 0;
 #pragma unroll
-  for (int k = 0; k < kMaxParts / kPrefixGroups; ++k) {
+  for (int k = 0; k < kPrefixPer; ++k) {
     const unsigned t = x[k];
     x[k] = sum;
     sum += t;
   }
-  s_g[grp][lane] = sum;
-  __syncthreads();
-  unsigned before = 0, total = 0;
-#pragma unroll
-  for (int g = 0; g < kPrefixGroups; ++g) {
-    const unsigned t = g < groups ? s_g[g][lane] : 0u;
-    before += g < grp ? t : 0u;
-    total += t;
+  unsigned before = 0, total = sum;
+  if (groups > 1) {                                  // uniform
+    s_g[threadIdx.x] = sum;
+    __syncthreads();
+    total = 0;
+    for (int g = 0; g < groups; ++g) {
+      const unsigned t = s_g[g * kpc + kl];
+      before += g < grp ? t : 0u;
+      total += t;
+    }
   }
   if (key < S) {
 #pragma unroll
-    for (int k = 0; k < kMaxParts / kPrefixGroups; ++k)
+    for (int k = 0; k < kPrefixPer; ++k)
       if (k < per && p0 + k < parts) c[(size_t)k * S] = before + x[k];
     if (grp == 0) sp.tot[(size_t)slab * S + key] = total;
   }
@@ -593,8 +599,9 @@ static cudaError_t launch_sort(const Params& p, const SortedPlan& sp, cudaStream
   msda_sort_part_kernel<LT, PT, false><<<grid, kSortThreads, smem, s>>>(p, sp);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  const dim3 gprefix((unsigned)((p.S + kPrefixKeys - 1) / kPrefixKeys), (unsigned)((size_t)p.N * p.M));
-  msda_sort_prefix_kernel<<<gprefix, kPrefixKeys * (sp.parts < kPrefixGroups ? sp.parts : kPrefixGroups), 0, s>>>(sp, p.S);
+  const int groups = prefix_groups(sp.parts), kpc = kPrefixThreads / groups;
+  const dim3 gprefix((unsigned)((p.S + kpc - 1) / kpc), (unsigned)((size_t)p.N * p.M));
+  msda_sort_prefix_kernel<<<gprefix, kPrefixThreads, 0, s>>>(sp, p.S, groups);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   msda_sort_part_kernel<LT, PT, true><<<grid, kSortThreads, smem, s>>>(p, sp);
   return cudaGetLastError();
