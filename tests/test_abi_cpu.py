@@ -73,6 +73,18 @@ def test_missing_library_fails_loudly(monkeypatch):
         _cabi.load()
 
 
+def test_library_override_from_the_environment_fails_loudly_too():
+    """MSDA_B200_LIB (A/B timing of kernel variants, tools/walker_variants.sh) names another build of the library; a path that
+    does not exist is an error, not a silent return to the default build."""
+    import subprocess
+    import sys
+    env = dict(os.environ, MSDA_B200_LIB='/nonexistent/libmsda_b200.so')
+    code = ('import sys; sys.path.insert(0, %r)\nimport vit_adapter_b200 as vab\n'
+            'try:\n    vab._cabi.load()\nexcept RuntimeError as e:\n    print("RAISED", e)\n' % ROOT)
+    out = subprocess.run([sys.executable, '-c', code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300).stdout
+    assert 'RAISED' in out and '/nonexistent/libmsda_b200.so' in out, out
+
+
 def test_product_path_never_touches_the_oracle():
     """oracle/ is test infrastructure: nothing under vit-adapter_b200/ or include/ may reference it."""
     pkg = os.path.join(ROOT, 'vit-adapter_b200')
