@@ -788,7 +788,7 @@ cudaError_t launch_dwconv_wgrad(const DwParams& p, int dtype, const void* grad_y
   if (e != cudaSuccess) return e;
   const dim3 block(32, 8);
   const size_t bt_total = (size_t)p.B * p.Ntok;
-  int ctas_x = 148 * 2;
+  int ctas_x = device_sm_count() * 2;
   int tokens_per_cta = (int)((bt_total + ctas_x - 1) / ctas_x);
   if (tokens_per_cta < 64) tokens_per_cta = 64;
   ctas_x = (int)((bt_total + tokens_per_cta - 1) / tokens_per_cta);

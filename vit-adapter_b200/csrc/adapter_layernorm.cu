@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(1024) adapter_ln_param_grad_kernel(const float
 
 static unsigned ln_grid(long long rows) {
   const long long need = (rows + kLnWarps - 1) / kLnWarps;
-  const long long resident = 148 * 2;
+  const long long resident = device_sm_count() * 2;
   return (unsigned)(need < resident ? (need ? need : 1) : resident);
 }
 

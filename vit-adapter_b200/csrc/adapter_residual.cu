@@ -47,7 +47,8 @@ __global__ void __launch_bounds__(256) adapter_residual_add_kernel(const float* 
 cudaError_t launch_residual_add(int branch_dtype, const float* res, const void* branch, float* out, long long n, cudaStream_t s) {
   const long long n8 = n / 8;
   long long blocks = (n8 + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  const long long cap = (long long)device_sm_count() * 16;
+  if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   if (branch_dtype == MSDA_BF16)
     adapter_residual_add_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, s>>>(res, reinterpret_cast<const __nv_bfloat16*>(branch), out, n8);

@@ -108,18 +108,7 @@ static int check_dims(const msda_dims* d, int dtype) {
 
 static bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
-// SMs of the current device (cudaDevAttrMultiProcessorCount, cached per device ordinal).
-static int sm_count() {
-  static std::atomic<int> cache[64];
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
-  int n = cache[dev].load();
-  if (n == 0) {
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    cache[dev].store(n);
-  }
-  return n;
-}
+static int sm_count() { return device_sm_count(); }
 
 // Queries per CTA chunk of the query-order kernels (a multiple of the queries one pass of the CTA serves). Two regimes,
 // MEASURED at every chunk size (tools/chunk_sweep.py, profiles/r2_chunk_sweep.jsonl; B / S / L, fp32 and bf16):
@@ -211,13 +200,13 @@ static bool plan_forward_smem(const msda_dims* d, int dtype, int G, const int64_
   const double bm = (double)d->batch * d->num_heads;
   const double g_smem = (double)d->num_query * nstaged * d->num_point * 4.0 * rowB;        // per (b,m), bytes
   const double g_l1 = (double)d->num_query * (L - nstaged) * d->num_point * 4.0 * rowB;
-  const double t_l1_only = (g_smem + g_l1) / 62.0 * ceil(bm / 148.0 / 4.0) ;  // rough; only the ratio below matters
+  const double t_l1_only = (g_smem + g_l1) / 62.0 * ceil(bm / (double)sm_count() / 4.0) ;  // rough; only the ratio below matters
   (void)t_l1_only;
   int best_c = 0;
   double best_t = 1e300;
   const int max_c = d->num_query / per_iter > 0 ? d->num_query / per_iter : 1;
   for (int c = 1; c <= 64 && c <= max_c; ++c) {
-    const double waves = ceil(bm * c / 148.0);
+    const double waves = ceil(bm * c / (double)sm_count());
     const double per_cta = (g_smem / 245.0 + g_l1 / 62.0) / c + (double)total / 80.0;
     const double t = waves * per_cta;
     if (t < best_t) { best_t = t; best_c = c; }

@@ -13,9 +13,25 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/msda_b200.h"
 
 namespace msda {
+
+// SMs of the current device (cudaDevAttrMultiProcessorCount, cached per device ordinal; 148 - a B200 - if the query fails).
+// Host side: the launchers size persistent grids and CTA chunks with it.
+inline int device_sm_count() {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int n = cache[dev].load();
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev].store(n);
+  }
+  return n;
+}
 
 constexpr int kThreads = 256;            // threads per CTA for every kernel in this library
 constexpr int kWarps = kThreads / 32;
