@@ -150,3 +150,15 @@ def test_backward_workspace_sizes_follow_the_kernel_selection():
         assert ws(1, 256, 6, 48, 1, 1344, 4, F32) == 0                 # no sorted kernel for this head width
     finally:
         _cabi.set_tuning(bwd_sorted=0)
+
+
+def test_traffic_file_covers_the_bench_line_and_the_north_star_block():
+    """bench.py reads `roofline.traffic` (ncu DRAM bytes per launch) from profiles/traffic.json under
+    <variant>_<dtype>_<call>_<fwd|bwd>: the headline workload and both north-star configurations must be there."""
+    import json
+    t = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
+    for variant, dtype in (('B', 'f32'), ('L', 'bf16'), ('L64', 'bf16')):
+        for call in ('injector', 'extractor'):
+            for d in ('fwd', 'bwd'):
+                key = '%s_%s_%s_%s' % (variant, dtype, call, d)
+                assert key in t and float(t[key]) > 1e6, key
